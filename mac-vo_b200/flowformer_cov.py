@@ -1,0 +1,571 @@
+"""FlowFormerCov frontend network — host-side PyTorch plumbing around the two hot-path kernels.
+
+This is a from-scratch, weight-compatible (same `state_dict` keys) functional
+re-implementation of the reference network
+
+    Module/Network/FlowFormerCov/flownet.py:18-44      (forward / inference)
+    Module/Network/FlowFormer/core/twins_svt.py:19-37   (Twins-SVT-L, 2 stages)
+    Module/Network/FlowFormer/core/encoder.py:12-295    (PatchEmbed, cost perceiver, MemoryEncoder)
+    Module/Network/FlowFormer/core/twins.py:22-243      (context-conditioned Twins blocks)
+    Module/Network/FlowFormerCov/covhead.py:60-140      (12-iteration flow + covariance decoder)
+    Module/Network/FlowFormer/core/gma.py, gru.py, attention.py
+
+The dense layers go through torch (cuDNN / cuBLAS) exactly as in the reference; the two operators
+`BASELINE.json: north_star` names are NOT torch ops here:
+
+* `corr_fn(f1, f2) -> (B, 1, H1, W1, H1, W1)`   all-pairs correlation volume (encoder.py:256-275)
+* `lookup_fn(cost_maps, coords) -> (B, 81, H1, W1)`  9x9 window lookup (decoder.py:141-153)
+
+By default both bind to the sm_100a CUDA kernels behind the C-ABI (`ops.corr_build`, `ops.corr_lookup`)
+and fail loudly when the library / a GPU is missing. Tests inject the CPU oracle instead.
+
+Restructuring relative to the reference (same arithmetic per output, fewer launches / bytes):
+* weights live in a flat dict keyed by the checkpoint names, the forward pass is functional;
+* eval mode only returns the last prediction, so the convex upsampling and both 576-channel mask
+  heads run once (after the last refinement) instead of 12 times;
+* z and r gates of each separable GRU share their input -> one conv with concatenated filters;
+* sine position encodings that do not depend on the input are built once per resolution.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from typing import Callable
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+# cfg constants: Module/Network/FlowFormer/configs/submission.py:16-32
+LATENT_TOKENS = 8
+LATENT_DIM = 128
+QUERY_DIM = 64
+COST_INPUT_DIM = 64
+VERT_C_DIM = 64
+ENCODER_DEPTH = 3
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter table (name -> shape, init kind); keys equal the reference checkpoint's
+# ----------------------------------------------------------------------------------------------
+def _svt_spec(prefix: str) -> list[tuple[str, tuple[int, ...], str]]:
+    out: list[tuple[str, tuple[int, ...], str]] = []
+    dims, heads, srs, patch, cin = (128, 256), (4, 8), (8, 4), (4, 2), (3, 128)
+    for s, (C, sr, ps, ci) in enumerate(zip(dims, srs, patch, cin)):
+        p = f"{prefix}.svt."
+        out += [(p + f"patch_embeds.{s}.proj.weight", (C, ci, ps, ps), "w"), (p + f"patch_embeds.{s}.proj.bias", (C,), "b"),
+                (p + f"patch_embeds.{s}.norm.weight", (C,), "one"), (p + f"patch_embeds.{s}.norm.bias", (C,), "zero")]
+        for j in range(2):
+            b = p + f"blocks.{s}.{j}."
+            out += [(b + "norm1.weight", (C,), "one"), (b + "norm1.bias", (C,), "zero")]
+            if j == 0:
+                out += [(b + "attn.qkv.weight", (3 * C, C), "w"), (b + "attn.qkv.bias", (3 * C,), "b")]
+            else:
+                out += [(b + "attn.q.weight", (C, C), "w"), (b + "attn.q.bias", (C,), "b"),
+                        (b + "attn.kv.weight", (2 * C, C), "w"), (b + "attn.kv.bias", (2 * C,), "b")]
+            out += [(b + "attn.proj.weight", (C, C), "w"), (b + "attn.proj.bias", (C,), "b")]
+            if j == 1:
+                out += [(b + "attn.sr.weight", (C, C, sr, sr), "w"), (b + "attn.sr.bias", (C,), "b"),
+                        (b + "attn.norm.weight", (C,), "one"), (b + "attn.norm.bias", (C,), "zero")]
+            out += [(b + "norm2.weight", (C,), "one"), (b + "norm2.bias", (C,), "zero"),
+                    (b + "mlp.fc1.weight", (4 * C, C), "w"), (b + "mlp.fc1.bias", (4 * C,), "b"),
+                    (b + "mlp.fc2.weight", (C, 4 * C), "w"), (b + "mlp.fc2.bias", (C,), "b")]
+        out += [(p + f"pos_block.{s}.proj.0.weight", (C, 1, 3, 3), "w"), (p + f"pos_block.{s}.proj.0.bias", (C,), "b")]
+    return out
+
+
+def _attn_layer_spec(p: str, qdim: int, tdim: int, proj_in: int) -> list[tuple[str, tuple[int, ...], str]]:
+    return [(p + "norm1.weight", (qdim,), "one"), (p + "norm1.bias", (qdim,), "zero"),
+            (p + "norm2.weight", (qdim,), "one"), (p + "norm2.bias", (qdim,), "zero"),
+            (p + "q.weight", (qdim, qdim), "w"), (p + "q.bias", (qdim,), "b"),
+            (p + "k.weight", (qdim, tdim), "w"), (p + "k.bias", (qdim,), "b"),
+            (p + "v.weight", (qdim, tdim), "w"), (p + "v.bias", (qdim,), "b"),
+            (p + "proj.weight", (qdim, proj_in), "w"), (p + "proj.bias", (qdim,), "b"),
+            (p + "ffn.0.weight", (qdim, qdim), "w"), (p + "ffn.0.bias", (qdim,), "b"),
+            (p + "ffn.3.weight", (qdim, qdim), "w"), (p + "ffn.3.bias", (qdim,), "b")]
+
+
+def _gru_spec(p: str) -> list[tuple[str, tuple[int, ...], str]]:
+    out = []
+    for g in "zrq":
+        out += [(p + f"conv{g}1.weight", (128, 512, 1, 5), "w"), (p + f"conv{g}1.bias", (128,), "b")]
+    for g in "zrq":
+        out += [(p + f"conv{g}2.weight", (128, 512, 5, 1), "w"), (p + f"conv{g}2.bias", (128,), "b")]
+    return out
+
+
+def param_spec() -> list[tuple[str, tuple[int, ...], str]]:
+    """All 428 tensors of the reference `FlowFormerCov.state_dict()`."""
+    D = LATENT_DIM
+    s = _svt_spec("memory_encoder.feat_encoder")
+    s += [("memory_encoder.channel_convertor.weight", (256, 256, 1, 1), "w")]
+    c = "memory_encoder.cost_perceiver_encoder."
+    s += [(c + "latent_tokens", (1, LATENT_TOKENS, D), "randn")]
+    pe = c + "patch_embed."
+    s += [(pe + "proj.0.weight", (16, 1, 6, 6), "w"), (pe + "proj.0.bias", (16,), "b"),
+          (pe + "proj.2.weight", (32, 16, 6, 6), "w"), (pe + "proj.2.bias", (32,), "b"),
+          (pe + "proj.4.weight", (64, 32, 6, 6), "w"), (pe + "proj.4.bias", (64,), "b"),
+          (pe + "ffn_with_coord.0.weight", (D, D, 1, 1), "w"), (pe + "ffn_with_coord.0.bias", (D,), "b"),
+          (pe + "ffn_with_coord.2.weight", (D, D, 1, 1), "w"), (pe + "ffn_with_coord.2.bias", (D,), "b"),
+          (pe + "norm.weight", (D,), "one"), (pe + "norm.bias", (D,), "zero")]
+    s += _attn_layer_spec(c + "input_layer.", D, D, D)
+    for i in range(ENCODER_DEPTH):
+        s += _attn_layer_spec(c + f"encoder_layers.{i}.", D, D, D)
+    for i in range(ENCODER_DEPTH):
+        for blk in ("local_block", "global_block"):
+            b = c + f"vertical_encoder_layers.{i}.{blk}."
+            s += [(b + "norm1.weight", (D,), "one"), (b + "norm1.bias", (D,), "zero"),
+                  (b + "attn.context_proj.weight", (VERT_C_DIM, 256), "w"), (b + "attn.context_proj.bias", (VERT_C_DIM,), "b"),
+                  (b + "attn.q.weight", (D, D + VERT_C_DIM), "w"), (b + "attn.q.bias", (D,), "b")]
+            kin = D + VERT_C_DIM if blk == "local_block" else D
+            s += [(b + "attn.k.weight", (D, kin), "w"), (b + "attn.k.bias", (D,), "b"),
+                  (b + "attn.v.weight", (D, D), "w"), (b + "attn.v.bias", (D,), "b"),
+                  (b + "attn.proj.weight", (D, D), "w"), (b + "attn.proj.bias", (D,), "b")]
+            if blk == "global_block":
+                s += [(b + "attn.sr_key.weight", (D, D + VERT_C_DIM, 4, 4), "w"), (b + "attn.sr_key.bias", (D,), "b"),
+                      (b + "attn.sr_value.weight", (D, D, 4, 4), "w"), (b + "attn.sr_value.bias", (D,), "b"),
+                      (b + "attn.norm.weight", (D,), "one"), (b + "attn.norm.bias", (D,), "zero")]
+            s += [(b + "norm2.weight", (D,), "one"), (b + "norm2.bias", (D,), "zero"),
+                  (b + "mlp.fc1.weight", (4 * D, D), "w"), (b + "mlp.fc1.bias", (4 * D,), "b"),
+                  (b + "mlp.fc2.weight", (D, 4 * D), "w"), (b + "mlp.fc2.bias", (D,), "b")]
+    m = "memory_decoder."
+    s += [(m + "delta", (1, 9, 9, 2), "delta"),
+          (m + "flow_token_encoder.0.weight", (QUERY_DIM, 81, 1, 1), "w"), (m + "flow_token_encoder.0.bias", (QUERY_DIM,), "b"),
+          (m + "flow_token_encoder.2.weight", (QUERY_DIM, QUERY_DIM, 1, 1), "w"), (m + "flow_token_encoder.2.bias", (QUERY_DIM,), "b"),
+          (m + "proj.weight", (256, 256, 1, 1), "w"), (m + "proj.bias", (256,), "b")]
+    s += _attn_layer_spec(m + "decoder_layer.cross_attend.", QUERY_DIM, D, 2 * QUERY_DIM)
+    e = m + "update_block.encoder."
+    s += [(e + "convc1.weight", (256, 81 + QUERY_DIM, 1, 1), "w"), (e + "convc1.bias", (256,), "b"),
+          (e + "convc2.weight", (192, 256, 3, 3), "w"), (e + "convc2.bias", (192,), "b"),
+          (e + "convf1.weight", (128, 2, 7, 7), "w"), (e + "convf1.bias", (128,), "b"),
+          (e + "convf2.weight", (64, 128, 3, 3), "w"), (e + "convf2.bias", (64,), "b"),
+          (e + "conv.weight", (126, 256, 3, 3), "w"), (e + "conv.bias", (126,), "b")]
+    s += _gru_spec(m + "update_block.gru.")
+    s += [(m + "update_block.flow_head.conv1.weight", (256, 128, 3, 3), "w"), (m + "update_block.flow_head.conv1.bias", (256,), "b"),
+          (m + "update_block.flow_head.conv2.weight", (2, 256, 3, 3), "w"), (m + "update_block.flow_head.conv2.bias", (2,), "b"),
+          (m + "update_block.mask.0.weight", (256, 128, 3, 3), "w"), (m + "update_block.mask.0.bias", (256,), "b"),
+          (m + "update_block.mask.2.weight", (576, 256, 1, 1), "w"), (m + "update_block.mask.2.bias", (576,), "b"),
+          (m + "update_block.aggregator.gamma", (1,), "gamma"),
+          (m + "update_block.aggregator.to_v.weight", (128, 128, 1, 1), "w"),
+          (m + "att.to_qk.weight", (256, 128, 1, 1), "w")]
+    s += _gru_spec(m + "cov_update.gru.")
+    h = m + "cov_update.cov_head."
+    s += [(h + "conv1.weight", (256, 128, 3, 3), "w"), (h + "conv1.bias", (256,), "b"),
+          (h + "conv2.weight", (128, 256, 3, 3), "w"), (h + "conv2.bias", (128,), "b"),
+          (h + "conv3.weight", (64, 128, 3, 3), "w"), (h + "conv3.bias", (64,), "b"),
+          (h + "conv4.weight", (2, 64, 3, 3), "w"), (h + "conv4.bias", (2,), "b"),
+          (m + "cov_update.mask.0.weight", (256, 128, 3, 3), "w"), (m + "cov_update.mask.0.bias", (256,), "b"),
+          (m + "cov_update.mask.2.weight", (576, 256, 1, 1), "w"), (m + "cov_update.mask.2.bias", (576,), "b")]
+    s += _svt_spec("context_encoder")
+    return s
+
+
+def synthetic_state_dict(seed: int = 0) -> dict[str, Tensor]:
+    """Deterministic stand-in for the released checkpoint (absent: no network).
+
+    Every tensor is drawn from its own generator seeded by (seed, crc32(key)), so the values do not
+    depend on module construction order and can be loaded into the reference model as well
+    (`tests/golden/make_golden.py`) — that is how the golden fixtures are tied to these weights.
+    Weights ~ U(+-1/sqrt(fan_in)) (torch's default conv/linear init), norms (1, 0), GMA gamma 0.5
+    (the reference initialises it to 0, which would leave the aggregation path untested).
+    """
+    sd: dict[str, Tensor] = {}
+    for key, shape, kind in param_spec():
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) % (2 ** 31))
+        if kind == "one":
+            t = torch.ones(shape)
+        elif kind == "zero":
+            t = torch.zeros(shape)
+        elif kind == "randn":
+            t = torch.randn(shape, generator=g)
+        elif kind == "gamma":
+            t = torch.full(shape, 0.5)
+        elif kind == "delta":
+            t = window_delta()
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            if kind == "b":  # bias: fan_in unknown from its own shape; same +-1/sqrt(.) family
+                fan_in = max(shape[0], 16)
+            bound = 1.0 / math.sqrt(fan_in)
+            t = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        sd[key] = t
+    return sd
+
+
+def window_delta() -> Tensor:
+    """`MemoryDecoder.delta` buffer (decoder.py:124-129): delta[0,i,j] = (i-4, j-4)."""
+    r = torch.linspace(-4, 4, 9)
+    return torch.stack(torch.meshgrid(r, r, indexing="ij"), dim=-1).view(1, 9, 9, 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# small functional helpers
+# ----------------------------------------------------------------------------------------------
+def coords_grid(batch: int, ht: int, wd: int, device, dtype) -> Tensor:
+    """(B, 2, H, W) with channel 0 = x, 1 = y  (core/utils.py:36-43)."""
+    ys, xs = torch.meshgrid(torch.arange(ht, device=device, dtype=dtype),
+                            torch.arange(wd, device=device, dtype=dtype), indexing="ij")
+    return torch.stack((xs, ys), dim=0).unsqueeze(0).repeat(batch, 1, 1, 1)
+
+
+def sine_embed(xy: Tensor, dim: int) -> Tensor:
+    """LinearPositionEmbeddingSine (core/attention.py:71-101): cat(sin x f, cos x f, sin y f, cos y f)."""
+    freq = torch.arange(dim // 4, device=xy.device, dtype=xy.dtype) * (1 / 200) * torch.pi
+    ax = xy[..., -2:-1] * freq
+    ay = xy[..., -1:] * freq
+    return torch.cat([torch.sin(ax), torch.cos(ax), torch.sin(ay), torch.cos(ay)], dim=-1)
+
+
+def _sdpa(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
+    return F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False)
+
+
+def _explicit_mha(q: Tensor, k: Tensor, v: Tensor, heads: int) -> Tensor:
+    """`MultiHeadAttention` (core/attention.py:32-68): softmax(q k^T * scale) v with explicit ops."""
+    B, I, C = q.shape
+    J = k.shape[1]
+    d = C // heads
+    q = q.view(B, I, heads, d).permute(0, 2, 1, 3)
+    k = k.view(B, J, heads, d).permute(0, 2, 1, 3)
+    v = v.view(B, J, heads, d).permute(0, 2, 1, 3)
+    attn = (torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)).softmax(dim=-1)
+    return torch.matmul(attn, v).permute(0, 2, 1, 3).reshape(B, I, C)
+
+
+class FlowFormerCovNet:
+    """Functional FlowFormerCov. `inference(image1, image2) -> (flow, cov)` like flownet.py:37-44."""
+
+    def __init__(self, state_dict: dict[str, Tensor], device, enc_dtype=torch.float32, dec_dtype=torch.float32,
+                 decoder_depth: int = 12,
+                 corr_fn: Callable[[Tensor, Tensor], Tensor] | None = None,
+                 lookup_fn: Callable[[Tensor, Tensor], Tensor] | None = None):
+        self.device = torch.device(device)
+        self.enc_dtype, self.dec_dtype, self.depth = enc_dtype, dec_dtype, decoder_depth
+        if corr_fn is None or lookup_fn is None:
+            from . import ops  # binds to the CUDA library; raises if it cannot be loaded
+            corr_fn = corr_fn or ops.corr_build
+            lookup_fn = lookup_fn or ops.corr_lookup
+        self.corr_fn, self.lookup_fn = corr_fn, lookup_fn
+        self.load_state_dict(state_dict)
+        self._cache: dict = {}
+
+    # ---- weights -------------------------------------------------------------------------------
+    def load_state_dict(self, ckpt: dict[str, Tensor]) -> None:
+        """Accepts the reference checkpoint layout incl. DDP `module.` prefixes (flownet.py:46-53)."""
+        ckpt = {(k[7:] if k.startswith("module.") else k): v for k, v in ckpt.items()}
+        W: dict[str, Tensor] = {}
+        missing = []
+        for key, shape, _ in param_spec():
+            if key not in ckpt:
+                missing.append(key)
+                continue
+            t = ckpt[key]
+            assert tuple(t.shape) == shape, f"{key}: expected {shape}, got {tuple(t.shape)}"
+            if key.startswith("memory_decoder."):
+                dt = self.dec_dtype
+                if key.startswith("memory_decoder.proj."):
+                    dt = torch.float32  # MemoryDecoder.proj is not cast (covhead.py:52-58 omits it)
+            else:
+                dt = self.enc_dtype
+            W[key] = t.detach().to(device=self.device, dtype=dt).contiguous()
+        if missing:
+            raise KeyError(f"checkpoint misses {len(missing)} tensors, e.g. {missing[:3]}")
+        self.W = W
+        # fused GRU gate filters (z|r share their input)
+        for p in ("memory_decoder.update_block.gru.", "memory_decoder.cov_update.gru."):
+            for o in "12":
+                W[p + f"convzr{o}.weight"] = torch.cat([W[p + f"convz{o}.weight"], W[p + f"convr{o}.weight"]], 0).contiguous()
+                W[p + f"convzr{o}.bias"] = torch.cat([W[p + f"convz{o}.bias"], W[p + f"convr{o}.bias"]], 0).contiguous()
+
+    def state_dict(self) -> dict[str, Tensor]:
+        return {k: self.W[k] for k, _, _ in param_spec()}
+
+    def _lin(self, x: Tensor, p: str) -> Tensor:
+        return F.linear(x, self.W[p + ".weight"], self.W.get(p + ".bias"))
+
+    def _conv(self, x: Tensor, p: str, stride=1, padding=0, groups=1) -> Tensor:
+        return F.conv2d(x, self.W[p + ".weight"], self.W.get(p + ".bias"), stride=stride, padding=padding, groups=groups)
+
+    def _ln(self, x: Tensor, p: str, eps: float = 1e-5) -> Tensor:
+        return F.layer_norm(x, (x.shape[-1],), self.W[p + ".weight"], self.W[p + ".bias"], eps)
+
+    def _memo(self, key, fn):
+        if key not in self._cache:
+            self._cache[key] = fn()
+        return self._cache[key]
+
+    # ---- Twins-SVT-L, first two stages (core/twins_svt.py:19-37, Twins/svt_large.py) -------------
+    def svt(self, x: Tensor, prefix: str) -> Tensor:
+        B = x.shape[0]
+        for s, (heads, sr, ps) in enumerate(((4, 8, 4), (8, 4, 2))):
+            p = f"{prefix}.svt."
+            x = self._conv(x, p + f"patch_embeds.{s}.proj", stride=ps)
+            C, H, W = x.shape[1:]
+            x = self._ln(x.flatten(2).transpose(1, 2), p + f"patch_embeds.{s}.norm")
+            b0, b1 = p + f"blocks.{s}.0.", p + f"blocks.{s}.1."
+            # block 0: locally-grouped attention (7x7 windows, zero padded after the norm)
+            x = x + self._svt_local_attn(self._ln(x, b0 + "norm1", 1e-6), (H, W), b0 + "attn.", heads)
+            x = x + self._mlp(self._ln(x, b0 + "norm2", 1e-6), b0 + "mlp.")
+            # PEG: depthwise 3x3 + identity
+            t = x.transpose(1, 2).reshape(B, C, H, W)
+            t = self._conv(t, p + f"pos_block.{s}.proj.0", padding=1, groups=C) + t
+            x = t.flatten(2).transpose(1, 2)
+            # block 1: globally sub-sampled attention
+            x = x + self._svt_global_attn(self._ln(x, b1 + "norm1", 1e-6), (H, W), b1 + "attn.", heads, sr)
+            x = x + self._mlp(self._ln(x, b1 + "norm2", 1e-6), b1 + "mlp.")
+            x = x.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+        return x
+
+    def _mlp(self, x: Tensor, p: str) -> Tensor:
+        return self._lin(F.gelu(self._lin(x, p + "fc1")), p + "fc2")
+
+    @staticmethod
+    def _to_windows(x: Tensor, ws: int) -> tuple[Tensor, tuple[int, int, int, int]]:
+        """(B, H, W, C) -> (B*nh*nw, ws*ws, C), zero padded on the right / bottom."""
+        B, H, W, C = x.shape
+        pr, pb = (ws - W % ws) % ws, (ws - H % ws) % ws
+        x = F.pad(x, (0, 0, 0, pr, 0, pb))
+        nh, nw = (H + pb) // ws, (W + pr) // ws
+        x = x.reshape(B, nh, ws, nw, ws, C).transpose(2, 3).reshape(B * nh * nw, ws * ws, C)
+        return x, (B, nh, nw, C)
+
+    @staticmethod
+    def _from_windows(x: Tensor, meta: tuple[int, int, int, int], ws: int, H: int, W: int) -> Tensor:
+        B, nh, nw, C = meta
+        x = x.reshape(B, nh, nw, ws, ws, C).transpose(2, 3).reshape(B, nh * ws, nw * ws, C)
+        return x[:, :H, :W, :].reshape(B, H * W, C)
+
+    def _svt_local_attn(self, x: Tensor, size, p: str, heads: int, ws: int = 7) -> Tensor:
+        B, N, C = x.shape
+        H, W = size
+        xw, meta = self._to_windows(x.view(B, H, W, C), ws)
+        qkv = self._lin(xw, p + "qkv").reshape(xw.shape[0], ws * ws, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+        o = _sdpa(qkv[0], qkv[1], qkv[2]).transpose(1, 2).reshape(xw.shape[0], ws * ws, C)
+        return self._lin(self._from_windows(o, meta, ws, H, W), p + "proj")
+
+    def _svt_global_attn(self, x: Tensor, size, p: str, heads: int, sr: int) -> Tensor:
+        B, N, C = x.shape
+        d = C // heads
+        q = self._lin(x, p + "q").reshape(B, N, heads, d).permute(0, 2, 1, 3)
+        t = self._conv(x.permute(0, 2, 1).reshape(B, C, *size), p + "sr", stride=sr)
+        t = self._ln(t.reshape(B, C, -1).permute(0, 2, 1), p + "norm")
+        kv = self._lin(t, p + "kv").reshape(B, -1, 2, heads, d).permute(2, 0, 3, 1, 4)
+        o = _sdpa(q, kv[0], kv[1]).transpose(1, 2).reshape(B, N, C)
+        return self._lin(o, p + "proj")
+
+    # ---- cost perceiver encoder (core/encoder.py:194-244) -------------------------------------
+    def patch_embed(self, cost_maps: Tensor) -> Tensor:
+        """(M, 1, H2, W2) -> (M, h*w, 128) tokens  (PatchEmbed, core/encoder.py:12-55)."""
+        p = "memory_encoder.cost_perceiver_encoder.patch_embed."
+        M, _, H2, W2 = cost_maps.shape
+        x = F.pad(cost_maps, (0, (8 - W2 % 8) % 8, 0, (8 - H2 % 8) % 8))
+        x = F.relu(self._conv(x, p + "proj.0", stride=2, padding=2))
+        x = F.relu(self._conv(x, p + "proj.2", stride=2, padding=2))
+        x = self._conv(x, p + "proj.4", stride=2, padding=2)
+        h, w = x.shape[2:]
+
+        def coord_term():
+            xy = coords_grid(1, h, w, x.device, x.dtype) * 8 + 4
+            enc = sine_embed(xy.view(1, 2, -1).permute(0, 2, 1), COST_INPUT_DIM)          # (1, hw, 64)
+            return enc.permute(0, 2, 1).reshape(1, COST_INPUT_DIM, h, w)
+        enc = self._memo(("pe", h, w, x.dtype), coord_term)
+        x = torch.cat([x, enc.expand(M, -1, -1, -1)], dim=1)
+        x = self._conv(F.relu(self._conv(x, p + "ffn_with_coord.0")), p + "ffn_with_coord.2")
+        return self._ln(x.flatten(2).transpose(1, 2), p + "norm")
+
+    def _latent_layer(self, x: Tensor, p: str) -> Tensor:
+        """SelfAttentionLayer over the 8 latent tokens of each source pixel (core/encoder.py:97-140)."""
+        y = self._ln(x, p + "norm1")
+        a = _explicit_mha(self._lin(y, p + "q"), self._lin(y, p + "k"), self._lin(y, p + "v"), 8)
+        x = x + self._lin(a, p + "proj")
+        return x + self._lin(F.gelu(self._lin(self._ln(x, p + "norm2"), p + "ffn.0")), p + "ffn.3")
+
+    def _context_tokens(self, context: Tensor, p: str, reps: int) -> Tensor:
+        """context_proj of the context map, tiled like `context.repeat(B//b, 1, 1, 1)` (twins.py:55-58):
+        row i of the (B*8)-batch sees context[i % b] — a reference quirk that is kept."""
+        b, _, H, W = context.shape
+        c = self._lin(context.view(b, -1, H * W).permute(0, 2, 1), p + "context_proj").view(b, H, W, -1)
+        return c.repeat(reps, 1, 1, 1)
+
+    def _vert_local_attn(self, x: Tensor, size, context: Tensor, p: str, ws: int = 7, heads: int = 8) -> Tensor:
+        Bt, N, C = x.shape
+        H, W = size
+        ctx = self._context_tokens(context, p, Bt // context.shape[0])
+        xg = x.view(Bt, H, W, C)
+        xw, meta = self._to_windows(xg, ws)
+        qkw, _ = self._to_windows(torch.cat([xg, ctx], dim=-1), ws)
+        enc = self._memo(("win", ws, C + VERT_C_DIM, x.dtype, x.device), lambda: sine_embed(
+            coords_grid(1, ws, ws, x.device, x.dtype).view(1, 2, -1).permute(0, 2, 1), C + VERT_C_DIM))
+        qkw = qkw + enc
+        d = C // heads
+        nwin = xw.shape[0]
+        q = self._lin(qkw, p + "q").reshape(nwin, ws * ws, heads, d).transpose(1, 2)
+        k = self._lin(qkw, p + "k").reshape(nwin, ws * ws, heads, d).transpose(1, 2)
+        v = self._lin(xw, p + "v").reshape(nwin, ws * ws, heads, d).transpose(1, 2)
+        o = _sdpa(q.contiguous(), k.contiguous(), v.contiguous()).transpose(1, 2).reshape(nwin, ws * ws, C)
+        return self._lin(self._from_windows(o, meta, ws, H, W), p + "proj")
+
+    def _vert_global_attn(self, x: Tensor, size, context: Tensor, p: str, sr: int = 4, heads: int = 8) -> Tensor:
+        Bt, N, C = x.shape
+        H, W = size
+        ctx = self._context_tokens(context, p, Bt // context.shape[0])
+        xg = x.view(Bt, H, W, C)
+        qk = torch.cat([xg, ctx], dim=-1)
+        pr, pb = (sr - W % sr) % sr, (sr - H % sr) % sr
+        xg, qk = F.pad(xg, (0, 0, 0, pr, 0, pb)), F.pad(qk, (0, 0, 0, pr, 0, pb))
+        Hp, Wp = H + pb, W + pr
+        d = C // heads
+        Cq = C + VERT_C_DIM
+        enc_full = self._memo(("full", Hp, Wp, Cq, x.dtype, x.device), lambda: sine_embed(
+            coords_grid(1, Hp, Wp, x.device, x.dtype).view(1, 2, -1).permute(0, 2, 1), Cq))
+        q = self._lin(qk.reshape(Bt, Hp * Wp, Cq) + enc_full, p + "q").reshape(Bt, Hp * Wp, heads, d).permute(0, 2, 1, 3)
+        v_in = self._conv(xg.permute(0, 3, 1, 2), p + "sr_value", stride=sr).reshape(Bt, C, -1).permute(0, 2, 1)
+        k_in = self._conv(qk.permute(0, 3, 1, 2), p + "sr_key", stride=sr).reshape(Bt, C, -1).permute(0, 2, 1)
+        v_in, k_in = self._ln(v_in, p + "norm"), self._ln(k_in, p + "norm")
+        enc_sub = self._memo(("sub", Hp // sr, Wp // sr, sr, C, x.dtype, x.device), lambda: sine_embed(
+            coords_grid(1, Hp // sr, Wp // sr, x.device, x.dtype).view(1, 2, -1).permute(0, 2, 1) * sr, C))
+        M = k_in.shape[1]
+        k = self._lin(k_in + enc_sub, p + "k").reshape(Bt, M, heads, d).permute(0, 2, 1, 3)
+        v = self._lin(v_in, p + "v").reshape(Bt, M, heads, d).permute(0, 2, 1, 3)
+        o = _sdpa(q, k, v).transpose(1, 2).reshape(Bt, Hp, Wp, C)[:, :H, :W, :].reshape(Bt, N, C)
+        return self._lin(o, p + "proj")
+
+    def _vert_block(self, x: Tensor, size, context: Tensor, p: str, local: bool) -> Tensor:
+        attn = self._vert_local_attn if local else self._vert_global_attn
+        x = x + attn(self._ln(x, p + "norm1"), size, context, p + "attn.")
+        return x + self._mlp(self._ln(x, p + "norm2"), p + "mlp.")
+
+    def cost_perceiver(self, cost_volume: Tensor, context: Tensor) -> tuple[Tensor, Tensor]:
+        c = "memory_encoder.cost_perceiver_encoder."
+        B, heads, H1, W1, H2, W2 = cost_volume.shape
+        assert heads == 1
+        cost_maps = cost_volume.view(B * H1 * W1, 1, H2, W2)     # contiguous view: heads == 1
+        tokens = self.patch_embed(cost_maps)                     # (B*N, hw, 128)
+        # input_layer: 8 learned latents cross-attend to each pixel's patch tokens (encoder.py:150-191)
+        p = c + "input_layer."
+        lat = self.W[c + "latent_tokens"]                        # (1, 8, 128)
+        M = tokens.shape[0]
+        q = self._lin(self._ln(lat, p + "norm1"), p + "q").view(1, LATENT_TOKENS, 8, 16).permute(0, 2, 1, 3).expand(M, -1, -1, -1)
+        k = self._lin(tokens, p + "k").view(M, -1, 8, 16).permute(0, 2, 1, 3)
+        v = self._lin(tokens, p + "v").view(M, -1, 8, 16).permute(0, 2, 1, 3)
+        a = _sdpa(q, k, v).permute(0, 2, 1, 3).reshape(M, LATENT_TOKENS, LATENT_DIM)
+        x = lat + self._lin(a, p + "proj")
+        x = x + self._lin(F.gelu(self._lin(self._ln(x, p + "norm2"), p + "ffn.0")), p + "ffn.3")
+        short_cut = x
+        N = H1 * W1
+        for i in range(ENCODER_DEPTH):
+            x = self._latent_layer(x, c + f"encoder_layers.{i}.")
+            x = x.view(B, N, LATENT_TOKENS, -1).permute(0, 2, 1, 3).reshape(B * LATENT_TOKENS, N, -1)
+            v_ = c + f"vertical_encoder_layers.{i}."
+            x = self._vert_block(x, (H1, W1), context, v_ + "local_block.", True)
+            x = self._vert_block(x, (H1, W1), context, v_ + "global_block.", False)
+            x = x.view(B, LATENT_TOKENS, N, -1).permute(0, 2, 1, 3).reshape(B * N, LATENT_TOKENS, -1)
+        return x + short_cut, cost_maps
+
+    def memory_encoder(self, img1: Tensor, img2: Tensor, context: Tensor) -> tuple[Tensor, Tensor]:
+        feats = self.svt(torch.cat([img1, img2], dim=0), "memory_encoder.feat_encoder")
+        feats = self._conv(feats, "memory_encoder.channel_convertor")
+        B = feats.shape[0] // 2
+        cost_volume = self.corr_fn(feats[:B], feats[B:]).to(feats.dtype)   # encoder.py:289-290
+        return self.cost_perceiver(cost_volume, context)
+
+    # ---- decoder (covhead.py:60-140) -----------------------------------------------------------
+    def _gru(self, h: Tensor, x: Tensor, p: str) -> Tensor:
+        for o, pad in (("1", (0, 2)), ("2", (2, 0))):
+            hx = torch.cat([h, x], dim=1)
+            zr = torch.sigmoid(self._conv(hx, p + f"convzr{o}", padding=pad))
+            z, r = zr[:, :128], zr[:, 128:]
+            q = torch.tanh(self._conv(torch.cat([r * h, x], dim=1), p + f"convq{o}", padding=pad))
+            h = (1 - z) * h + z * q
+        return h
+
+    @staticmethod
+    def convex_upsample(flow: Tensor, mask: Tensor) -> Tensor:
+        """`upsample_flow` (decoder.py:131-139): softmax over the 9 neighbours, 8x."""
+        N, C, H, W = flow.shape
+        mask = mask.view(N, 9, 8, 8, H, W).softmax(dim=1)
+        up = F.unfold(8 * flow, (3, 3), padding=1).view(N, C, 9, H, W)
+        out = (mask.unsqueeze(1) * up.unsqueeze(-3).unsqueeze(-3)).sum(dim=2)
+        return out.permute(0, 1, 4, 2, 5, 3).reshape(N, C, 8 * H, 8 * W)
+
+    def memory_decoder(self, cost_memory: Tensor, context: Tensor, cost_maps: Tensor) -> tuple[Tensor, Tensor]:
+        m, dd = "memory_decoder.", self.dec_dtype
+        cost_memory = cost_memory.to(dd)
+        B, _, H1, W1 = context.shape
+        N = H1 * W1
+        coords0 = coords_grid(B, H1, W1, context.device, context.dtype)
+        coords1, ccoords1 = coords0.clone(), coords0.clone()
+        ctx = self._conv(context, m + "proj")
+        net = ctx[:, :128].tanh().to(dd)
+        cnet = net.clone()
+        inp = ctx[:, 128:].relu().to(dd)
+        # GMA attention, once per frame (gma.py:39-82): softmax over the N x N similarity
+        qk = self._conv(inp, m + "att.to_qk")
+        qv = (qk[:, :128] * (128 ** -0.5)).flatten(2).transpose(1, 2)            # (B, N, 128)
+        attention = torch.matmul(qv, qk[:, 128:].flatten(2)).softmax(dim=-1)     # (B, N, N)
+        ca = m + "decoder_layer.cross_attend."
+        key = self._lin(cost_memory, ca + "k")
+        value = self._lin(cost_memory, ca + "v")
+        ub, cu = m + "update_block.", m + "cov_update."
+        gamma = self.W[ub + "aggregator.gamma"]
+        for _ in range(self.depth):
+            flow = (coords1 - coords0).to(dd)
+            cost_forward = self.lookup_fn(cost_maps, coords1).to(dd)             # fp32 lookup (covhead.py:91-93)
+            query = self._conv(F.gelu(self._conv(cost_forward, m + "flow_token_encoder.0")), m + "flow_token_encoder.2")
+            query = query.permute(0, 2, 3, 1).reshape(B * N, 1, QUERY_DIM)
+            # cross attention of each pixel's query to its 8 cost-memory tokens (decoder.py:56-76)
+            enc = sine_embed(coords1.to(dd).permute(0, 2, 3, 1).reshape(B * N, 1, 2), QUERY_DIM)
+            q = self._lin(self._ln(query, ca + "norm1") + enc, ca + "q")
+            a = _explicit_mha(q, key, value, 8)
+            g = query + self._lin(torch.cat([a, query], dim=2), ca + "proj")
+            g = g + self._lin(F.gelu(self._lin(self._ln(g, ca + "norm2"), ca + "ffn.0")), ca + "ffn.3")
+            cost_global = g.view(B, H1, W1, QUERY_DIM).permute(0, 3, 1, 2)
+            corr = torch.cat([cost_global, cost_forward], dim=1)
+            # motion encoder (gru.py:45-64)
+            e = ub + "encoder."
+            cor = F.relu(self._conv(F.relu(self._conv(corr, e + "convc1")), e + "convc2", padding=1))
+            flo = F.relu(self._conv(F.relu(self._conv(flow, e + "convf1", padding=3)), e + "convf2", padding=1))
+            mf = torch.cat([F.relu(self._conv(torch.cat([cor, flo], dim=1), e + "conv", padding=1)), flow], dim=1)
+            # GMA aggregation (gma.py:84-130)
+            v = self._conv(mf, ub + "aggregator.to_v").flatten(2).transpose(1, 2)   # (B, N, 128)
+            agg = torch.matmul(attention, v).transpose(1, 2).reshape(B, 128, H1, W1)
+            inp_cat = torch.cat([inp, mf, mf + gamma * agg], dim=1)
+            net = self._gru(net, inp_cat, ub + "gru.")
+            d_flow = self._conv(F.relu(self._conv(net, ub + "flow_head.conv1", padding=1)), ub + "flow_head.conv2", padding=1)
+            cnet = self._gru(cnet, inp_cat, cu + "gru.")
+            h = cu + "cov_head."
+            t = self._conv(F.relu(self._conv(cnet, h + "conv1", padding=1)), h + "conv2", padding=1)
+            d_cov = self._conv(F.relu(self._conv(t, h + "conv3", padding=1)), h + "conv4", padding=1)
+            coords1 = coords1 + d_flow.float()
+            ccoords1 = ccoords1 + d_cov.float()
+        # the reference evaluates both mask heads + upsampling every iteration but (eval mode) returns
+        # only the last one (covhead.py:137-140) -> evaluate once
+        up_mask = 0.25 * self._conv(F.relu(self._conv(net, ub + "mask.0", padding=1)), ub + "mask.2").float()
+        cov_mask = (0.25 * self._conv(F.relu(self._conv(cnet, cu + "mask.0", padding=1)), cu + "mask.2")).float()
+        return self.convex_upsample(coords1 - coords0, up_mask), self.convex_upsample(ccoords1 - coords0, cov_mask)
+
+    # ---- top level (flownet.py:18-44) -----------------------------------------------------------
+    @torch.inference_mode()
+    def forward(self, image1: Tensor, image2: Tensor) -> tuple[Tensor, Tensor]:
+        image1 = ((2 * image1) - 1.0).to(self.enc_dtype)
+        image2 = ((2 * image2) - 1.0).to(self.enc_dtype)
+        context = self.svt(image1, "context_encoder")
+        cost_memory, cost_maps = self.memory_encoder(image1, image2, context)
+        return self.memory_decoder(cost_memory, context.float(), cost_maps.float())
+
+    @torch.inference_mode()
+    def inference(self, image1: Tensor, image2: Tensor) -> tuple[Tensor, Tensor]:
+        """(B,3,H,W) x2 in [0,1] -> flow (B,2,H,W), cov = exp(2 log sigma) (B,2,H,W)."""
+        H, W = image1.shape[-2:]
+        ph, pw = (-H) % 8, (-W) % 8
+        pad = [pw // 2, pw - pw // 2, ph // 2, ph - ph // 2]       # InputPadder 'sintel' (core/utils.py:4-24)
+        if ph or pw:
+            image1, image2 = F.pad(image1, pad, mode="replicate"), F.pad(image2, pad, mode="replicate")
+        flow, logsig = self.forward(image1, image2)
+        if ph or pw:
+            flow = flow[..., pad[2]:flow.shape[-2] - pad[3], pad[0]:flow.shape[-1] - pad[1]]
+            logsig = logsig[..., pad[2]:logsig.shape[-2] - pad[3], pad[0]:logsig.shape[-1] - pad[1]]
+        return flow, torch.exp(logsig * 2)
