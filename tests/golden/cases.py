@@ -1,0 +1,184 @@
+"""Seeded synthetic inputs shared by tests/golden/make_golden.py (reference side, build container)
+and the parity tests (oracle / CUDA side, also on the GPU box). SURVEY.md §8(d) shapes.
+
+Only CPU torch generators are used -> identical values wherever the same torch build runs.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+Tensor = torch.Tensor
+
+
+def _gen(seed: int) -> torch.Generator:
+    return torch.Generator().manual_seed(seed)
+
+
+# ---- correlation volume -------------------------------------------------------------------------
+CORR_CASES = {"tiny": (2, 5, 7), "small": (2, 12, 16), "ragged": (1, 9, 13), "clip": (1, 30, 40)}
+
+
+def corr_inputs(B: int, H1: int, W1: int, D: int = 256, seed: int = 2) -> tuple[Tensor, Tensor]:
+    g = _gen(seed + 17 * H1 + W1)
+    return torch.randn(B, D, H1, W1, generator=g) * 0.5, torch.randn(B, D, H1, W1, generator=g) * 0.5
+
+
+def corr_sample_index(N: int) -> tuple[Tensor, Tensor]:
+    rows = torch.unique(torch.linspace(0, N - 1, min(N, 48)).long())
+    cols = torch.unique(torch.linspace(0, N - 1, min(N, 64)).long())
+    return rows, cols
+
+
+# ---- window lookup --------------------------------------------------------------------------------
+LOOKUP_CASES = {"tiny": (1, 5, 7), "small": (2, 12, 16)}
+
+
+def lookup_inputs(B: int, H1: int, W1: int, seed: int = 3) -> tuple[Tensor, Tensor]:
+    g = _gen(seed + 17 * H1 + W1)
+    cost_maps = torch.randn(B * H1 * W1, 1, H1, W1, generator=g)
+    ys, xs = torch.meshgrid(torch.arange(H1, dtype=torch.float32), torch.arange(W1, dtype=torch.float32), indexing="ij")
+    grid = torch.stack([xs, ys], 0).unsqueeze(0).repeat(B, 1, 1, 1)
+    coords = grid + torch.randn(B, 2, H1, W1, generator=g) * 3.0       # includes out-of-range targets
+    coords[:, :, 0, 0] = -20.0                                          # a fully out-of-range window
+    coords[:, 0, 0, 1], coords[:, 1, 0, 1] = float(W1 - 1), float(H1 - 1)  # exact corner
+    coords[:, :, 1, 0] = 2.0                                            # exact integer coordinates
+    return cost_maps, coords
+
+
+# ---- network --------------------------------------------------------------------------------------
+NET_CASES = {"small": (2, 96, 128), "odd": (1, 100, 130)}
+
+
+def net_inputs(B: int, H: int, W: int, seed: int = 1000) -> tuple[Tensor, Tensor]:
+    g = _gen(seed + H + W)
+    base = torch.rand(B, 3, H + 8, W + 8, generator=g)
+    base = torch.nn.functional.avg_pool2d(base, 5, stride=1, padding=2)
+    return base[..., 4:-4, 4:-4].contiguous(), base[..., 3:-5, 6:-2].contiguous()
+
+
+# ---- dense post-processing -------------------------------------------------------------------------
+DENSE_CASES = {"small": (64, 96)}
+
+
+def dense_inputs(H: int, W: int, seed: int = 4) -> tuple[Tensor, Tensor]:
+    g = _gen(seed + H + W)
+    flow = torch.randn(2, 2, H, W, generator=g) * 3.0
+    flow[0, 0] = -(torch.rand(H, W, generator=g) * 30 + 1)              # stereo slot: disparity 1..31 px
+    flow[0, 0, 0, :4] = torch.tensor([0.0, 1e-3, 2.5, -1e-4])           # zero / tiny / positive disparity
+    cov = torch.exp(torch.randn(2, 2, H, W, generator=g))
+    return flow, cov
+
+
+# ---- selectors --------------------------------------------------------------------------------------
+SELECTOR_RNG_SEED = 5
+SELECTOR_CASES = {
+    "small": (160, 224, 64, "plain"),
+    "cfgA_512": (480, 640, 512, "plain"),
+    "cfgA_2048": (480, 640, 2048, "plain"),
+    "ties": (160, 224, 4096, "ties"),
+    "nan": (160, 224, 128, "nan"),
+    "masked": (160, 224, 128, "masked"),
+    "flat": (96, 128, 50, "flat"),
+}
+
+
+def selector_inputs(H: int, W: int, variant: str, seed: int = 4) -> tuple[Tensor, Tensor]:
+    g = _gen(seed + H + W + sum(map(ord, variant)))
+    flow = torch.randn(2, 2, H, W, generator=g) * 3.0
+    flow[0, 0] = -(torch.rand(H, W, generator=g) * 30 + 1)
+    cov = torch.exp(torch.randn(2, 2, H, W, generator=g))
+    if variant == "ties":      # quantised -> many equal minima inside one NMS window, equal medians
+        cov = (cov * 4).round() / 4 + 0.25
+    elif variant == "nan":
+        idx = torch.randint(0, H * W, (200,), generator=g)
+        cov[1, 0].view(-1)[idx] = float("nan")
+        cov[1, 1].view(-1)[idx[:50] + 1] = float("inf")
+    elif variant == "flat":    # constant quality: every pixel is its window minimum
+        cov = torch.full_like(cov, 0.75)
+    return flow, cov
+
+
+def selector_match_mask(H: int, W: int, seed: int = 7) -> Tensor:
+    return torch.rand(1, 1, H, W, generator=_gen(seed + H + W)) > 0.3
+
+
+# ---- covariance model ---------------------------------------------------------------------------------
+COV_CASES = {
+    "int_default": (160, 224, 96, "int_default"),
+    "float_cov": (160, 224, 96, "float_cov"),
+    "float_fullcov": (160, 224, 96, "float_fullcov"),
+    "none": (160, 224, 32, "none"),
+    "cfgA_512": (480, 640, 512, "float_cov"),
+}
+
+
+def cov_inputs(H: int, W: int, K: int, kind: str, seed: int = 8):
+    g = _gen(seed + H + W + K + sum(map(ord, kind)))
+    depth = 2.0 + 28.0 * torch.rand(1, 1, H, W, generator=g)
+    depth = torch.nn.functional.avg_pool2d(depth, 9, stride=1, padding=4)          # locally smooth, like a depth map
+    depth = depth + 0.05 * torch.randn(1, 1, H, W, generator=g)
+    u = torch.randint(33, W - 33, (K,), generator=g)
+    v = torch.randint(33, H - 33, (K,), generator=g)
+    if kind == "int_default":
+        kp = torch.stack([u, v], dim=-1)                                            # int64, like kp0_uv
+        flow_cov = torch.ones(K, 3) * 0.25
+        flow_cov[:, 2] = 0.0
+    elif kind == "none":
+        kp = torch.stack([u, v], dim=-1)
+        flow_cov = None
+    else:
+        kp = torch.stack([u, v], dim=-1).float() + torch.rand(K, 2, generator=g)   # fp32, like kp1_uv
+        su = torch.exp(torch.randn(K, generator=g)) * 0.8
+        sv = torch.exp(torch.randn(K, generator=g)) * 0.8
+        su[:4] = torch.tensor([0.01, 0.0625, 40.0, 1e-4])                           # exercises the clamp
+        suv = torch.zeros(K)
+        if kind == "float_fullcov":
+            suv = (torch.rand(K, generator=g) - 0.5) * 0.2
+        flow_cov = torch.stack([su, sv, suv], dim=-1)
+    return kp, depth, flow_cov
+
+
+# ---- two-frame pose-graph optimisation -------------------------------------------------------------------
+PGO_CASES = {"k64": (64, 6), "k512": (512, 6), "k200_far": (200, 9), "k12": (12, 3)}
+
+
+def pgo_inputs(K: int, seed: int) -> dict:
+    """NED points x~U(2,30), y,z~U(-.6x,.6x); true pose Exp([.05,-.02,.01,.01,-.02,.015]);
+    observations = projection + N(0, Sigma_i), 5 % gross outliers; init = identity. fp32 like the map stores."""
+    from oracle import pgo as opgo
+    rng = np.random.default_rng(seed * 7919 + K)
+    x = rng.uniform(2, 30, K)
+    pts = np.stack([x, rng.uniform(-0.6, 0.6, K) * x, rng.uniform(-0.6, 0.6, K) * x], -1)
+    true_pose = opgo.se3_exp(np.array([0.05, -0.02, 0.01, 0.01, -0.02, 0.015]) * (3.0 if seed == 9 else 1.0))
+    fx = fy = 320.0
+    cx, cy, bl = 320.0, 240.0, 0.25
+    pc = opgo.se3_act(opgo.se3_inv(true_pose), pts)
+    uv = np.stack([fx * pc[:, 1] / pc[:, 0] + cx, fy * pc[:, 2] / pc[:, 0] + cy], -1)
+    disp = fx * bl / pc[:, 0]
+    suu, svv = rng.uniform(0.0625, 4, K), rng.uniform(0.0625, 4, K)
+    sdd = rng.uniform(0.01, 1, K)
+    uv = uv + rng.normal(size=(K, 2)) * np.sqrt(np.stack([suu, svv], -1)) * 0.3
+    disp = disp + rng.normal(size=K) * np.sqrt(sdd) * 0.1
+    out = rng.uniform(size=K) < 0.05
+    uv[out] += rng.uniform(5, 30, (int(out.sum()), 2))
+    f32 = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32)
+    return {
+        "pos_Tw": f32(pts), "kp2_uv": f32(uv), "kp2_disp": f32(disp),
+        "uv_cov": f32(np.stack([suu, svv, np.zeros(K)], -1)), "disp_cov": f32(sdd),
+        "K": torch.tensor([[fx, 0., cx], [0., fy, cy], [0., 0., 1.]]), "baseline": bl,
+        "init_pose": torch.tensor([0., 0., 0., 0., 0., 0., 1.]),
+        "true_pose": torch.tensor(true_pose),
+    }
+
+
+def pgo_graph(c: dict):
+    """cases dict -> oracle.pgo.GraphData (fp32 values promoted to fp64, like `.to(torch.double)`)."""
+    from oracle import pgo as opgo
+    K = c["K"].double().numpy()
+    return opgo.GraphData(
+        pos_Tw=c["pos_Tw"].double().numpy(), kp2_uv=c["kp2_uv"].double().numpy(), kp2_disp=c["kp2_disp"].double().numpy(),
+        uv_cov=c["uv_cov"].double().numpy(), disp_cov=c["disp_cov"].double().numpy(),
+        fx=float(K[0, 0]), fy=float(K[1, 1]), cx=float(K[0, 2]), cy=float(K[1, 2]),
+        baseline=float(torch.tensor([c["baseline"]]).double().item()),
+        init_pose=c["init_pose"].double().numpy())

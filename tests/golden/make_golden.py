@@ -1,0 +1,155 @@
+"""Generate the golden fixtures under tests/golden/ by running the REFERENCE ITSELF on CPU.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+The fixtures are small `.pt` files holding seeded inputs + the reference's outputs; the GPU box
+(which has no /root/reference) only reads them. Everything is seeded -> re-running reproduces
+the files bit-for-bit on the same torch build.
+
+What executes here is the unmodified reference code:
+  corr      MemoryEncoder.corr                         Module/Network/FlowFormer/core/encoder.py:256
+  lookup    MemoryDecoder.encode_flow_token            Module/Network/FlowFormer/core/decoder.py:141
+  network   FlowFormerCov.inference (synthetic weights) Module/Network/FlowFormerCov/flownet.py:37
+  postproc  FlowFormerCovFrontend.inference_2_depth/_match  Module/Frontend/Frontend.py:184-200
+  selector  CovAwareSelector_NoDepth / MappingPointSelector Module/KeypointSelector.py:362,87
+  cov       MatchCovariance.estimate                   Module/Covariance/Project2to3.py:124
+  pgo       TwoFrame_PGO._optimize (LM_analytic + Analytic_ReprojDisp_TwoFramePGO) on top of the
+            restated pypose (oracle/pypose_shim) — the only non-reference code in the loop.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from types import SimpleNamespace
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+from tests.golden import refharness  # noqa: E402
+from tests.golden import cases  # noqa: E402
+
+
+def save(name: str, obj: dict) -> None:
+    path = os.path.join(HERE, name)
+    torch.save(obj, path)
+    print(f"wrote {name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def main() -> None:
+    refharness.install()
+    torch.set_num_threads(8)
+    import Module  # noqa: F401  (registers every plugin class)
+    from DataLoader import StereoData
+    from Module.Network.FlowFormer.configs.submission import get_cfg
+    from Module.Network.FlowFormerCov import build_flowformer
+    from Module.Frontend.Frontend import FlowFormerCovFrontend, IFrontend
+    from Module.Frontend.StereoDepth import IStereoDepth
+    from Module.Frontend.Matching import IMatcher
+    from Module.KeypointSelector import CovAwareSelector_NoDepth, MappingPointSelector
+    from Module.Covariance.Project2to3 import MatchCovariance
+    from Module.Optimization.TwoFramePGO.Optimizer import TwoFrame_PGO
+    from Module.Optimization.TwoFramePGO.Graphs import GraphInput
+    from Module.Map import MatchObs, PointNode
+    import pypose as pp
+    from macvo_b200.flowformer_cov import synthetic_state_dict
+
+    cfg = get_cfg()
+    model = build_flowformer(cfg, torch.float32, torch.float32).eval()
+    model.load_state_dict(synthetic_state_dict(0))
+
+    # ---- corr (a3) ------------------------------------------------------------------------
+    for name, (B, H1, W1) in cases.CORR_CASES.items():
+        f1, f2 = cases.corr_inputs(B, H1, W1)
+        out = model.memory_encoder.corr(f1, f2)
+        # keep fixtures small: store a strided sample of the volume + its full checksum
+        rows, cols = cases.corr_sample_index(H1 * W1)
+        save(f"corr_{name}.pt", {"shape": (B, H1, W1), "sample": out.reshape(B, H1 * W1, H1 * W1)[:, rows][:, :, cols].clone(),
+                                 "sum": out.double().sum(), "abs_sum": out.double().abs().sum()})
+
+    # ---- lookup (a5) ----------------------------------------------------------------------
+    for name, (B, H1, W1) in cases.LOOKUP_CASES.items():
+        cost_maps, coords = cases.lookup_inputs(B, H1, W1)
+        out = model.memory_decoder.encode_flow_token(cost_maps, coords.clone())
+        save(f"lookup_{name}.pt", {"shape": (B, H1, W1), "out": out.clone()})
+
+    # ---- network end to end (a2), synthetic weights -----------------------------------------
+    for name, (B, H, W) in cases.NET_CASES.items():
+        img1, img2 = cases.net_inputs(B, H, W)
+        flow, cov = model.inference(img1, img2)
+        save(f"net_{name}.pt", {"shape": (B, H, W), "flow": flow.clone(), "cov": cov.clone()})
+
+    # ---- dense post-processing (a7) ---------------------------------------------------------
+    def stereo(H, W, fx, bl):
+        return StereoData(T_BS=None, K=torch.tensor([[[fx, 0., W / 2], [0., fx, H / 2], [0., 0., 1.]]]),
+                          baseline=torch.tensor([bl]), time_ns=[0], height=H, width=W,
+                          imageL=torch.zeros(1, 3, H, W), imageR=torch.zeros(1, 3, H, W))
+
+    for name, (H, W) in cases.DENSE_CASES.items():
+        est_flow, est_cov = cases.dense_inputs(H, W)
+        frame = stereo(H, W, 320.0, 0.25)
+        for epd in (False, True):
+            d = FlowFormerCovFrontend.inference_2_depth(est_flow[0:1], est_cov[0:1], frame, epd)
+            m = FlowFormerCovFrontend.inference_2_match(est_flow[1:2], est_cov[1:2])
+            save(f"dense_{name}_{int(epd)}.pt", {
+                "shape": (H, W), "depth": d.depth, "disparity": d.disparity, "depth_cov": d.cov,
+                "disparity_uncertainty": d.disparity_uncertainty, "depth_mask": d.mask,
+                "flow": m.flow, "flow_cov": m.cov})
+
+    # ---- selectors (a8, a8'') ---------------------------------------------------------------
+    sel = CovAwareSelector_NoDepth(SimpleNamespace(device="cpu", kernel_size=7, mask_width=32, max_match_cov=100.0))
+    mapsel = MappingPointSelector(SimpleNamespace(max_depth=5.0, max_depth_cov=0.005, mask_width=32))
+    for name, (H, W, num, variant) in cases.SELECTOR_CASES.items():
+        est_flow, est_cov = cases.selector_inputs(H, W, variant)
+        frame = stereo(H, W, 320.0, 0.25)
+        depth = FlowFormerCovFrontend.inference_2_depth(est_flow[0:1], est_cov[0:1], frame, False)
+        match = FlowFormerCovFrontend.inference_2_match(est_flow[1:2], est_cov[1:2])
+        if variant == "masked":
+            match.mask = cases.selector_match_mask(H, W)
+        torch.manual_seed(cases.SELECTOR_RNG_SEED)
+        kp = sel.select_point(frame, num, depth, depth, match)
+        mp = mapsel.select_point(frame, 2000, depth, depth, match)      # second randperm of the frame
+        save(f"selector_{name}.pt", {"shape": (H, W), "num": num, "variant": variant, "kp": kp, "map_kp": mp})
+
+    # ---- covariance model (a10) ---------------------------------------------------------------
+    covm = MatchCovariance(SimpleNamespace(device="cpu", kernel_size=31, match_cov_default=0.25,
+                                           min_depth_cov=0.05, min_flow_cov=0.25))
+    for name, (H, W, K, kind) in cases.COV_CASES.items():
+        kp, depth_map, flow_cov = cases.cov_inputs(H, W, K, kind)
+        frame = stereo(H, W, 320.0, 0.25)
+        dest = IStereoDepth.Output(depth=depth_map)
+        fc = None if flow_cov is None else flow_cov.clone()
+        out = covm.estimate(frame, kp, dest, None, fc)
+        save(f"covariance_{name}.pt", {"shape": (H, W, K), "kind": kind, "out": out,
+                                       "flow_cov_after": fc})
+
+    # ---- two-frame PGO (a13-a16) --------------------------------------------------------------
+    for name, (K, seed) in cases.PGO_CASES.items():
+        c = cases.pgo_inputs(K, seed)
+        obs = MatchObs.init({
+            "pixel1_uv": torch.zeros(K, 2), "pixel2_uv": c["kp2_uv"],
+            "pixel1_d": torch.zeros(K, 1), "pixel2_d": torch.zeros(K, 1),
+            "pixel1_disp": torch.zeros(K, 1), "pixel2_disp": c["kp2_disp"].unsqueeze(-1),
+            "pixel1_disp_cov": torch.zeros(K, 1), "pixel2_disp_cov": c["disp_cov"].unsqueeze(-1),
+            "pixel1_d_cov": torch.zeros(K, 1), "pixel2_d_cov": torch.zeros(K, 1),
+            "pixel1_uv_cov": torch.zeros(K, 3), "pixel2_uv_cov": c["uv_cov"],
+            "obs1_covTc": torch.zeros(K, 3, 3, dtype=torch.double), "obs2_covTc": torch.zeros(K, 3, 3, dtype=torch.double)})
+        pts = PointNode.init({"pos_Tw": c["pos_Tw"], "cov_Tw": torch.zeros(K, 3, 3, dtype=torch.double),
+                              "color": torch.zeros(K, 3, dtype=torch.uint8)})
+        gi = GraphInput(torch.tensor([1]), torch.tensor([0]), pp.SE3(c["init_pose"].unsqueeze(0)),
+                        torch.tensor([c["baseline"]]), obs, pts, c["K"], torch.zeros(K, dtype=torch.long), "cpu")
+        ctx = TwoFrame_PGO.init_context(SimpleNamespace(autodiff=False, graph_type="disp", device="cpu",
+                                                        vectorize=True, parallel=False))
+        # `_optimize` asks for torch.cuda.current_stream() only to hand it to an inactive Timer
+        # (Optimizer.py:83-84); this container has no CUDA driver, so give it a placeholder.
+        _cs, torch.cuda.current_stream = torch.cuda.current_stream, (lambda *a, **k: None)
+        try:
+            _, out = TwoFrame_PGO._optimize(ctx, gi)
+        finally:
+            torch.cuda.current_stream = _cs
+        save(f"pgo_{name}.pt", {"K": K, "seed": seed, "pose": out.motion.detach().as_subclass(torch.Tensor).clone().reshape(7)})
+
+
+if __name__ == "__main__":
+    main()

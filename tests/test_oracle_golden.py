@@ -1,0 +1,128 @@
+"""The CPU oracle (oracle/) pinned against fixtures produced by the reference itself
+(tests/golden/make_golden.py). No GPU, no /root/reference needed."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import covariance as ocov
+from oracle import frontend as ofe
+from oracle import keypoint as okp
+from oracle import pgo as opgo
+from tests.golden import cases
+
+
+@pytest.mark.parametrize("name", list(cases.CORR_CASES))
+def test_corr_volume(golden, name):
+    g = golden(f"corr_{name}.pt")
+    B, H1, W1 = g["shape"]
+    f1, f2 = cases.corr_inputs(B, H1, W1)
+    out = ofe.corr_volume(f1, f2)
+    assert out.shape == (B, 1, H1, W1, H1, W1)
+    rows, cols = cases.corr_sample_index(H1 * W1)
+    sample = out.reshape(B, H1 * W1, H1 * W1)[:, rows][:, :, cols]
+    assert torch.equal(sample, g["sample"])                         # same torch.bmm -> bit-identical
+    assert out.double().sum() == g["sum"]
+
+
+@pytest.mark.parametrize("name", list(cases.LOOKUP_CASES))
+def test_window_lookup(golden, name):
+    g = golden(f"lookup_{name}.pt")
+    B, H1, W1 = g["shape"]
+    cost_maps, coords = cases.lookup_inputs(B, H1, W1)
+    keep = coords.clone()
+    out = ofe.window_lookup(cost_maps, coords)
+    assert torch.equal(coords, keep)                                # the oracle must not mutate its input
+    assert torch.equal(out, g["out"])
+    loops = ofe.window_lookup_loops(cost_maps, coords)
+    torch.testing.assert_close(loops, g["out"], rtol=1e-5, atol=1e-5)
+
+
+def test_window_lookup_axis_quirk():
+    """x-ramp cost map: window axis 0 (the slow output-channel axis) steps in x."""
+    H1, W1 = 10, 10
+    ramp = torch.arange(W1, dtype=torch.float32).view(1, 1, 1, W1).expand(H1 * W1, 1, H1, W1).contiguous()
+    coords = torch.full((1, 2, H1, W1), 4.0)
+    out = ofe.window_lookup(ramp, coords)[0, :, 0, 0].view(9, 9)
+    assert torch.allclose(out[:, 0], torch.arange(0., 9.), atol=1e-5)   # i -> x offset
+    assert torch.allclose(out[4, :], torch.full((9,), 4.0), atol=1e-5)  # j -> y offset (no change on an x-ramp)
+
+
+@pytest.mark.parametrize("epd", [0, 1])
+def test_dense_postproc(golden, epd):
+    g = golden(f"dense_small_{epd}.pt")
+    H, W = g["shape"]
+    flow, cov = cases.dense_inputs(H, W)
+    out = ofe.dense_postproc(flow, cov, torch.tensor([0.25]).item(), torch.tensor(320.0).item(), bool(epd))
+    for k in ("depth", "disparity", "depth_cov", "disparity_uncertainty", "flow", "flow_cov"):
+        assert torch.equal(out[k].nan_to_num(123.0), g[k].nan_to_num(123.0)), k
+    if epd:
+        assert torch.equal(out["depth_mask"], g["depth_mask"])
+    else:
+        assert out["depth_mask"] is None and g["depth_mask"] is None
+
+
+@pytest.mark.parametrize("name", list(cases.SELECTOR_CASES))
+def test_selectors_bit_exact(golden, name):
+    g = golden(f"selector_{name}.pt")
+    H, W = g["shape"]
+    flow, cov = cases.selector_inputs(H, W, g["variant"])
+    d = ofe.dense_postproc(flow, cov, 0.25, 320.0)
+    mm = cases.selector_match_mask(H, W) if g["variant"] == "masked" else None
+    torch.manual_seed(cases.SELECTOR_RNG_SEED)
+    kp = okp.cov_aware_select_nodepth(d["flow_cov"], g["num"], 7, 32, 100.0, mm)
+    mp = okp.mapping_select(d["depth"], d["depth_cov"], 2000, 5.0, 0.005, 32)
+    assert kp.dtype == torch.int64 and torch.equal(kp, g["kp"])
+    assert torch.equal(mp, g["map_kp"])
+
+
+@pytest.mark.parametrize("name", list(cases.COV_CASES))
+def test_match_covariance(golden, name):
+    g = golden(f"covariance_{name}.pt")
+    H, W, K = g["shape"]
+    kp, depth, flow_cov = cases.cov_inputs(H, W, K, g["kind"])
+    out = ocov.match_covariance(kp, depth, flow_cov, 320.0, 320.0, W / 2, H / 2)
+    assert out.dtype == torch.float64 and out.shape == (K, 3, 3)
+    assert torch.equal(out, g["out"])
+    if flow_cov is not None:                                        # in-place clamp of the caller's tensor
+        assert torch.equal(flow_cov, g["flow_cov_after"])
+        assert flow_cov[:, :2].min() >= 0.0625
+
+
+@pytest.mark.parametrize("name", list(cases.PGO_CASES))
+def test_pgo_against_reference_lm(golden, name):
+    """numpy restatement vs the reference's LM_analytic + Analytic_ReprojDisp_TwoFramePGO run on the
+    pypose shim (same control flow => same accept/reject sequence; fp64 rounding only)."""
+    g = golden(f"pgo_{name}.pt")
+    c = cases.pgo_inputs(g["K"], g["seed"])
+    pose = opgo.lm_solve(cases.pgo_graph(c))
+    ref = g["pose"].double().numpy()
+    np.testing.assert_allclose(pose, ref, rtol=1e-9, atol=1e-10)
+    # and it actually solves the problem: close to the generating pose
+    true = c["true_pose"].numpy()
+    assert np.abs(pose[:3] - true[:3]).max() < 0.05 and np.abs(pose[3:] - true[3:]).max() < 0.01
+
+
+def test_pgo_jacobian_finite_difference():
+    c = cases.pgo_inputs(64, 6)
+    g = cases.pgo_graph(c)
+    pose = opgo.se3_exp(np.array([0.3, -0.1, 0.2, 0.05, -0.04, 0.03]))
+    r0, pc = opgo.residual(g, pose)
+    J = opgo.jacobian(g, pose, pc)
+    assert np.all(J[:, :, 6] == 0)
+    for k in range(6):
+        e = np.zeros(7)
+        e[k] = 1e-6
+        rp, _ = opgo.residual(g, opgo.retract(pose, e))
+        rm, _ = opgo.residual(g, opgo.retract(pose, -e))
+        np.testing.assert_allclose((rp - rm) / 2e-6, J[:, :, k], rtol=2e-5, atol=2e-5)
+
+
+def test_se3_group_identities():
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        a, b = opgo.se3_exp(rng.normal(size=6) * 0.5), opgo.se3_exp(rng.normal(size=6) * 0.5)
+        p = rng.normal(size=(4, 3))
+        np.testing.assert_allclose(opgo.se3_act(opgo.se3_mul(a, b), p), opgo.se3_act(a, opgo.se3_act(b, p)), atol=1e-12)
+        np.testing.assert_allclose(opgo.se3_act(opgo.se3_inv(a), opgo.se3_act(a, p)), p, atol=1e-12)
+        np.testing.assert_allclose(opgo.quat_matrix(a[3:]) @ p[0], opgo.quat_rot(a[3:], p[0]), atol=1e-12)
+    np.testing.assert_allclose(opgo.se3_exp(np.zeros(6)), [0, 0, 0, 0, 0, 0, 1])
