@@ -1,0 +1,189 @@
+/*
+ * macvo_b200.h — C ABI of the B200 (sm_100a) hot path for MAC-VO.
+ *
+ * MAC-VO's plugin boundary is a Python class registry, not an FFI; this header is
+ * the thin C layer BELOW the plugin classes (`mac-vo_b200/plugins.py`). Every entry point takes raw
+ * device pointers + sizes + a CUDA stream, enqueues work on that stream (CUDA-graph capturable
+ * unless noted) and returns 0 on success, a negative MACVO_E_* code for bad arguments or a positive
+ * cudaError_t. No ownership is transferred: all buffers are allocated by the caller (PyTorch on the
+ * Python side) and must outlive the stream work. `stream` is a `cudaStream_t` passed as `void*` so
+ * the header needs no CUDA include.
+ *
+ * Each function cites the reference interface (file:line under the MAC-VO tree) it replaces.
+ */
+#ifndef MACVO_B200_H
+#define MACVO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MACVO_OK 0
+#define MACVO_E_ARG (-1)        /* null pointer / non-positive size / unsupported shape            */
+#define MACVO_E_WORKSPACE (-2)  /* workspace too small (query the *_workspace_bytes function)      */
+#define MACVO_E_UNSUPPORTED (-3)/* mode not available for these shapes on this device              */
+#define MACVO_E_DRIVER (-4)     /* driver entry point (cuTensorMapEncodeTiled) could not be loaded */
+
+/* library identification: "macvo_b200 <version> sm_100a" */
+const char* macvo_b200_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a3) all-pairs correlation volume — replaces MemoryEncoder.corr
+ *      Module/Network/FlowFormer/core/encoder.py:256-275 (torch.bmm of the two feature maps).
+ *
+ *   corr[b, i, j] = sum_d fmap1[b, d, i] * fmap2[b, d, j]        (no 1/sqrt(d) scaling)
+ *
+ * fmap1/fmap2: (batch, dim, n) row-major fp32 — exactly the NCHW output of `channel_convertor`
+ * viewed as (B, D, H1*W1). corr: (batch, n, n) row-major fp32 == the contiguous
+ * (B, 1, H1, W1, H1, W1) tensor the cost perceiver and the decoder view.
+ *
+ * mode: MACVO_CORR_SIMT      fp32 FFMA shared-memory tiled kernel (reference-accuracy baseline)
+ *       MACVO_CORR_TC_3XF16  tcgen05 (5th-gen tensor core) kernel: each fp32 operand is split into
+ *                            fp16 hi + lo; hi*hi + hi*lo + lo*hi accumulated in fp32 TMEM
+ *                            (~2^-22 relative product error: fp32-class accuracy)
+ *       MACVO_CORR_TC_1XF16  tcgen05, operands rounded to fp16 once (MACVO_Fast: fp16 encoder)
+ * The tensor-core modes need dim % 64 == 0 and n % 8 == 0 and a workspace of
+ * macvo_corr_workspace_bytes() bytes (device memory, 1024-byte aligned).
+ */
+#define MACVO_CORR_SIMT 0
+#define MACVO_CORR_TC_3XF16 1
+#define MACVO_CORR_TC_1XF16 2
+size_t macvo_corr_workspace_bytes(int batch, int dim, int n, int mode);
+int macvo_corr_build(const float* fmap1, const float* fmap2, float* corr, int batch, int dim, int n, int mode,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a5) 9x9 bilinear window lookup — replaces MemoryDecoder.encode_flow_token
+ *      Module/Network/FlowFormer/core/decoder.py:141-153 (+ bilinear_sampler core/utils.py:26-34,
+ *      the `delta` buffer decoder.py:124-129; grid_sample align_corners=True, zeros padding).
+ *
+ * cost_maps: (batch*h1*w1, h2, w2) fp32 (one map per query pixel), coords: (batch, 2, h1, w1) fp32
+ * [x, y] in cost-map pixels, out: (batch, 81, h1, w1) fp32; out channel i*9+j samples at
+ * (x + i - 4, y + j - 4)  — the reference's transposed window (first axis steps in x).
+ */
+int macvo_corr_lookup(const float* cost_maps, const float* coords, float* out, int batch, int h1, int w1, int h2,
+                      int w2, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a7)+(a8 scoring) fused dense post-processing of one `estimate_pair` + keypoint scoring —
+ *      replaces FlowFormerCovFrontend.inference_2_depth / inference_2_match
+ *      (Module/Frontend/Frontend.py:184-200), disparity_to_depth / disparity_to_depth_cov
+ *      (Module/Frontend/StereoDepth.py:271-282), IMatcher.Output.from_partial_cov
+ *      (Module/Frontend/Matching.py:29-40) and the quality / NMS part of
+ *      CovAwareSelector_NoDepth.select_point (Module/KeypointSelector.py:368-379).
+ *
+ * est_flow, est_cov: (2, 2, h, w) fp32 network output; slot 0 = stereo pair (t2), slot 1 = temporal.
+ * Outputs (any may be NULL to skip): depth, disparity, depth_cov (h*w fp32 each),
+ * depth_mask (h*w uint8, 1 where flow_x <= 0; only written if non-NULL), flow_cov (3, h, w) fp32
+ * = cat(est_cov[1], 0). bl_fx = baseline*fx and bl_fx_sq = (baseline*fx)^2 evaluated in double by
+ * the caller exactly like the reference's Python floats.
+ * Scoring (if score != NULL): quality = cov_uu + cov_vv - 2 cov_uv of `score_cov` (3, h, w) —
+ * pass flow_cov to fuse, or any (3,h,w) map for a standalone selector — written to `score->quality`;
+ * `score->nms` (h*w uint8) = quality == min over the ksize x ksize window and no NaN in it;
+ * NMS survivors' quality values are appended (unordered) to score->cand_vals, count in *score->n_cand
+ * (caller zeroes it). All pointers device memory.
+ */
+typedef struct {
+    const float* score_cov; /* (3,h,w) or NULL = use the freshly written flow_cov */
+    float* quality;         /* h*w */
+    uint8_t* nms;           /* h*w */
+    float* cand_vals;       /* capacity h*w */
+    int* n_cand;            /* 1 */
+    int ksize;              /* odd, <= 15 */
+} macvo_score_t;
+int macvo_dense_postproc(const float* est_flow, const float* est_cov, int h, int w, double bl_fx, double bl_fx_sq,
+                         float* depth, float* disparity, float* depth_cov, uint8_t* depth_mask, float* flow_cov,
+                         const macvo_score_t* score, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a8) candidate selection — the rest of CovAwareSelector_NoDepth.select_point
+ *      (Module/KeypointSelector.py:381-400): threshold = min(max_match_cov, 1.5 * lower-median of
+ *      the NMS survivors), mask = nms & border & quality < threshold [& extra_mask], then the
+ *      row-major ordered list of candidates (== torch.nonzero order).
+ * cand_idx: capacity h*w int32 (linear pixel index row*w+col, ascending); *n_out: number written;
+ * *thresh_out: the fp32 threshold; *status: 0 ok, 1 = no NMS survivor (reference raises).
+ * workspace: macvo_select_workspace_bytes(h, w) bytes.
+ */
+size_t macvo_select_workspace_bytes(int h, int w);
+int macvo_select_candidates(const float* quality, const uint8_t* nms, const float* cand_vals, const int* n_cand,
+                            const uint8_t* extra_mask, int h, int w, int mask_width, double max_match_cov,
+                            int* cand_idx, int* n_out, float* thresh_out, int* status, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* (a8'') MappingPointSelector.select_point candidates (Module/KeypointSelector.py:87-97):
+ *      depth < max_depth & depth_cov < max_depth_cov & border, row-major ordered. */
+int macvo_select_mapping_candidates(const float* depth, const float* depth_cov, int h, int w, int mask_width,
+                                    float max_depth, float max_depth_cov, int* cand_idx, int* n_out,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* pixels[k] = (u, v) = (cand_idx[perm[k]] % w, cand_idx[perm[k]] / w) as int64 — the
+ * `selected_points[perm][..., 2:].roll(1)` gather (KeypointSelector.py:404-405). */
+int macvo_gather_pixels(const int* cand_idx, const int64_t* perm, int k, int w, int64_t* pixels_uv, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a9) IFrontend.retrieve_pixels (Module/Frontend/Frontend.py:104-118): out[c, k] =
+ *      map[0, c, (long) v_k, (long) u_k]. kp is (k, 2) [u, v], int64 (kp_is_int64 = 1) or fp32.
+ */
+int macvo_retrieve_pixels(const void* kp, int kp_is_int64, int k, const float* map, int channels, int h, int w,
+                          float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a10)+(a11) observation covariance — replaces MatchCovariance.estimate
+ *      (Module/Covariance/Project2to3.py:124-182), gaussain_full_kernels (Utility/Math.py:44-63),
+ *      Covariance_2to3_full (Project2to3.py:377-424); optionally pixel2point_NED (Utility/Point.py:15).
+ *
+ * kp (k,2) [u,v] int64 or fp32; depth (h,w) fp32; flow_cov (k,3) fp32 [uu, vv, uv], CLAMPED IN
+ * PLACE to >= min_flow_cov^2 on its first two columns (reference side effect), or NULL = use
+ * match_cov_default. out_cov (k,3,3) float64 (NED order z,x,y); out_point (k,3) fp32 NED point of
+ * the CENTRE pixel depth (may be NULL); *status != 0 if a patch leaves the image (reference raises).
+ */
+int macvo_match_covariance(const void* kp, int kp_is_int64, int k, const float* depth, int h, int w, float* flow_cov,
+                           float fx, float fy, float cx, float cy, int kernel_size, float min_flow_cov,
+                           float min_depth_cov, float match_cov_default, double* out_cov, float* out_point,
+                           int* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a14)+(a15) two-frame pose-graph optimisation — replaces TwoFrame_PGO._optimize
+ *      (Module/Optimization/TwoFramePGO/Optimizer.py:82-102) = LM_analytic.step loop
+ *      (Module/Optimization/PyposeOptimizers.py:160-194) over Analytic_ReprojDisp_TwoFramePGO
+ *      (Module/Optimization/TwoFramePGO/Graphs.py:121-148, 201-230) with Huber(0.1) + FastTriggs,
+ *      PINV, TrustRegion(radius 1e3), StopOnPlateau(10, patience 2, 1e-5).
+ *
+ * One persistent launch runs the whole LM loop on the device (a cluster of `cluster` CTAs, 1..8;
+ * 0 = choose from k). Inputs fp64 (the reference promotes its fp32 buffers with .to(torch.double)):
+ * pos_Tw (k,3), kp2_uv (k,2), kp2_disp (k), uv_cov (k,3) [uu,vv,uv], disp_cov (k);
+ * intr = {fx, fy, cx, cy, baseline}; pose_io (7) [t, q_xyzw]: initial pose in, optimised pose out.
+ * stats (8 doubles, may be NULL): {steps, loss evaluations, final loss, initial loss, last reject count,
+ * final damping, 0, 0}.
+ */
+typedef struct {
+    int max_steps;      /* 10   */
+    int patience;       /* 2    */
+    int max_reject;     /* 16   */
+    int cluster;        /* 0 = auto */
+    double decreasing;  /* 1e-5 */
+    double huber_delta; /* 0.1  */
+    double radius;      /* 1e3  */
+    double diag_min;    /* 1e-6 */
+    double diag_max;    /* 1e32 */
+} macvo_pgo_params_t;
+int macvo_pgo_solve(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp, const double* uv_cov,
+                    const double* disp_cov, int k, const double* intr, double* pose_io,
+                    const macvo_pgo_params_t* params, double* stats, void* stream);
+
+/* One evaluation of the packed normal-equation accumulator for a SHARD of residual blocks
+ * (multi-GPU: each rank reduces its blocks, ranks all-reduce the 55 doubles):
+ * acc = [A upper 6x6 (21) | b (6) | G = Js^T Js upper (21) | h = Js^T Rs (6) | robust loss (1)].
+ */
+#define MACVO_PGO_ACC 55
+int macvo_pgo_accumulate(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp, const double* uv_cov,
+                         const double* disp_cov, int k, const double* intr, const double* pose, double huber_delta,
+                         double* acc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACVO_B200_H */

@@ -1,0 +1,411 @@
+// (a3) all-pairs correlation volume on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a.
+//
+// Replaces MemoryEncoder.corr (Module/Network/FlowFormer/core/encoder.py:256-275; one cuBLAS bmm in the
+// reference):  corr[b, i, j] = sum_d f1[b, d, i] * f2[b, d, j],  output (B, N, N) fp32 — 184 MB per
+// 640x480 `estimate_pair`, write-dominated: the roofline is HBM write bandwidth PROVIDED the K = 256
+// contraction runs on tensor cores (116 flop/B).
+//
+// fp32-class accuracy on fp16 tensor cores (MACVO_CORR_TC_3XF16): every operand is split
+//     x = hi + lo,  hi = fp16(x),  lo = fp16(x - hi)          (|x - hi - lo| <~ 2^-22 |x|)
+// and  hi*hi + hi*lo + lo*hi  is accumulated in fp32 in TMEM. MACVO_CORR_TC_1XF16 keeps only hi*hi
+// (exact for the MACVO_Fast configuration whose encoder already emits fp16 features).
+//
+// Two kernels:
+//   1. split_transpose_kernel   (B, D, N) fp32  ->  hi, lo  (B, N, D) fp16   (K-major operands)
+//   2. corr_tc_kernel           persistent, warp specialised, one CTA per SM:
+//        warp 0      TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) of 64-wide K slices into a
+//                                   multi-stage shared-memory ring, mbarrier expect_tx
+//        warp 1      MMA issuer   : one elected thread issues tcgen05.mma.kind::f16 (128 x 128 x 16),
+//                                   tcgen05.commit releases smem stages / publishes the accumulator
+//        warps 2..5  epilogue     : tcgen05.ld TMEM -> registers -> swizzled smem staging -> TMA store
+//      double-buffered TMEM accumulators (2 x 128 columns) overlap the epilogue of tile t with the MMAs
+//      of tile t+1; M/N edges are handled by TMA (zero fill on load, clipping on store).
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+
+constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 64, UMMA_K = 16;
+constexpr int STAGES = 3;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB (one of hi / lo)
+constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;          // 16 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // hi+lo of A and B: 64 KB
+constexpr int EPI_COLS = 32;                                 // fp32 columns per staged chunk (128 B rows)
+constexpr int EPI_WARP_BYTES = 32 * EPI_COLS * 4;            // 4 KB: 32 rows x 128 B
+constexpr int EPI_BUFS = 2;
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int SMEM_EPI_BYTES = NUM_EPI_WARPS * EPI_BUFS * EPI_WARP_BYTES;   // 32 KB
+constexpr int SMEM_BAR_BYTES = 256;
+constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + SMEM_EPI_BYTES + SMEM_BAR_BYTES + 1024;  // + alignment slack
+constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int TMEM_COLS = 256;                               // 2 accumulator stages x 128 fp32 columns
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();          // ~2 s
+    }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .b32 r;\n\t.reg .pred p;\n\t"
+        "elect.sync r|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout = 2
+// rows are 128 B (64 fp16) apart, 8-row groups (one swizzle atom) 1024 B apart.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                  // LBO (unused for swizzled K-major; canonical value)
+    d |= (uint64_t)(1024 >> 4) << 32;        // SBO
+    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- kernel 1: fp32 (B, D, N) -> fp16 hi / lo (B, N, D) --------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, int dim, int n) {
+    __shared__ float tile[64][33];                                   // [d][token]
+    const int b = blockIdx.z, d0 = blockIdx.y * 64, n0 = blockIdx.x * 32;
+    const float* s = src + (long long)b * dim * n;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 64; r += 8) {
+        const int d = d0 + r, t = n0 + tx;
+        tile[r][tx] = (d < dim && t < n) ? s[(long long)d * n + t] : 0.f;
+    }
+    __syncthreads();
+    // write: token-major rows, 64 consecutive d per row -> lanes cover d pairs (half2, 128 B per warp row)
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int t = n0 + r, d = d0 + 2 * tx;
+        if (t < n && d + 1 < dim + 1) {
+            const float x0 = tile[2 * tx][r], x1 = tile[2 * tx + 1][r];
+            const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+            const long long o = ((long long)b * n + t) * dim + d;
+            *reinterpret_cast<__half2*>(hi + o) = __halves2half2(h0, h1);
+            if (lo) {
+                const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+                *reinterpret_cast<__half2*>(lo + o) = __halves2half2(l0, l1);
+            }
+        }
+    }
+}
+
+// ---- kernel 2 -----------------------------------------------------------------------------------------------
+struct TileCoord { int b, m, n; };
+
+__device__ __forceinline__ TileCoord tile_coord(int t, int mt, int nt) {
+    TileCoord c;
+    c.n = t % nt;
+    const int r = t / nt;
+    c.m = r % mt;
+    c.b = r / mt;
+    return c;
+}
+
+template <int PASSES>   // 3: hi*hi + hi*lo + lo*hi     1: hi*hi
+__global__ void __launch_bounds__(THREADS, 1)
+corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ CUtensorMap map_out, int batch, int n, int dim) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + SMEM_EPI_BYTES);
+    // barrier slots: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * STAGES, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = ceil_div(n, BLOCK_M), nt = ceil_div(n, BLOCK_N), kblocks = dim / BLOCK_K;
+    const int total_tiles = batch * mt * nt;
+    // static contiguous tile ranges (n fastest: consecutive tiles of a CTA share the A rows -> L2 locality)
+    const int t_begin = (int)((long long)total_tiles * blockIdx.x / gridDim.x);
+    const int t_end = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, NUM_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_base_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const TileCoord tc = tile_coord(t, mt, nt);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t full = bar_full + 8 * stage;
+                    mbar_expect_tx(full, PASSES == 3 ? STAGE_BYTES : (A_TILE_BYTES + B_TILE_BYTES));
+                    tma_load_3d(sa, &map_a_hi, full, kb * BLOCK_K, tc.m * BLOCK_M, tc.b);
+                    tma_load_3d(sa + 2 * A_TILE_BYTES, &map_b_hi, full, kb * BLOCK_K, tc.n * BLOCK_N, tc.b);
+                    if (PASSES == 3) {
+                        tma_load_3d(sa + A_TILE_BYTES, &map_a_lo, full, kb * BLOCK_K, tc.m * BLOCK_M, tc.b);
+                        tma_load_3d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, full, kb * BLOCK_K, tc.n * BLOCK_N, tc.b);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);              // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + A_TILE_BYTES);
+                    const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES);
+                    const uint64_t b_lo = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);     // +32 B per K step inside the atom
+                        if (PASSES == 3) {   // small cross terms first, the dominant hi*hi product last
+                            umma_f16_ss(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
+                            umma_f16_ss(tmem_d, a_hi + koff, b_lo + koff, idesc, 1u);
+                            umma_f16_ss(tmem_d, a_hi + koff, b_hi + koff, idesc, 1u);
+                        } else {
+                            umma_f16_ss(tmem_d, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+                        }
+                    }
+                    umma_commit(bar_empty + 8 * stage);                  // smem stage free once these MMAs retire
+                    if (kb == kblocks - 1) umma_commit(bar_tfull + 8 * acc);   // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> smem -> TMA store =====================
+        const int quarter = warp & 3;                                     // TMEM lanes [32*quarter, +32)
+        const int ew = warp - 2;                                          // staging slot of this warp
+        uint8_t* stage_base = smem_epi + ew * EPI_BUFS * EPI_WARP_BYTES;
+        int acc = 0; uint32_t acc_phase = 0;
+        int buf = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            const TileCoord tc = tile_coord(t, mt, nt);
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / EPI_COLS; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * EPI_COLS, r);
+                tmem_ld_wait();
+                if (c == BLOCK_N / EPI_COLS - 1) {                        // accumulator fully read: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                }
+                // the staging buffer we are about to overwrite must have been read by its TMA store
+                if (lane == 0) tma_store_wait_read<EPI_BUFS - 1>();
+                __syncwarp();
+                uint8_t* sb = stage_base + buf * EPI_WARP_BYTES;
+                // row = lane (128 B), 16-byte chunk j stored at j ^ (row & 7)  (SWIZZLE_128B, conflict free)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 v = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    *reinterpret_cast<uint4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&map_out, smem_u32(sb), tc.n * BLOCK_N + c * EPI_COLS, tc.m * BLOCK_M + quarter * 32, tc.b);
+                    tma_store_commit();
+                }
+                buf ^= 1;
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+// 3-D tensor map over a (batch, rows, inner) row-major array; box = (1, box_rows, box_inner), 128B swizzle
+bool make_map_3d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, void* base, uint64_t inner, uint64_t rows,
+                 uint64_t batch, uint32_t box_inner, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {inner, rows, batch};
+    cuuint64_t strides[2] = {inner * elem_bytes, inner * rows * elem_bytes};
+    cuuint32_t box[3] = {box_inner, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t operand_bytes(int batch, int dim, int n) { return ((size_t)batch * n * dim * 2 + 1023) / 1024 * 1024; }
+
+}  // namespace
+
+size_t macvo_corr_tc_workspace_bytes(int batch, int dim, int n, int passes) {
+    return operand_bytes(batch, dim, n) * (passes == 3 ? 4 : 2);
+}
+
+int macvo_corr_build_tc(const float* f1, const float* f2, float* corr, int batch, int dim, int n, int passes,
+                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (dim % BLOCK_K != 0 || n % 8 != 0) return MACVO_E_UNSUPPORTED;
+    if (!workspace || workspace_bytes < macvo_corr_tc_workspace_bytes(batch, dim, n, passes)) return MACVO_E_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) || (reinterpret_cast<uintptr_t>(corr) & 15)) return MACVO_E_ARG;
+    const size_t ob = operand_bytes(batch, dim, n);
+    __half* a_hi = reinterpret_cast<__half*>(workspace);
+    __half* b_hi = reinterpret_cast<__half*>(static_cast<char*>(workspace) + ob);
+    __half* a_lo = passes == 3 ? reinterpret_cast<__half*>(static_cast<char*>(workspace) + 2 * ob) : nullptr;
+    __half* b_lo = passes == 3 ? reinterpret_cast<__half*>(static_cast<char*>(workspace) + 3 * ob) : nullptr;
+
+    dim3 pgrid(ceil_div(n, 32), ceil_div(dim, 64), batch);
+    split_transpose_kernel<<<pgrid, 256, 0, st>>>(f1, a_hi, a_lo, dim, n);
+    MACVO_LAUNCH_CHECK();
+    split_transpose_kernel<<<pgrid, 256, 0, st>>>(f2, b_hi, b_lo, dim, n);
+    MACVO_LAUNCH_CHECK();
+
+    CUtensorMap m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out;
+    bool ok = make_map_3d(&m_a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a_hi, dim, n, batch, BLOCK_K, BLOCK_M);
+    ok = ok && make_map_3d(&m_b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_hi, dim, n, batch, BLOCK_K, BLOCK_N);
+    ok = ok && make_map_3d(&m_a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, passes == 3 ? a_lo : a_hi, dim, n, batch, BLOCK_K, BLOCK_M);
+    ok = ok && make_map_3d(&m_b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, passes == 3 ? b_lo : b_hi, dim, n, batch, BLOCK_K, BLOCK_N);
+    ok = ok && make_map_3d(&m_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, corr, n, n, batch, EPI_COLS, 32);
+    if (!ok) return MACVO_E_DRIVER;
+
+    int dev = 0, sms = 0;
+    MACVO_CUDA_TRY(cudaGetDevice(&dev));
+    MACVO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int total_tiles = batch * ceil_div(n, BLOCK_M) * ceil_div(n, BLOCK_N);
+    const int grid = total_tiles < sms ? total_tiles : sms;
+    if (passes == 3) {
+        MACVO_CUDA_TRY(cudaFuncSetAttribute(corr_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        corr_tc_kernel<3><<<grid, THREADS, SMEM_TOTAL, st>>>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, batch, n, dim);
+    } else {
+        MACVO_CUDA_TRY(cudaFuncSetAttribute(corr_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        corr_tc_kernel<1><<<grid, THREADS, SMEM_TOTAL, st>>>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, batch, n, dim);
+    }
+    MACVO_LAUNCH_CHECK();
+    return MACVO_OK;
+}

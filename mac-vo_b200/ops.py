@@ -1,0 +1,376 @@
+"""ctypes binding of libmacvo_b200.so (the C ABI in include/macvo_b200.h) for torch CUDA tensors.
+
+PyTorch only supplies device memory and the current stream here; every operator below is a
+hand-written sm_100a kernel. There is NO CPU / eager fallback: if the library is missing or the
+tensors are not on a CUDA device the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+from .build import LIB_PATH
+
+Tensor = torch.Tensor
+
+CORR_SIMT, CORR_TC_3XF16, CORR_TC_1XF16 = 0, 1, 2
+PGO_ACC = 55
+
+_lib = None
+_lock = threading.Lock()
+
+
+class MacvoB200Error(RuntimeError):
+    pass
+
+
+class _ScoreT(C.Structure):
+    _fields_ = [("score_cov", C.c_void_p), ("quality", C.c_void_p), ("nms", C.c_void_p),
+                ("cand_vals", C.c_void_p), ("n_cand", C.c_void_p), ("ksize", C.c_int)]
+
+
+class _PgoParams(C.Structure):
+    _fields_ = [("max_steps", C.c_int), ("patience", C.c_int), ("max_reject", C.c_int), ("cluster", C.c_int),
+                ("decreasing", C.c_double), ("huber_delta", C.c_double), ("radius", C.c_double),
+                ("diag_min", C.c_double), ("diag_max", C.c_double)]
+
+
+EXPORTS = {
+    "macvo_b200_version": (C.c_char_p, []),
+    "macvo_corr_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "macvo_corr_build": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "macvo_corr_lookup": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
+    "macvo_dense_postproc": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_double] * 2 + [C.c_void_p] * 5
+                             + [C.POINTER(_ScoreT), C.c_void_p]),
+    "macvo_select_workspace_bytes": (C.c_size_t, [C.c_int] * 2),
+    "macvo_select_candidates": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_double] + [C.c_void_p] * 5
+                                + [C.c_size_t, C.c_void_p]),
+    "macvo_select_mapping_candidates": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 3 + [C.c_float] * 2
+                                        + [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p]),
+    "macvo_gather_pixels": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p] * 2),
+    "macvo_retrieve_pixels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p] * 2),
+    "macvo_match_covariance": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+                               + [C.c_float] * 4 + [C.c_int] + [C.c_float] * 3 + [C.c_void_p] * 4),
+    "macvo_pgo_solve": (C.c_int, [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2 + [C.POINTER(_PgoParams)]
+                        + [C.c_void_p] * 2),
+    "macvo_pgo_accumulate": (C.c_int, [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2 + [C.c_double]
+                             + [C.c_void_p] * 2),
+}
+
+
+def load_library(path: str | None = None):
+    """dlopen the C-ABI library (no CUDA call is made) and bind every symbol of include/macvo_b200.h."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = path or os.environ.get("MACVO_B200_LIB", LIB_PATH)
+        if not os.path.exists(path):
+            raise MacvoB200Error(f"{path} not found: build it first with `python -m macvo_b200.build` "
+                                 "(or __graft_entry__.build()); there is no CPU fallback")
+        lib = C.CDLL(path)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)       # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+        return lib
+
+
+def version() -> str:
+    return load_library().macvo_b200_version().decode()
+
+
+def _check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    names = {-1: "MACVO_E_ARG", -2: "MACVO_E_WORKSPACE", -3: "MACVO_E_UNSUPPORTED", -4: "MACVO_E_DRIVER"}
+    raise MacvoB200Error(f"{what} failed: {names.get(rc, f'cudaError {rc}')}")
+
+
+def _dev(t: Tensor, dtype, what: str) -> Tensor:
+    if not isinstance(t, Tensor) or not t.is_cuda:
+        raise MacvoB200Error(f"{what}: expected a CUDA tensor (the B200 path has no CPU fallback), got "
+                             f"{getattr(t, 'device', type(t))}")
+    if t.dtype != dtype:
+        raise MacvoB200Error(f"{what}: expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+_ws: dict = {}
+
+
+def _workspace(key, nbytes: int, device) -> Tensor:
+    """Grow-only scratch buffers (allocated outside CUDA-graph capture by the warm-up runs)."""
+    k = (key, str(device))
+    buf = _ws.get(k)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1024) + 1024, dtype=torch.uint8, device=device)
+        _ws[k] = buf
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + max(nbytes, 1)]
+
+
+# ------------------------------------------------------------------------------------------------
+# (a3) correlation volume
+# ------------------------------------------------------------------------------------------------
+def default_corr_mode(dim: int, n: int) -> int:
+    env = os.environ.get("MACVO_B200_CORR_MODE")
+    if env is not None:
+        return {"simt": CORR_SIMT, "tc3": CORR_TC_3XF16, "tc1": CORR_TC_1XF16}[env]
+    return CORR_TC_3XF16 if (dim % 64 == 0 and n % 8 == 0) else CORR_SIMT
+
+
+def corr_build(fmap1: Tensor, fmap2: Tensor, mode: int | None = None) -> Tensor:
+    """(B,D,H,W) x2 -> (B,1,H,W,H,W) fp32, `MemoryEncoder.corr` (encoder.py:256-275).
+
+    fp16 feature maps (MACVO_Fast) use the single-pass tensor-core mode, which is exact for them."""
+    lib = load_library()
+    B, D, H, W = fmap1.shape
+    n = H * W
+    if mode is None:
+        mode = default_corr_mode(D, n)
+        if fmap1.dtype == torch.float16 and mode == CORR_TC_3XF16:
+            mode = CORR_TC_1XF16
+    f1 = _dev(fmap1.float() if fmap1.dtype != torch.float32 else fmap1, torch.float32, "corr_build fmap1")
+    f2 = _dev(fmap2.float() if fmap2.dtype != torch.float32 else fmap2, torch.float32, "corr_build fmap2")
+    out = torch.empty((B, 1, H, W, H, W), dtype=torch.float32, device=f1.device)
+    nbytes = lib.macvo_corr_workspace_bytes(B, D, n, mode)
+    ws = _workspace("corr", nbytes, f1.device) if nbytes else None
+    rc = lib.macvo_corr_build(f1.data_ptr(), f2.data_ptr(), out.data_ptr(), B, D, n, mode,
+                              ws.data_ptr() if ws is not None else None, nbytes, _stream())
+    _check(rc, "macvo_corr_build")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# (a5) window lookup
+# ------------------------------------------------------------------------------------------------
+def corr_lookup(cost_maps: Tensor, coords: Tensor) -> Tensor:
+    """cost_maps (B*H1*W1, 1, H2, W2) fp32, coords (B,2,H1,W1) fp32 -> (B,81,H1,W1) fp32 (decoder.py:141-153)."""
+    lib = load_library()
+    cm = _dev(cost_maps, torch.float32, "corr_lookup cost_maps")
+    co = _dev(coords, torch.float32, "corr_lookup coords")
+    B, _, H1, W1 = co.shape
+    H2, W2 = cm.shape[-2:]
+    assert cm.shape[0] == B * H1 * W1, "one cost map per query pixel"
+    out = torch.empty((B, 81, H1, W1), dtype=torch.float32, device=cm.device)
+    _check(lib.macvo_corr_lookup(cm.data_ptr(), co.data_ptr(), out.data_ptr(), B, H1, W1, H2, W2, _stream()),
+           "macvo_corr_lookup")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# (a7) + (a8)
+# ------------------------------------------------------------------------------------------------
+class ScoreBuffers:
+    """Device buffers filled by the fused scoring pass; consumed by `select_candidates`."""
+
+    def __init__(self, h: int, w: int, device, ksize: int):
+        self.h, self.w, self.ksize = h, w, ksize
+        self.quality = torch.empty((h, w), dtype=torch.float32, device=device)
+        self.nms = torch.empty((h, w), dtype=torch.uint8, device=device)
+        self.cand_vals = torch.empty((h * w,), dtype=torch.float32, device=device)
+        self.n_cand = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.source_ptr = 0        # data_ptr of the (3,h,w) covariance map these scores belong to
+        self.source_version = -1
+
+    def struct(self, score_cov_ptr) -> _ScoreT:
+        return _ScoreT(score_cov_ptr, self.quality.data_ptr(), self.nms.data_ptr(), self.cand_vals.data_ptr(),
+                       self.n_cand.data_ptr(), self.ksize)
+
+
+def dense_postproc(est_flow: Tensor, est_cov: Tensor, bl_fx: float, enforce_positive_disparity: bool = False,
+                   score: ScoreBuffers | None = None) -> dict:
+    """One `estimate_pair` of dense maps (Frontend.py:184-200, 291-299) + optional fused keypoint scoring.
+
+    est_flow / est_cov: (2,2,H,W) fp32. bl_fx = baseline*fx as a python float (double), like the reference."""
+    lib = load_library()
+    fl = _dev(est_flow, torch.float32, "dense_postproc est_flow")
+    cv = _dev(est_cov, torch.float32, "dense_postproc est_cov")
+    assert fl.shape[:2] == (2, 2) and cv.shape == fl.shape
+    H, W = fl.shape[-2:]
+    dev = fl.device
+    depth = torch.empty((1, 1, H, W), dtype=torch.float32, device=dev)
+    disparity = torch.empty_like(depth)
+    depth_cov = torch.empty_like(depth)
+    mask = torch.empty((1, 1, H, W), dtype=torch.uint8, device=dev) if enforce_positive_disparity else None
+    flow_cov = torch.empty((1, 3, H, W), dtype=torch.float32, device=dev)
+    st = None
+    if score is not None:
+        score.n_cand.zero_()
+        st = score.struct(None)
+        score.source_ptr, score.source_version = flow_cov.data_ptr(), flow_cov._version
+    rc = lib.macvo_dense_postproc(fl.data_ptr(), cv.data_ptr(), H, W, float(bl_fx), float(bl_fx) ** 2,
+                                  depth.data_ptr(), disparity.data_ptr(), depth_cov.data_ptr(),
+                                  mask.data_ptr() if mask is not None else None, flow_cov.data_ptr(),
+                                  C.byref(st) if st is not None else None, _stream())
+    _check(rc, "macvo_dense_postproc")
+    return {"depth": depth, "disparity": disparity, "depth_cov": depth_cov,
+            "disparity_uncertainty": cv[0:1, :1], "depth_mask": mask.bool() if mask is not None else None,
+            "flow": fl[1:2], "flow_cov": flow_cov}
+
+
+def score_only(match_cov: Tensor, score: ScoreBuffers) -> None:
+    """Quality / NMS scoring of an arbitrary (1,3,H,W) covariance map (standalone selector plugin)."""
+    lib = load_library()
+    mc = _dev(match_cov, torch.float32, "score_only match_cov")
+    H, W = mc.shape[-2:]
+    score.n_cand.zero_()
+    st = score.struct(mc.data_ptr())
+    rc = lib.macvo_dense_postproc(None, None, H, W, 0.0, 0.0, None, None, None, None, None, C.byref(st), _stream())
+    _check(rc, "macvo_dense_postproc(score)")
+    score.source_ptr, score.source_version = match_cov.data_ptr(), match_cov._version
+
+
+class CandidateList:
+    def __init__(self, h: int, w: int, device):
+        self.idx = torch.empty((h * w,), dtype=torch.int32, device=device)
+        self.n = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.thresh = torch.zeros((1,), dtype=torch.float32, device=device)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.host = torch.zeros((2,), dtype=torch.int32).pin_memory()      # [n, status]
+        self.w = w
+
+
+def select_candidates(score: ScoreBuffers, mask_width: int, max_match_cov: float, extra_mask: Tensor | None,
+                      out: CandidateList) -> None:
+    lib = load_library()
+    h, w = score.h, score.w
+    nbytes = lib.macvo_select_workspace_bytes(h, w)
+    ws = _workspace("select", nbytes, score.quality.device)
+    em = None
+    if extra_mask is not None:
+        em = _dev(extra_mask.to(torch.uint8) if extra_mask.dtype != torch.uint8 else extra_mask, torch.uint8, "extra_mask")
+    rc = lib.macvo_select_candidates(score.quality.data_ptr(), score.nms.data_ptr(), score.cand_vals.data_ptr(),
+                                     score.n_cand.data_ptr(), em.data_ptr() if em is not None else None, h, w,
+                                     int(mask_width), float(max_match_cov), out.idx.data_ptr(), out.n.data_ptr(),
+                                     out.thresh.data_ptr(), out.status.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    _check(rc, "macvo_select_candidates")
+
+
+def select_mapping_candidates(depth: Tensor, depth_cov: Tensor, mask_width: int, max_depth: float,
+                              max_depth_cov: float, out: CandidateList) -> None:
+    lib = load_library()
+    d = _dev(depth, torch.float32, "mapping depth")
+    dc = _dev(depth_cov, torch.float32, "mapping depth_cov")
+    h, w = d.shape[-2:]
+    nbytes = lib.macvo_select_workspace_bytes(h, w)
+    ws = _workspace("select", nbytes, d.device)
+    out.status.zero_()
+    rc = lib.macvo_select_mapping_candidates(d.data_ptr(), dc.data_ptr(), h, w, int(mask_width), float(max_depth),
+                                             float(max_depth_cov), out.idx.data_ptr(), out.n.data_ptr(),
+                                             ws.data_ptr(), nbytes, _stream())
+    _check(rc, "macvo_select_mapping_candidates")
+
+
+def sample_candidates(cand: CandidateList, num_point: int) -> Tensor:
+    """`perm = torch.randperm(n)[:numPoint]` on the CPU default generator (KeypointSelector.py:404) — the one
+    host round trip of the selector (the reference has two: `.item()` and `nonzero`)."""
+    lib = load_library()
+    dev = cand.idx.device
+    cand.host[0:1].copy_(cand.n, non_blocking=True)
+    cand.host[1:2].copy_(cand.status, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    n, status = int(cand.host[0]), int(cand.host[1])
+    if status != 0:
+        raise RuntimeError("median() input tensor cannot be empty: no NMS survivor in the covariance map")
+    perm = torch.randperm(n)[:num_point]
+    k = perm.numel()
+    out = torch.empty((k, 2), dtype=torch.int64, device=dev)
+    if k:
+        perm_d = perm.pin_memory().to(dev, non_blocking=True)
+        _check(lib.macvo_gather_pixels(cand.idx.data_ptr(), perm_d.data_ptr(), k, cand.w, out.data_ptr(), _stream()),
+               "macvo_gather_pixels")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# (a9) retrieve_pixels
+# ------------------------------------------------------------------------------------------------
+def retrieve_pixels(pixel_uv: Tensor, scalar_map: Tensor) -> Tensor:
+    lib = load_library()
+    sm = _dev(scalar_map, torch.float32, "retrieve_pixels map")
+    if pixel_uv.dtype not in (torch.int64, torch.float32):
+        pixel_uv = pixel_uv.float()
+    kp = _dev(pixel_uv, pixel_uv.dtype, "retrieve_pixels kp")
+    Cc, H, W = sm.shape[-3:]
+    K = kp.shape[0]
+    out = torch.empty((Cc, K), dtype=torch.float32, device=sm.device)
+    _check(lib.macvo_retrieve_pixels(kp.data_ptr(), int(kp.dtype == torch.int64), K, sm.data_ptr(), Cc, H, W,
+                                     out.data_ptr(), _stream()), "macvo_retrieve_pixels")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# (a10)
+# ------------------------------------------------------------------------------------------------
+def match_covariance(kp: Tensor, depth_map: Tensor, flow_cov: Tensor | None, fx: float, fy: float, cx: float,
+                     cy: float, kernel_size: int = 31, min_flow_cov: float = 0.25, min_depth_cov: float = 0.05,
+                     match_cov_default: float = 0.25, want_point: bool = False):
+    """-> (cov (K,3,3) float64 on the device, point (K,3) fp32 or None, status int32 tensor)."""
+    lib = load_library()
+    dm = _dev(depth_map, torch.float32, "match_covariance depth")
+    if kp.dtype not in (torch.int64, torch.float32):
+        kp = kp.float()
+    kpd = _dev(kp, kp.dtype, "match_covariance kp")
+    K = kpd.shape[0]
+    H, W = dm.shape[-2:]
+    fc = None
+    if flow_cov is not None:
+        if not (flow_cov.is_cuda and flow_cov.dtype == torch.float32 and flow_cov.is_contiguous()):
+            raise MacvoB200Error("match_covariance: flow_cov must be a contiguous fp32 CUDA tensor (clamped in place)")
+        fc = flow_cov
+    cov = torch.empty((K, 3, 3), dtype=torch.float64, device=dm.device)
+    pt = torch.empty((K, 3), dtype=torch.float32, device=dm.device) if want_point else None
+    status = torch.zeros((1,), dtype=torch.int32, device=dm.device)
+    rc = lib.macvo_match_covariance(kpd.data_ptr(), int(kpd.dtype == torch.int64), K, dm.data_ptr(), H, W,
+                                    fc.data_ptr() if fc is not None else None, fx, fy, cx, cy, kernel_size,
+                                    min_flow_cov, min_depth_cov, match_cov_default, cov.data_ptr(),
+                                    pt.data_ptr() if pt is not None else None, status.data_ptr(), _stream())
+    _check(rc, "macvo_match_covariance")
+    return cov, pt, status
+
+
+# ------------------------------------------------------------------------------------------------
+# (a14) + (a15)
+# ------------------------------------------------------------------------------------------------
+def _pgo_params(max_steps=10, patience=2, max_reject=16, cluster=0, decreasing=1e-5, huber_delta=0.1, radius=1e3,
+                diag_min=1e-6, diag_max=1e32) -> _PgoParams:
+    return _PgoParams(max_steps, patience, max_reject, cluster, decreasing, huber_delta, radius, diag_min, diag_max)
+
+
+def pgo_solve(pos_Tw: Tensor, kp2_uv: Tensor, kp2_disp: Tensor, uv_cov: Tensor, disp_cov: Tensor,
+              intr: tuple[float, float, float, float, float], init_pose: Tensor, cluster: int = 0, **kw):
+    """All inputs CUDA float64. Returns (pose (7,) float64 CUDA, stats (8,) float64 CUDA); asynchronous."""
+    lib = load_library()
+    P = [_dev(t, torch.float64, f"pgo_solve arg{i}") for i, t in enumerate((pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov))]
+    K = P[0].shape[0]
+    pose = _dev(init_pose, torch.float64, "pgo_solve init_pose").reshape(7).clone()
+    stats = torch.zeros((8,), dtype=torch.float64, device=pose.device)
+    intr_c = (C.c_double * 5)(*[float(v) for v in intr])
+    prm = _pgo_params(cluster=cluster, **kw)
+    rc = lib.macvo_pgo_solve(*(t.data_ptr() for t in P), K, C.cast(intr_c, C.c_void_p), pose.data_ptr(),
+                             C.byref(prm), stats.data_ptr(), _stream())
+    _check(rc, "macvo_pgo_solve")
+    return pose, stats
+
+
+def pgo_accumulate(pos_Tw: Tensor, kp2_uv: Tensor, kp2_disp: Tensor, uv_cov: Tensor, disp_cov: Tensor,
+                   intr: tuple[float, float, float, float, float], pose: Tensor, huber_delta: float = 0.1) -> Tensor:
+    lib = load_library()
+    P = [_dev(t, torch.float64, f"pgo_accumulate arg{i}") for i, t in enumerate((pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov))]
+    K = P[0].shape[0]
+    ps = _dev(pose, torch.float64, "pgo_accumulate pose").reshape(7)
+    acc = torch.empty((PGO_ACC,), dtype=torch.float64, device=ps.device)
+    intr_c = (C.c_double * 5)(*[float(v) for v in intr])
+    rc = lib.macvo_pgo_accumulate(*(t.data_ptr() for t in P), K, C.cast(intr_c, C.c_void_p), ps.data_ptr(),
+                                  float(huber_delta), acc.data_ptr(), _stream())
+    _check(rc, "macvo_pgo_accumulate")
+    return acc
