@@ -90,7 +90,7 @@ def test_corr_full_size_properties(ops):
     c21 = ops.corr_build(d2, d1).reshape(B, 4800, 4800)
     torch.testing.assert_close(c12, c21.transpose(1, 2), rtol=1e-5, atol=2e-5)
     c_scaled = ops.corr_build(2 * d1, d2).reshape(B, 4800, 4800)
-    torch.testing.assert_close(c_scaled, 2 * c12, rtol=1e-6, atol=1e-6)           # exact power-of-two scaling
+    torch.testing.assert_close(c_scaled, 2 * c12, rtol=1e-5, atol=3e-5)           # power-of-two scaling (up to fp16-subnormal rounding of lo)
     colsum = c12.double().sum(dim=2).cpu()                                         # sum_j C[i,j] = f1[:,i] . sum_j f2[:,j]
     ref = torch.einsum("bdi,bd->bi", f1.reshape(B, 256, -1).double(), f2.reshape(B, 256, -1).double().sum(-1))
     torch.testing.assert_close(colsum, ref, rtol=1e-5, atol=2e-3)
