@@ -5,43 +5,60 @@
 // 640x480 `estimate_pair`, write-dominated: the roofline is HBM write bandwidth PROVIDED the K = 256
 // contraction runs on tensor cores (116 flop/B).
 //
-// fp32-class accuracy on fp16 tensor cores (MACVO_CORR_TC_3XF16): every operand is split
+// fp32-class accuracy on fp16 tensor cores (MACVO_CORR_TC_3XF16): every operand is scaled by 2^6 and split
 //     x = hi + lo,  hi = fp16(x),  lo = fp16(x - hi)          (|x - hi - lo| <~ 2^-22 |x|)
-// and  hi*hi + hi*lo + lo*hi  is accumulated in fp32 in TMEM. MACVO_CORR_TC_1XF16 keeps only hi*hi
-// (exact for the MACVO_Fast configuration whose encoder already emits fp16 features).
+// and  hi*hi + hi*lo + lo*hi  is accumulated in fp32 in TMEM, rescaled by 2^-12 in the epilogue (the
+// power-of-two scale keeps `lo` out of the fp16 subnormal range for |x| > 4e-3; fp16(x * 64) stays finite
+// for |x| < 1023). MACVO_CORR_TC_1XF16 keeps only hi*hi, unscaled (exact for the MACVO_Fast configuration
+// whose encoder already emits fp16 features).
 //
-// Two kernels:
-//   1. split_transpose_kernel   (B, D, N) fp32  ->  hi, lo  (B, N, D) fp16   (K-major operands)
-//   2. corr_tc_kernel           persistent, warp specialised, one CTA per SM:
-//        warp 0      TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) of 64-wide K slices into a
-//                                   multi-stage shared-memory ring, mbarrier expect_tx
-//        warp 1      MMA issuer   : one elected thread issues tcgen05.mma.kind::f16 (128 x 128 x 16),
-//                                   tcgen05.commit releases smem stages / publishes the accumulator
-//        warps 2..5  epilogue     : tcgen05.ld TMEM -> registers -> swizzled smem staging -> TMA store
-//      double-buffered TMEM accumulators (2 x 128 columns) overlap the epilogue of tile t with the MMAs
-//      of tile t+1; M/N edges are handled by TMA (zero fill on load, clipping on store).
+// v1 of this kernel (both operands from shared memory, SS-mode MMA, one CTA per tile) measured 72 us at
+// 640x480: ncu showed the tensor pipe only 50 % active — bound by the L2->SM operand stream (256 KB per
+// 64 KB of output) and by shared-memory bandwidth (8 KB of operand reads per 64-cycle MMA).
+// This version moves A out of shared memory and shares B across a CTA pair:
+//
+//   * A (the 128 query rows of a tile, all K = 256) lives in TENSOR MEMORY (2 x 128 columns, fp16 hi | lo).
+//     When a cluster moves to a new row of tiles the TMA producer pushes the A block through the same
+//     shared-memory ring as 4 extra stages and the MMA thread forwards each stage with tcgen05.cp
+//     (smem -> TMEM, 128x256b); tcgen05.cp / tcgen05.mma execute in issue order, so no further
+//     synchronisation is needed. A then stays put for the whole row (A-stationary) and tcgen05.mma runs in
+//     TS mode (A from TMEM, B from smem) -> half the shared-memory operand reads of SS mode.
+//     (v2 staged A with per-thread global loads + tcgen05.st from the epilogue warps: ncu showed those
+//     warps spending ~35 % of their time in the scattered loads.)
+//   * both operands are pre-split by one small pre-pass into K-major fp16 hi/lo; B is streamed by TMA
+//     (SWIZZLE_128B, 64-wide K slices) through a 4-stage mbarrier ring. The two CTAs of a cluster work on
+//     vertically adjacent tiles (same key columns), so each CTA loads HALF of every stage and
+//     .multicast::cluster delivers it to both -> L2->SM traffic per output byte drops 4x vs v1.
+//   * 192 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warps 2..5 epilogue
+//     (tcgen05.ld TMEM -> registers -> swizzled smem -> TMA store). Double-buffered TMEM
+//     accumulators (2 x 128 columns) overlap the epilogue of tile t with the MMAs of tile t+1.
+//   * Persistent: every cluster owns a contiguous run of (batch, row-pair, column) steps; M/N edges are
+//     handled by TMA (zero fill on load, clipping on store) and by row guards in the A loader.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <mutex>
-#include <unordered_map>
+#include <cstdlib>
 
 namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 64, UMMA_K = 16;
-constexpr int STAGES = 3;
-constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB (one of hi / lo)
-constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;          // 16 KB
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // hi+lo of A and B: 64 KB
+constexpr int STAGES = 4;
+constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;          // 16 KB (hi or lo)
+constexpr int STAGE_BYTES = 2 * B_TILE_BYTES;                // hi + lo: 32 KB
 constexpr int EPI_COLS = 32;                                 // fp32 columns per staged chunk (128 B rows)
+constexpr int EPI_CHUNKS = BLOCK_N / EPI_COLS;               // 4
 constexpr int EPI_WARP_BYTES = 32 * EPI_COLS * 4;            // 4 KB: 32 rows x 128 B
-constexpr int EPI_BUFS = 2;
 constexpr int NUM_EPI_WARPS = 4;
-constexpr int SMEM_EPI_BYTES = NUM_EPI_WARPS * EPI_BUFS * EPI_WARP_BYTES;   // 32 KB
+constexpr int SMEM_EPI_BYTES = NUM_EPI_WARPS * EPI_CHUNKS * EPI_WARP_BYTES;   // 64 KB
 constexpr int SMEM_BAR_BYTES = 256;
 constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + SMEM_EPI_BYTES + SMEM_BAR_BYTES + 1024;  // + alignment slack
 constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);
-constexpr int TMEM_COLS = 256;                               // 2 accumulator stages x 128 fp32 columns
+constexpr int TMEM_COLS = 512;            // [0,256): 2 accumulators x 128 | [256,384): A hi | [384,512): A lo
+constexpr int TMEM_A_HI = 256, TMEM_A_LO = 384;
+constexpr int KMAX = 256;                 // A-stationary capacity: K fp16 = 128 TMEM columns per half
+constexpr float SPLIT_SCALE = 64.f;       // 2^6 on both operands
+constexpr float SPLIT_UNSCALE = 1.f / 4096.f;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,6 +98,23 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// multicast load: the box lands at the same smem offset in every CTA of `mask`, and each destination CTA's
+// mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -91,8 +125,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -106,13 +139,22 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]
-__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem desc]      (TS mode)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// smem (matrix descriptor: 128 rows x 32 B slice) -> TMEM (128 lanes x 8 columns)
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t desc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
+}
+// arrive (once the issuing thread's prior MMAs retire) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -129,7 +171,6 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) 
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout = 2
 // rows are 128 B (64 fp16) apart, 8-row groups (one swizzle atom) 1024 B apart.
@@ -147,24 +188,30 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
     return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// ---- kernel 1: fp32 (B, D, N) -> fp16 hi / lo (B, N, D) --------------------------------------------------
+// ---- kernel 1: operand pre-pass: fp32 (B, D, N) -> fp16 hi / lo (B, N, D), scaled (both maps, one launch) ----
 __global__ void __launch_bounds__(256)
-split_transpose_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, int dim, int n) {
+split_transpose_kernel(const float* __restrict__ f1, const float* __restrict__ f2, __half* __restrict__ a_hi,
+                       __half* __restrict__ a_lo, __half* __restrict__ b_hi, __half* __restrict__ b_lo, int batch,
+                       int dim, int n, float scale) {
     __shared__ float tile[64][33];                                   // [d][token]
-    const int b = blockIdx.z, d0 = blockIdx.y * 64, n0 = blockIdx.x * 32;
-    const float* s = src + (long long)b * dim * n;
+    const bool second = (int)blockIdx.z >= batch;
+    const int b = second ? blockIdx.z - batch : blockIdx.z;
+    const int d0 = blockIdx.y * 64, n0 = blockIdx.x * 32;
+    const float* s = (second ? f2 : f1) + (long long)b * dim * n;
+    __half* hi = second ? b_hi : a_hi;
+    __half* lo = second ? b_lo : a_lo;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
 #pragma unroll
     for (int r = ty; r < 64; r += 8) {
         const int d = d0 + r, t = n0 + tx;
-        tile[r][tx] = (d < dim && t < n) ? s[(long long)d * n + t] : 0.f;
+        tile[r][tx] = (d < dim && t < n) ? s[(long long)d * n + t] * scale : 0.f;
     }
     __syncthreads();
     // write: token-major rows, 64 consecutive d per row -> lanes cover d pairs (half2, 128 B per warp row)
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
         const int t = n0 + r, d = d0 + 2 * tx;
-        if (t < n && d + 1 < dim + 1) {
+        if (t < n) {
             const float x0 = tile[2 * tx][r], x1 = tile[2 * tx + 1][r];
             const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
             const long long o = ((long long)b * n + t) * dim + d;
@@ -178,22 +225,11 @@ split_transpose_kernel(const float* __restrict__ src, __half* __restrict__ hi, _
 }
 
 // ---- kernel 2 -----------------------------------------------------------------------------------------------
-struct TileCoord { int b, m, n; };
-
-__device__ __forceinline__ TileCoord tile_coord(int t, int mt, int nt) {
-    TileCoord c;
-    c.n = t % nt;
-    const int r = t / nt;
-    c.m = r % mt;
-    c.b = r / mt;
-    return c;
-}
-
 template <int PASSES>   // 3: hi*hi + hi*lo + lo*hi     1: hi*hi
 __global__ void __launch_bounds__(THREADS, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-               const __grid_constant__ CUtensorMap map_out, int batch, int n, int dim) {
+               const __grid_constant__ CUtensorMap map_out, int batch, int n, int dim, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;
@@ -204,20 +240,25 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = ceil_div(n, BLOCK_M), nt = ceil_div(n, BLOCK_N), kblocks = dim / BLOCK_K;
-    const int total_tiles = batch * mt * nt;
-    // static contiguous tile ranges (n fastest: consecutive tiles of a CTA share the A rows -> L2 locality)
-    const int t_begin = (int)((long long)total_tiles * blockIdx.x / gridDim.x);
-    const int t_end = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
+    const uint32_t rank = cluster_ctarank();                    // 0 / 1: upper / lower tile of the row pair
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int mt = ceil_div(n, BLOCK_M), nt = ceil_div(n, BLOCK_N), prows = (mt + 1) / 2, kblocks = dim / BLOCK_K;
+    const int total_steps = batch * prows * nt;
+    // static contiguous runs (column index fastest -> A stays put for up to a whole row of tiles)
+    const int s_begin = (int)((long long)total_steps * cluster_id / num_clusters);
+    const int s_end = (int)((long long)total_steps * (cluster_id + 1) / num_clusters);
+    // a step is (row = b * prows + prow, column tile); both CTAs of the cluster walk the same sequence
+    const int row_begin = s_begin / nt, col_begin = s_begin - row_begin * nt;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, NUM_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_base_slot), TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                       // peer barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
@@ -225,29 +266,69 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // ===================== TMA producer =====================
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                const TileCoord tc = tile_coord(t, mt, nt);
+            int row = row_begin, col = col_begin;
+            bool new_row = true;
+            for (int s = s_begin; s < s_end; ++s) {
+                const int b = row / prows, m_tile = 2 * (row - b * prows) + (int)rank;
+                if (new_row) {
+                    // A block of this CTA's 128 rows: kblocks ring stages of (hi | lo), own CTA only
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint32_t full = bar_full + 8 * stage;
+                        mbar_expect_tx(full, PASSES == 3 ? STAGE_BYTES : B_TILE_BYTES);
+                        tma_load_3d(sa, &map_a_hi, full, kb * BLOCK_K, m_tile * BLOCK_M, b);
+                        if (PASSES == 3) tma_load_3d(sa + B_TILE_BYTES, &map_a_lo, full, kb * BLOCK_K, m_tile * BLOCK_M, b);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+                // B tile (key columns) of this step: each CTA loads half of every stage, multicast to both
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);      // both CTAs released this slot
+                    const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES);
                     const uint32_t full = bar_full + 8 * stage;
-                    mbar_expect_tx(full, PASSES == 3 ? STAGE_BYTES : (A_TILE_BYTES + B_TILE_BYTES));
-                    tma_load_3d(sa, &map_a_hi, full, kb * BLOCK_K, tc.m * BLOCK_M, tc.b);
-                    tma_load_3d(sa + 2 * A_TILE_BYTES, &map_b_hi, full, kb * BLOCK_K, tc.n * BLOCK_N, tc.b);
+                    mbar_expect_tx(full, PASSES == 3 ? STAGE_BYTES : B_TILE_BYTES);
                     if (PASSES == 3) {
-                        tma_load_3d(sa + A_TILE_BYTES, &map_a_lo, full, kb * BLOCK_K, tc.m * BLOCK_M, tc.b);
-                        tma_load_3d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, full, kb * BLOCK_K, tc.n * BLOCK_N, tc.b);
+                        if (rank == 0) tma_load_3d_mc(sb, &map_b_hi, full, kb * BLOCK_K, col * BLOCK_N, b, 3);
+                        else tma_load_3d_mc(sb + B_TILE_BYTES, &map_b_lo, full, kb * BLOCK_K, col * BLOCK_N, b, 3);
+                    } else if ((uint32_t)(kb & 1) == rank) {
+                        tma_load_3d_mc(sb, &map_b_hi, full, kb * BLOCK_K, col * BLOCK_N, b, 3);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                new_row = false;
+                if (++col == nt) { col = 0; ++row; new_row = true; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (TS mode: A from TMEM, B from smem) =====================
         constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = t_begin; t < t_end; ++t) {
+        int col = col_begin;
+        bool new_row = true;
+        for (int s = s_begin; s < s_end; ++s) {
+            if (new_row) {
+                // forward the A block smem -> TMEM; issue order keeps it behind the MMAs of the previous row
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + B_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                            const uint32_t acol = (uint32_t)((kb * BLOCK_K + k * UMMA_K) >> 1);
+                            tmem_cp_128x256b(tmem_base + TMEM_A_HI + acol, a_hi + koff);
+                            if (PASSES == 3) tmem_cp_128x256b(tmem_base + TMEM_A_LO + acol, a_lo + koff);
+                        }
+                        umma_commit_mc(bar_empty + 8 * stage, 3);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);              // epilogue drained this accumulator
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -255,75 +336,87 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + A_TILE_BYTES);
-                    const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES);
-                    const uint64_t b_lo = make_kmajor_sw128_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                    const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t b_hi = make_kmajor_sw128_desc(sb), b_lo = make_kmajor_sw128_desc(sb + B_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);     // +32 B per K step inside the atom
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);          // +32 B per K step in the atom
+                        const uint32_t acol = (uint32_t)((kb * BLOCK_K + k * UMMA_K) >> 1);   // 2 fp16 per TMEM column
+                        if (dbg & 2) continue;                                   // profiling aid: no MMA
                         if (PASSES == 3) {   // small cross terms first, the dominant hi*hi product last
-                            umma_f16_ss(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
-                            umma_f16_ss(tmem_d, a_hi + koff, b_lo + koff, idesc, 1u);
-                            umma_f16_ss(tmem_d, a_hi + koff, b_hi + koff, idesc, 1u);
+                            umma_f16_ts(tmem_d, tmem_base + TMEM_A_LO + acol, b_hi + koff, idesc, (kb | k) != 0);
+                            umma_f16_ts(tmem_d, tmem_base + TMEM_A_HI + acol, b_lo + koff, idesc, 1u);
+                            umma_f16_ts(tmem_d, tmem_base + TMEM_A_HI + acol, b_hi + koff, idesc, 1u);
                         } else {
-                            umma_f16_ss(tmem_d, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0);
+                            umma_f16_ts(tmem_d, tmem_base + TMEM_A_HI + acol, b_hi + koff, idesc, (kb | k) != 0);
                         }
                     }
-                    umma_commit(bar_empty + 8 * stage);                  // smem stage free once these MMAs retire
+                    umma_commit_mc(bar_empty + 8 * stage, 3);            // slot reusable in BOTH CTAs once these retire
                     if (kb == kblocks - 1) umma_commit(bar_tfull + 8 * acc);   // accumulator complete
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            new_row = false;
+            if (++col == nt) { col = 0; new_row = true; }
         }
     } else {
-        // ===================== epilogue: TMEM -> registers -> smem -> TMA store =====================
+        // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
         const int quarter = warp & 3;                                     // TMEM lanes [32*quarter, +32)
         const int ew = warp - 2;                                          // staging slot of this warp
-        uint8_t* stage_base = smem_epi + ew * EPI_BUFS * EPI_WARP_BYTES;
+        uint8_t* stage_base = smem_epi + ew * EPI_CHUNKS * EPI_WARP_BYTES;
         int acc = 0; uint32_t acc_phase = 0;
-        int buf = 0;
-        for (int t = t_begin; t < t_end; ++t) {
-            const TileCoord tc = tile_coord(t, mt, nt);
+        int row = row_begin, col = col_begin;
+        for (int s = s_begin; s < s_end; ++s) {
+            const int b = row / prows, m_tile = 2 * (row - b * prows) + (int)rank;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / EPI_COLS; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * EPI_COLS, r);
-                tmem_ld_wait();
-                if (c == BLOCK_N / EPI_COLS - 1) {                        // accumulator fully read: hand it back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-                }
-                // the staging buffer we are about to overwrite must have been read by its TMA store
-                if (lane == 0) tma_store_wait_read<EPI_BUFS - 1>();
-                __syncwarp();
-                uint8_t* sb = stage_base + buf * EPI_WARP_BYTES;
+            uint32_t r[EPI_CHUNKS][32];
+#pragma unroll
+            for (int c = 0; c < EPI_CHUNKS; ++c)
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * EPI_COLS, r[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);             // accumulator is in registers: hand it back
+            if (lane == 0) tma_store_wait_read_all();                     // previous tile's stores have read the staging smem
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < EPI_CHUNKS; ++c) {
+                if (dbg & 4) break;                                           // profiling aid: no staging writes
+                uint8_t* sb = stage_base + c * EPI_WARP_BYTES;
                 // row = lane (128 B), 16-byte chunk j stored at j ^ (row & 7)  (SWIZZLE_128B, conflict free)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const uint4 v = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    uint4 v = make_uint4(r[c][4 * j], r[c][4 * j + 1], r[c][4 * j + 2], r[c][4 * j + 3]);
+                    if (PASSES == 3) {
+                        v.x = __float_as_uint(__uint_as_float(v.x) * SPLIT_UNSCALE);
+                        v.y = __float_as_uint(__uint_as_float(v.y) * SPLIT_UNSCALE);
+                        v.z = __float_as_uint(__uint_as_float(v.z) * SPLIT_UNSCALE);
+                        v.w = __float_as_uint(__uint_as_float(v.w) * SPLIT_UNSCALE);
+                    }
                     *reinterpret_cast<uint4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_3d(&map_out, smem_u32(sb), tc.n * BLOCK_N + c * EPI_COLS, tc.m * BLOCK_M + quarter * 32, tc.b);
-                    tma_store_commit();
-                }
-                buf ^= 1;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(dbg & 1)) {                                 // dbg bit 0: profiling aid, no stores
+#pragma unroll
+                for (int c = 0; c < EPI_CHUNKS; ++c)
+                    tma_store_3d(&map_out, smem_u32(stage_base + c * EPI_WARP_BYTES), col * BLOCK_N + c * EPI_COLS,
+                                 m_tile * BLOCK_M + quarter * 32, b);
+                tma_store_commit();
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++col == nt) { col = 0; ++row; }
         }
         if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                       // no CTA exits while its peer may still multicast into / arrive on it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -363,6 +456,27 @@ bool make_map_3d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, void*
 
 size_t operand_bytes(int batch, int dim, int n) { return ((size_t)batch * n * dim * 2 + 1023) / 1024 * 1024; }
 
+template <int PASSES>
+int launch_main(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                const CUtensorMap& m_out, int batch, int n, int dim, int clusters, cudaStream_t st) {
+    MACVO_CUDA_TRY(cudaFuncSetAttribute(corr_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static const int dbg = getenv("MACVO_B200_CORR_DEBUG") ? atoi(getenv("MACVO_B200_CORR_DEBUG")) : 0;
+    MACVO_CUDA_TRY(cudaLaunchKernelEx(&cfg, corr_tc_kernel<PASSES>, a_hi, a_lo, b_hi, b_lo, m_out, batch, n, dim, dbg));
+    return MACVO_OK;
+}
+
 }  // namespace
 
 size_t macvo_corr_tc_workspace_bytes(int batch, int dim, int n, int passes) {
@@ -371,19 +485,20 @@ size_t macvo_corr_tc_workspace_bytes(int batch, int dim, int n, int passes) {
 
 int macvo_corr_build_tc(const float* f1, const float* f2, float* corr, int batch, int dim, int n, int passes,
                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    if (dim % BLOCK_K != 0 || n % 8 != 0) return MACVO_E_UNSUPPORTED;
+    if (dim % BLOCK_K != 0 || dim > KMAX || n % 8 != 0) return MACVO_E_UNSUPPORTED;
     if (!workspace || workspace_bytes < macvo_corr_tc_workspace_bytes(batch, dim, n, passes)) return MACVO_E_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(workspace) & 1023) || (reinterpret_cast<uintptr_t>(corr) & 15)) return MACVO_E_ARG;
     const size_t ob = operand_bytes(batch, dim, n);
-    __half* a_hi = reinterpret_cast<__half*>(workspace);
-    __half* b_hi = reinterpret_cast<__half*>(static_cast<char*>(workspace) + ob);
-    __half* a_lo = passes == 3 ? reinterpret_cast<__half*>(static_cast<char*>(workspace) + 2 * ob) : nullptr;
-    __half* b_lo = passes == 3 ? reinterpret_cast<__half*>(static_cast<char*>(workspace) + 3 * ob) : nullptr;
+    char* ws = static_cast<char*>(workspace);
+    __half* a_hi = reinterpret_cast<__half*>(ws);
+    __half* b_hi = reinterpret_cast<__half*>(ws + ob);
+    __half* a_lo = passes == 3 ? reinterpret_cast<__half*>(ws + 2 * ob) : nullptr;
+    __half* b_lo = passes == 3 ? reinterpret_cast<__half*>(ws + 3 * ob) : nullptr;
 
-    dim3 pgrid(ceil_div(n, 32), ceil_div(dim, 64), batch);
-    split_transpose_kernel<<<pgrid, 256, 0, st>>>(f1, a_hi, a_lo, dim, n);
-    MACVO_LAUNCH_CHECK();
-    split_transpose_kernel<<<pgrid, 256, 0, st>>>(f2, b_hi, b_lo, dim, n);
+    // one launch splits both feature maps: blockIdx.z in [0, batch) -> f1, [batch, 2 batch) -> f2
+    dim3 pgrid(ceil_div(n, 32), ceil_div(dim, 64), 2 * batch);
+    split_transpose_kernel<<<pgrid, 256, 0, st>>>(f1, f2, a_hi, a_lo, b_hi, b_lo, batch, dim, n,
+                                                  passes == 3 ? SPLIT_SCALE : 1.f);
     MACVO_LAUNCH_CHECK();
 
     CUtensorMap m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out;
@@ -397,15 +512,11 @@ int macvo_corr_build_tc(const float* f1, const float* f2, float* corr, int batch
     int dev = 0, sms = 0;
     MACVO_CUDA_TRY(cudaGetDevice(&dev));
     MACVO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int total_tiles = batch * ceil_div(n, BLOCK_M) * ceil_div(n, BLOCK_N);
-    const int grid = total_tiles < sms ? total_tiles : sms;
-    if (passes == 3) {
-        MACVO_CUDA_TRY(cudaFuncSetAttribute(corr_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        corr_tc_kernel<3><<<grid, THREADS, SMEM_TOTAL, st>>>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, batch, n, dim);
-    } else {
-        MACVO_CUDA_TRY(cudaFuncSetAttribute(corr_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        corr_tc_kernel<1><<<grid, THREADS, SMEM_TOTAL, st>>>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, batch, n, dim);
-    }
-    MACVO_LAUNCH_CHECK();
-    return MACVO_OK;
+    const int mt = ceil_div(n, BLOCK_M), nt = ceil_div(n, BLOCK_N);
+    const int total_steps = batch * ((mt + 1) / 2) * nt;
+    int clusters = sms / 2;
+    if (clusters > total_steps) clusters = total_steps;
+    if (clusters < 1) clusters = 1;
+    return passes == 3 ? launch_main<3>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, batch, n, dim, clusters, st)
+                       : launch_main<1>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, batch, n, dim, clusters, st);
 }
