@@ -26,12 +26,18 @@
 //     (v2 staged A with per-thread global loads + tcgen05.st from the epilogue warps: ncu showed those
 //     warps spending ~35 % of their time in the scattered loads.)
 //   * both operands are pre-split by one small pre-pass into K-major fp16 hi/lo; B is streamed by TMA
-//     (SWIZZLE_128B, 64-wide K slices) through a 4-stage mbarrier ring. The two CTAs of a cluster work on
-//     vertically adjacent tiles (same key columns), so each CTA loads HALF of every stage and
-//     .multicast::cluster delivers it to both -> L2->SM traffic per output byte drops 4x vs v1.
-//   * 192 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warps 2..5 epilogue
-//     (tcgen05.ld TMEM -> registers -> swizzled smem -> TMA store). Double-buffered TMEM
-//     accumulators (2 x 128 columns) overlap the epilogue of tile t with the MMAs of tile t+1.
+//     (SWIZZLE_128B, 64-wide K slices) through a ring of 16 KB mbarrier-guarded slots. The two CTAs of a
+//     cluster form a tcgen05 CTA PAIR (cta_group::2): one thread of the leader issues 256 x 128 x 16 MMAs
+//     that span both SMs; each CTA keeps its own 128 A rows in its TMEM and stages only HALF of every B
+//     tile (64 key rows) in its shared memory -> per-SM operand ingest and smem operand reads are halved
+//     again (v3, which multicast the full B tile into both CTAs, was bound by exactly those two: its MMA
+//     time and its TMA load time ADDED UP instead of overlapping).
+//   * 320 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warps 2..9 epilogue
+//     (tcgen05.ld TMEM -> registers -> 256-bit st.global: every lane writes full 32-byte sectors of its own
+//     output row). An event trace of v4 (4 epilogue warps, smem-staged TMA stores) showed the epilogue taking
+//     2.6-3.5 us per step against 1.7 us of MMA work: K = 256 is so short that draining the accumulator is
+//     the critical path, so the drain is now spread over 8 warps and bypasses shared memory and the TMA store
+//     engine. Double-buffered TMEM accumulators (2 x 128 columns) overlap it with the next tile's MMAs.
 //   * Persistent: every cluster owns a contiguous run of (batch, row-pair, column) steps; M/N edges are
 //     handled by TMA (zero fill on load, clipping on store) and by row guards in the A loader.
 #include "common.cuh"
@@ -43,16 +49,13 @@
 namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 64, UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;          // 16 KB (hi or lo)
-constexpr int STAGE_BYTES = 2 * B_TILE_BYTES;                // hi + lo: 32 KB
-constexpr int EPI_COLS = 32;                                 // fp32 columns per staged chunk (128 B rows)
-constexpr int EPI_CHUNKS = BLOCK_N / EPI_COLS;               // 4
-constexpr int EPI_WARP_BYTES = 32 * EPI_COLS * 4;            // 4 KB: 32 rows x 128 B
-constexpr int NUM_EPI_WARPS = 4;
-constexpr int SMEM_EPI_BYTES = NUM_EPI_WARPS * EPI_CHUNKS * EPI_WARP_BYTES;   // 64 KB
-constexpr int SMEM_BAR_BYTES = 256;
-constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + SMEM_EPI_BYTES + SMEM_BAR_BYTES + 1024;  // + alignment slack
+constexpr int SLOTS = 12;                                    // shared-memory ring of 16 KB slots
+constexpr int SLOT_BYTES = BLOCK_M * BLOCK_K * 2;            // 16 KB: one A k-block half (128 rows x 64 fp16)
+constexpr int B_HALF_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;    // 8 KB: this CTA's 64 key rows x 64 fp16 (hi or lo)
+constexpr int NUM_EPI_WARPS = 8;                             // 2 per TMEM lane quarter: each drains 64 of the 128 columns
+constexpr int EPI_COLS = BLOCK_N / 2;                        // 64 fp32 columns per epilogue warp
+constexpr int SMEM_BAR_BYTES = 512;
+constexpr int SMEM_TOTAL = SLOTS * SLOT_BYTES + SMEM_BAR_BYTES + 1024;  // + alignment slack
 constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = 512;            // [0,256): 2 accumulators x 128 | [256,384): A hi | [384,512): A lo
 constexpr int TMEM_A_HI = 256, TMEM_A_LO = 384;
@@ -106,19 +109,27 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// multicast load: the box lands at the same smem offset in every CTA of `mask`, and each destination CTA's
-// mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                               uint16_t mask) {
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;    // shared-window address with the CTA-pair rank bit cleared -> CTA 0
+// 2-CTA TMA load: data lands in THIS CTA's smem, the complete_tx goes to the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(rank) : "memory");
+}
+// 256-bit global store (STG.E.256): one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_v8(float* p, const uint32_t* r, float scale) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p),
+                 "f"(__uint_as_float(r[0]) * scale), "f"(__uint_as_float(r[1]) * scale), "f"(__uint_as_float(r[2]) * scale),
+                 "f"(__uint_as_float(r[3]) * scale), "f"(__uint_as_float(r[4]) * scale), "f"(__uint_as_float(r[5]) * scale),
+                 "f"(__uint_as_float(r[6]) * scale), "f"(__uint_as_float(r[7]) * scale) : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -133,31 +144,28 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem desc]      (TS mode)
+// D[tmem] (+)= A[tmem] * B[smem desc]      (TS mode, CTA pair: M = 256 over two SMs, each supplies half of B)
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // smem (matrix descriptor: 128 rows x 32 B slice) -> TMEM (128 lanes x 8 columns)
 __device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t desc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
+    asm volatile("tcgen05.cp.cta_group::2.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
 }
 // arrive (once the issuing thread's prior MMAs retire) on the barrier at this offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -229,194 +237,197 @@ template <int PASSES>   // 3: hi*hi + hi*lo + lo*hi     1: hi*hi
 __global__ void __launch_bounds__(THREADS, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-               const __grid_constant__ CUtensorMap map_out, int batch, int n, int dim, int dbg) {
+               float* __restrict__ corr, int batch, int n, int dim, int dbg, unsigned long long* __restrict__ trace) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + SMEM_EPI_BYTES);
-    // barrier slots: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
-    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * STAGES;
-    const uint32_t bar_tfull = bar_empty + 8 * STAGES, bar_tempty = bar_tfull + 16;
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SLOTS * SLOT_BYTES);
+    // barrier slots: full[SLOTS] (leader CTA only), empty[SLOTS], tmem_full[2], tmem_empty[2] (leader only), TMEM base
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * SLOTS;
+    const uint32_t bar_tfull = bar_empty + 8 * SLOTS, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * SLOTS + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();                    // 0 / 1: upper / lower tile of the row pair
+    const uint32_t rank = cluster_ctarank();                    // 0 = leader (issues every MMA of the pair), 1 = peer
+    const bool leader = rank == 0;
+    // profiling aid (dbg bit 3): timestamped events of cluster 0 -> trace[cta][role][event] (ns)
+    int tr_n = 0;
+    auto TR = [&](int role, int tag) {
+        if (trace != nullptr && (blockIdx.x >> 1) == 0 && tr_n < 512) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            trace[(((blockIdx.x & 1) * 4 + role) * 512 + tr_n) * 2] = t;
+            trace[(((blockIdx.x & 1) * 4 + role) * 512 + tr_n) * 2 + 1] = tag;
+            ++tr_n;
+        }
+    };
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
     const int mt = ceil_div(n, BLOCK_M), nt = ceil_div(n, BLOCK_N), prows = (mt + 1) / 2, kblocks = dim / BLOCK_K;
     const int total_steps = batch * prows * nt;
     // static contiguous runs (column index fastest -> A stays put for up to a whole row of tiles)
     const int s_begin = (int)((long long)total_steps * cluster_id / num_clusters);
     const int s_end = (int)((long long)total_steps * (cluster_id + 1) / num_clusters);
-    // a step is (row = b * prows + prow, column tile); both CTAs of the cluster walk the same sequence
+    // a step is (row = b * prows + prow, column tile) = one 256 x 128 output block of the CTA pair
     const int row_begin = s_begin / nt, col_begin = s_begin - row_begin * nt;
+    constexpr int A_SLOTS_PER_KB = PASSES == 3 ? 2 : 1;        // A k-block: hi slot (+ lo slot)
+    constexpr uint32_t A_SLOT_TX = 2 * SLOT_BYTES;              // both CTAs deliver 16 KB
+    constexpr uint32_t B_SLOT_TX = 2 * (PASSES == 3 ? 2 : 1) * B_HALF_BYTES;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, NUM_EPI_WARPS); }
+        for (int s = 0; s < SLOTS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 2 * NUM_EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_base_slot), TMEM_COLS);
+    if (warp == 1) tmem_alloc(smem_u32(tmem_base_slot), TMEM_COLS);   // cta_group::2: the same warp of both CTAs
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                       // peer barriers are initialised before any remote arrive / multicast
+    cluster_sync_all();                       // peer barriers are initialised before any remote arrive / 2-CTA copy
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (both CTAs; completion is signalled on the leader's barriers) ==========
         if (elect_one()) {
-            int stage = 0; uint32_t phase = 0;
+            int slot = 0; uint32_t phase = 0;
             int row = row_begin, col = col_begin;
             bool new_row = true;
             for (int s = s_begin; s < s_end; ++s) {
                 const int b = row / prows, m_tile = 2 * (row - b * prows) + (int)rank;
                 if (new_row) {
-                    // A block of this CTA's 128 rows: kblocks ring stages of (hi | lo), own CTA only
+                    // this CTA's 128 query rows, K-major: one 16 KB slot per (k-block, hi | lo)
                     for (int kb = 0; kb < kblocks; ++kb) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                        const uint32_t full = bar_full + 8 * stage;
-                        mbar_expect_tx(full, PASSES == 3 ? STAGE_BYTES : B_TILE_BYTES);
-                        tma_load_3d(sa, &map_a_hi, full, kb * BLOCK_K, m_tile * BLOCK_M, b);
-                        if (PASSES == 3) tma_load_3d(sa + B_TILE_BYTES, &map_a_lo, full, kb * BLOCK_K, m_tile * BLOCK_M, b);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        for (int h = 0; h < A_SLOTS_PER_KB; ++h) {
+                            mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+                            const uint32_t full = bar_full + 8 * slot;
+                            if (leader) mbar_expect_tx(full, A_SLOT_TX);
+                            tma_load_3d_2cta(smem_u32(smem + slot * SLOT_BYTES), h == 0 ? &map_a_hi : &map_a_lo, full,
+                                             kb * BLOCK_K, m_tile * BLOCK_M, b);
+                            if (++slot == SLOTS) { slot = 0; phase ^= 1; }
+                        }
                     }
                 }
-                // B tile (key columns) of this step: each CTA loads half of every stage, multicast to both
+                // this CTA's half (64 key rows) of the B tile: [hi 8 KB | lo 8 KB] per k-block slot
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);      // both CTAs released this slot
-                    const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t full = bar_full + 8 * stage;
-                    mbar_expect_tx(full, PASSES == 3 ? STAGE_BYTES : B_TILE_BYTES);
-                    if (PASSES == 3) {
-                        if (rank == 0) tma_load_3d_mc(sb, &map_b_hi, full, kb * BLOCK_K, col * BLOCK_N, b, 3);
-                        else tma_load_3d_mc(sb + B_TILE_BYTES, &map_b_lo, full, kb * BLOCK_K, col * BLOCK_N, b, 3);
-                    } else if ((uint32_t)(kb & 1) == rank) {
-                        tma_load_3d_mc(sb, &map_b_hi, full, kb * BLOCK_K, col * BLOCK_N, b, 3);
-                    }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+                    TR(0, 100 + slot);
+                    const uint32_t sb = smem_u32(smem + slot * SLOT_BYTES);
+                    const uint32_t full = bar_full + 8 * slot;
+                    if (leader) mbar_expect_tx(full, B_SLOT_TX);
+                    const int brow = col * BLOCK_N + (int)rank * (BLOCK_N / 2);
+                    tma_load_3d_2cta(sb, &map_b_hi, full, kb * BLOCK_K, brow, b);
+                    if (PASSES == 3) tma_load_3d_2cta(sb + B_HALF_BYTES, &map_b_lo, full, kb * BLOCK_K, brow, b);
+                    TR(0, 200 + slot);
+                    if (++slot == SLOTS) { slot = 0; phase ^= 1; }
                 }
                 new_row = false;
                 if (++col == nt) { col = 0; ++row; new_row = true; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (TS mode: A from TMEM, B from smem) =====================
-        constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N);
-        int stage = 0; uint32_t phase = 0;
-        int acc = 0; uint32_t acc_phase = 0;
-        int col = col_begin;
-        bool new_row = true;
-        for (int s = s_begin; s < s_end; ++s) {
-            if (new_row) {
-                // forward the A block smem -> TMEM; issue order keeps it behind the MMAs of the previous row
+        // ===================== MMA issuer: leader CTA only, cta_group::2, TS mode =====================
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BLOCK_N);      // M = 256 across the pair
+            int slot = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            int col = col_begin;
+            bool new_row = true;
+            for (int s = s_begin; s < s_end; ++s) {
+                if (new_row) {
+                    // forward the A block smem -> TMEM in both CTAs; issue order keeps it behind the previous row's MMAs
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        for (int h = 0; h < A_SLOTS_PER_KB; ++h) {
+                            mbar_wait(bar_full + 8 * slot, phase);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem + slot * SLOT_BYTES));
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                    const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                                    const uint32_t acol = (uint32_t)((kb * BLOCK_K + k * UMMA_K) >> 1);
+                                    tmem_cp_128x256b(tmem_base + (h == 0 ? TMEM_A_HI : TMEM_A_LO) + acol, adesc + koff);
+                                }
+                                umma_commit_mc(bar_empty + 8 * slot, 3);
+                            }
+                            __syncwarp();
+                            if (++slot == SLOTS) { slot = 0; phase ^= 1; }
+                        }
+                    }
+                }
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);              // both CTAs' epilogues drained this accumulator
+                if (lane == 0) TR(1, 300 + acc);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(bar_full + 8 * stage, phase);
+                    mbar_wait(bar_full + 8 * slot, phase);
                     tc_fence_after();
+                    if (lane == 0) TR(1, 400 + slot);
                     if (elect_one()) {
-                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                        const uint64_t a_hi = make_kmajor_sw128_desc(sa), a_lo = make_kmajor_sw128_desc(sa + B_TILE_BYTES);
+                        const uint32_t sb = smem_u32(smem + slot * SLOT_BYTES);
+                        const uint64_t b_hi = make_kmajor_sw128_desc(sb), b_lo = make_kmajor_sw128_desc(sb + B_HALF_BYTES);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-                            const uint32_t acol = (uint32_t)((kb * BLOCK_K + k * UMMA_K) >> 1);
-                            tmem_cp_128x256b(tmem_base + TMEM_A_HI + acol, a_hi + koff);
-                            if (PASSES == 3) tmem_cp_128x256b(tmem_base + TMEM_A_LO + acol, a_lo + koff);
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);          // +32 B per K step in the atom
+                            const uint32_t acol = (uint32_t)((kb * BLOCK_K + k * UMMA_K) >> 1);   // 2 fp16 per TMEM column
+                            if (dbg & 2) continue;                                   // profiling aid: no MMA
+                            if (PASSES == 3) {   // small cross terms first, the dominant hi*hi product last
+                                umma_f16_ts(tmem_d, tmem_base + TMEM_A_LO + acol, b_hi + koff, idesc, (kb | k) != 0);
+                                umma_f16_ts(tmem_d, tmem_base + TMEM_A_HI + acol, b_lo + koff, idesc, 1u);
+                                umma_f16_ts(tmem_d, tmem_base + TMEM_A_HI + acol, b_hi + koff, idesc, 1u);
+                            } else {
+                                umma_f16_ts(tmem_d, tmem_base + TMEM_A_HI + acol, b_hi + koff, idesc, (kb | k) != 0);
+                            }
                         }
-                        umma_commit_mc(bar_empty + 8 * stage, 3);
+                        umma_commit_mc(bar_empty + 8 * slot, 3);             // slot reusable in BOTH CTAs once these retire
+                        if (kb == kblocks - 1) umma_commit_mc(bar_tfull + 8 * acc, 3);   // accumulator complete, both CTAs
                     }
                     __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++slot == SLOTS) { slot = 0; phase ^= 1; }
                 }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                new_row = false;
+                if (++col == nt) { col = 0; new_row = true; }
             }
-            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);              // epilogue drained this accumulator
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-            for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait(bar_full + 8 * stage, phase);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t b_hi = make_kmajor_sw128_desc(sb), b_lo = make_kmajor_sw128_desc(sb + B_TILE_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);          // +32 B per K step in the atom
-                        const uint32_t acol = (uint32_t)((kb * BLOCK_K + k * UMMA_K) >> 1);   // 2 fp16 per TMEM column
-                        if (dbg & 2) continue;                                   // profiling aid: no MMA
-                        if (PASSES == 3) {   // small cross terms first, the dominant hi*hi product last
-                            umma_f16_ts(tmem_d, tmem_base + TMEM_A_LO + acol, b_hi + koff, idesc, (kb | k) != 0);
-                            umma_f16_ts(tmem_d, tmem_base + TMEM_A_HI + acol, b_lo + koff, idesc, 1u);
-                            umma_f16_ts(tmem_d, tmem_base + TMEM_A_HI + acol, b_hi + koff, idesc, 1u);
-                        } else {
-                            umma_f16_ts(tmem_d, tmem_base + TMEM_A_HI + acol, b_hi + koff, idesc, (kb | k) != 0);
-                        }
-                    }
-                    umma_commit_mc(bar_empty + 8 * stage, 3);            // slot reusable in BOTH CTAs once these retire
-                    if (kb == kblocks - 1) umma_commit(bar_tfull + 8 * acc);   // accumulator complete
-                }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            new_row = false;
-            if (++col == nt) { col = 0; new_row = true; }
         }
     } else {
-        // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
-        const int quarter = warp & 3;                                     // TMEM lanes [32*quarter, +32)
-        const int ew = warp - 2;                                          // staging slot of this warp
-        uint8_t* stage_base = smem_epi + ew * EPI_CHUNKS * EPI_WARP_BYTES;
+        // ===================== epilogue: TMEM -> registers -> 256-bit global stores =====================
+        // 8 warps: warp w drains TMEM lanes [32 (w & 3), +32) x columns [64 h, +64), h = (w - 2) >> 2. A lane owns
+        // one output row and writes 256 contiguous bytes of it per tile as eight full 32-byte sectors; no
+        // shared-memory staging, so the smem port stays free for the operand stream.
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const float unscale = PASSES == 3 ? SPLIT_UNSCALE : 1.f;
         int acc = 0; uint32_t acc_phase = 0;
         int row = row_begin, col = col_begin;
         for (int s = s_begin; s < s_end; ++s) {
             const int b = row / prows, m_tile = 2 * (row - b * prows) + (int)rank;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            uint32_t r[EPI_CHUNKS][32];
-#pragma unroll
-            for (int c = 0; c < EPI_CHUNKS; ++c)
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * EPI_COLS, r[c]);
+            if (warp == 2 && lane == 0) TR(2, 500 + acc);
+            uint32_t r[2][32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * EPI_COLS;
+            tmem_ld_32x32b_x32(taddr, r[0]);
+            tmem_ld_32x32b_x32(taddr + 32, r[1]);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);             // accumulator is in registers: hand it back
-            if (lane == 0) tma_store_wait_read_all();                     // previous tile's stores have read the staging smem
-            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * acc, 0);   // accumulator is in registers: hand it back
+            if (warp == 2 && lane == 0) TR(2, 600 + acc);
+            const int orow = m_tile * BLOCK_M + quarter * 32 + lane;
+            const int ocol = col * BLOCK_N + half * EPI_COLS;
+            if (orow < n && !(dbg & 1)) {
+                float* dst = corr + ((long long)b * n + orow) * n + ocol;
 #pragma unroll
-            for (int c = 0; c < EPI_CHUNKS; ++c) {
-                if (dbg & 4) break;                                           // profiling aid: no staging writes
-                uint8_t* sb = stage_base + c * EPI_WARP_BYTES;
-                // row = lane (128 B), 16-byte chunk j stored at j ^ (row & 7)  (SWIZZLE_128B, conflict free)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint4 v = make_uint4(r[c][4 * j], r[c][4 * j + 1], r[c][4 * j + 2], r[c][4 * j + 3]);
-                    if (PASSES == 3) {
-                        v.x = __float_as_uint(__uint_as_float(v.x) * SPLIT_UNSCALE);
-                        v.y = __float_as_uint(__uint_as_float(v.y) * SPLIT_UNSCALE);
-                        v.z = __float_as_uint(__uint_as_float(v.z) * SPLIT_UNSCALE);
-                        v.w = __float_as_uint(__uint_as_float(v.w) * SPLIT_UNSCALE);
-                    }
-                    *reinterpret_cast<uint4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
-                }
+                for (int j = 0; j < 8; ++j)
+                    if (ocol + 8 * j < n) st_global_v8(dst + 8 * j, &r[j >> 2][8 * (j & 3)], unscale);   // n % 8 == 0
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0 && !(dbg & 1)) {                                 // dbg bit 0: profiling aid, no stores
-#pragma unroll
-                for (int c = 0; c < EPI_CHUNKS; ++c)
-                    tma_store_3d(&map_out, smem_u32(stage_base + c * EPI_WARP_BYTES), col * BLOCK_N + c * EPI_COLS,
-                                 m_tile * BLOCK_M + quarter * 32, b);
-                tma_store_commit();
-            }
+            if (warp == 2 && lane == 0) TR(2, 700 + acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             if (++col == nt) { col = 0; ++row; }
         }
-        if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                       // no CTA exits while its peer may still multicast into / arrive on it
+    cluster_sync_all();                       // no CTA exits while its peer may still signal / copy into it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -456,9 +467,11 @@ bool make_map_3d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, void*
 
 size_t operand_bytes(int batch, int dim, int n) { return ((size_t)batch * n * dim * 2 + 1023) / 1024 * 1024; }
 
+unsigned long long* g_trace = nullptr;
+
 template <int PASSES>
 int launch_main(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                const CUtensorMap& m_out, int batch, int n, int dim, int clusters, cudaStream_t st) {
+                float* m_out, int batch, int n, int dim, int clusters, cudaStream_t st) {
     MACVO_CUDA_TRY(cudaFuncSetAttribute(corr_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
@@ -473,7 +486,15 @@ int launch_main(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensor
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     static const int dbg = getenv("MACVO_B200_CORR_DEBUG") ? atoi(getenv("MACVO_B200_CORR_DEBUG")) : 0;
-    MACVO_CUDA_TRY(cudaLaunchKernelEx(&cfg, corr_tc_kernel<PASSES>, a_hi, a_lo, b_hi, b_lo, m_out, batch, n, dim, dbg));
+    unsigned long long* trace = nullptr;
+    if (dbg & 8) {   // profiling aid: leave the event trace of cluster 0 in a managed buffer and dump it at exit
+        static unsigned long long* tbuf = nullptr;
+        if (!tbuf) { cudaMallocManaged(&tbuf, 2 * 4 * 512 * 2 * sizeof(unsigned long long)); }
+        cudaMemsetAsync(tbuf, 0, 2 * 4 * 512 * 2 * sizeof(unsigned long long), st);
+        trace = tbuf;
+        g_trace = tbuf;
+    }
+    MACVO_CUDA_TRY(cudaLaunchKernelEx(&cfg, corr_tc_kernel<PASSES>, a_hi, a_lo, b_hi, b_lo, m_out, batch, n, dim, dbg, trace));
     return MACVO_OK;
 }
 
@@ -487,7 +508,7 @@ int macvo_corr_build_tc(const float* f1, const float* f2, float* corr, int batch
                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (dim % BLOCK_K != 0 || dim > KMAX || n % 8 != 0) return MACVO_E_UNSUPPORTED;
     if (!workspace || workspace_bytes < macvo_corr_tc_workspace_bytes(batch, dim, n, passes)) return MACVO_E_WORKSPACE;
-    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) || (reinterpret_cast<uintptr_t>(corr) & 15)) return MACVO_E_ARG;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) || (reinterpret_cast<uintptr_t>(corr) & 31)) return MACVO_E_ARG;
     const size_t ob = operand_bytes(batch, dim, n);
     char* ws = static_cast<char*>(workspace);
     __half* a_hi = reinterpret_cast<__half*>(ws);
@@ -501,12 +522,12 @@ int macvo_corr_build_tc(const float* f1, const float* f2, float* corr, int batch
                                                   passes == 3 ? SPLIT_SCALE : 1.f);
     MACVO_LAUNCH_CHECK();
 
-    CUtensorMap m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out;
+    CUtensorMap m_a_hi, m_a_lo, m_b_hi, m_b_lo;
+    float* m_out = corr;
     bool ok = make_map_3d(&m_a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a_hi, dim, n, batch, BLOCK_K, BLOCK_M);
-    ok = ok && make_map_3d(&m_b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_hi, dim, n, batch, BLOCK_K, BLOCK_N);
+    ok = ok && make_map_3d(&m_b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_hi, dim, n, batch, BLOCK_K, BLOCK_N / 2);
     ok = ok && make_map_3d(&m_a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, passes == 3 ? a_lo : a_hi, dim, n, batch, BLOCK_K, BLOCK_M);
-    ok = ok && make_map_3d(&m_b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, passes == 3 ? b_lo : b_hi, dim, n, batch, BLOCK_K, BLOCK_N);
-    ok = ok && make_map_3d(&m_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, corr, n, n, batch, EPI_COLS, 32);
+    ok = ok && make_map_3d(&m_b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, passes == 3 ? b_lo : b_hi, dim, n, batch, BLOCK_K, BLOCK_N / 2);
     if (!ok) return MACVO_E_DRIVER;
 
     int dev = 0, sms = 0;
@@ -519,4 +540,13 @@ int macvo_corr_build_tc(const float* f1, const float* f2, float* corr, int batch
     if (clusters < 1) clusters = 1;
     return passes == 3 ? launch_main<3>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, batch, n, dim, clusters, st)
                        : launch_main<1>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, batch, n, dim, clusters, st);
+}
+
+// profiling aid: copy the last event trace (dbg bit 3) to host memory; returns the number of u64 written
+extern "C" int macvo_corr_debug_trace(unsigned long long* out, int capacity) {
+    if (!g_trace) return 0;
+    cudaDeviceSynchronize();
+    const int n = 2 * 4 * 512 * 2;
+    for (int i = 0; i < n && i < capacity; ++i) out[i] = g_trace[i];
+    return n < capacity ? n : capacity;
 }
