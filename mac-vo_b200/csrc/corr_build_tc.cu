@@ -33,11 +33,11 @@
 //     again (v3, which multicast the full B tile into both CTAs, was bound by exactly those two: its MMA
 //     time and its TMA load time ADDED UP instead of overlapping).
 //   * 320 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warps 2..9 epilogue
-//     (tcgen05.ld TMEM -> registers -> 256-bit st.global: every lane writes full 32-byte sectors of its own
-//     output row). An event trace of v4 (4 epilogue warps, smem-staged TMA stores) showed the epilogue taking
-//     2.6-3.5 us per step against 1.7 us of MMA work: K = 256 is so short that draining the accumulator is
-//     the critical path, so the drain is now spread over 8 warps and bypasses shared memory and the TMA store
-//     engine. Double-buffered TMEM accumulators (2 x 128 columns) overlap it with the next tile's MMAs.
+//     (tcgen05.ld TMEM -> registers -> per-warp smem transpose -> coalesced 128-bit st.global). An event
+//     trace of v4 (4 epilogue warps, smem-staged TMA stores) showed the epilogue taking 2.6-3.5 us per step
+//     against 1.7 us of MMA work: K = 256 is so short that draining the accumulator is the critical path,
+//     so the drain is spread over 8 warps. Double-buffered TMEM accumulators (2 x 128 columns) overlap it
+//     with the next tile's MMAs.
 //   * Persistent: every cluster owns a contiguous run of (batch, row-pair, column) steps; M/N edges are
 //     handled by TMA (zero fill on load, clipping on store) and by row guards in the A loader.
 #include "common.cuh"
@@ -49,13 +49,15 @@
 namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 64, UMMA_K = 16;
-constexpr int SLOTS = 12;                                    // shared-memory ring of 16 KB slots
+constexpr int SLOTS = 10;                                    // shared-memory ring of 16 KB slots
 constexpr int SLOT_BYTES = BLOCK_M * BLOCK_K * 2;            // 16 KB: one A k-block half (128 rows x 64 fp16)
 constexpr int B_HALF_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;    // 8 KB: this CTA's 64 key rows x 64 fp16 (hi or lo)
 constexpr int NUM_EPI_WARPS = 8;                             // 2 per TMEM lane quarter: each drains 64 of the 128 columns
 constexpr int EPI_COLS = BLOCK_N / 2;                        // 64 fp32 columns per epilogue warp
+constexpr int EPI_WARP_BYTES = 32 * EPI_COLS * 4;            // 8 KB transpose buffer per epilogue warp
+constexpr int SMEM_EPI_BYTES = NUM_EPI_WARPS * EPI_WARP_BYTES;  // 64 KB
 constexpr int SMEM_BAR_BYTES = 512;
-constexpr int SMEM_TOTAL = SLOTS * SLOT_BYTES + SMEM_BAR_BYTES + 1024;  // + alignment slack
+constexpr int SMEM_TOTAL = SLOTS * SLOT_BYTES + SMEM_EPI_BYTES + SMEM_BAR_BYTES + 1024;  // + alignment slack
 constexpr int THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = 512;            // [0,256): 2 accumulators x 128 | [256,384): A hi | [384,512): A lo
 constexpr int TMEM_A_HI = 256, TMEM_A_LO = 384;
@@ -71,9 +73,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -124,21 +123,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(bar), "r"(rank) : "memory");
 }
-// 256-bit global store (STG.E.256): one full 32-byte sector per lane
-__device__ __forceinline__ void st_global_v8(float* p, const uint32_t* r, float scale) {
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p),
-                 "f"(__uint_as_float(r[0]) * scale), "f"(__uint_as_float(r[1]) * scale), "f"(__uint_as_float(r[2]) * scale),
-                 "f"(__uint_as_float(r[3]) * scale), "f"(__uint_as_float(r[4]) * scale), "f"(__uint_as_float(r[5]) * scale),
-                 "f"(__uint_as_float(r[6]) * scale), "f"(__uint_as_float(r[7]) * scale) : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -240,7 +224,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                float* __restrict__ corr, int batch, int n, int dim, int dbg, unsigned long long* __restrict__ trace) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SLOTS * SLOT_BYTES);
+    uint8_t* smem_epi = smem + SLOTS * SLOT_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + SMEM_EPI_BYTES);
     // barrier slots: full[SLOTS] (leader CTA only), empty[SLOTS], tmem_full[2], tmem_empty[2] (leader only), TMEM base
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * SLOTS;
     const uint32_t bar_tfull = bar_empty + 8 * SLOTS, bar_tempty = bar_tfull + 16;
@@ -274,7 +259,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < SLOTS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 2 * NUM_EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, NUM_EPI_WARPS); }   // 4 warps x 2 CTAs per accumulator
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_base_slot), TMEM_COLS);   // cta_group::2: the same warp of both CTAs
@@ -388,40 +373,69 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue: TMEM -> registers -> 256-bit global stores =====================
-        // 8 warps: warp w drains TMEM lanes [32 (w & 3), +32) x columns [64 h, +64), h = (w - 2) >> 2. A lane owns
-        // one output row and writes 256 contiguous bytes of it per tile as eight full 32-byte sectors; no
-        // shared-memory staging, so the smem port stays free for the operand stream.
+        // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global stores ==========
+        // 8 warps in two groups of four; group g owns accumulator g, i.e. every second step, so the TMEM drain of
+        // one tile (TMEM read port) overlaps the global stores of the previous one (LSU). Warp w covers TMEM
+        // lanes [32 (w & 3), +32) and drains the 128 columns in two halves of 64.
+        // tcgen05.ld hands every lane one output ROW. Storing that directly costs 32 distinct cache lines per
+        // warp instruction (an event trace showed those stores saturating the LSU queue and delaying the TMA
+        // producer's issue slots by ~1 us per step), so the warp transposes each 32 x 64 block through a private
+        // 8 KB XOR-swizzled shared-memory buffer and writes 2 rows x 256 contiguous bytes per instruction.
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int group = (warp - 2) >> 2;
         const float unscale = PASSES == 3 ? SPLIT_UNSCALE : 1.f;
-        int acc = 0; uint32_t acc_phase = 0;
-        int row = row_begin, col = col_begin;
-        for (int s = s_begin; s < s_end; ++s) {
+        uint8_t* tbuf = smem_epi + (warp - 2) * EPI_WARP_BYTES;
+        const int acc = group;
+        uint32_t acc_phase = 0;
+        int row = row_begin, col = col_begin + group;
+        while (col >= nt) { col -= nt; ++row; }
+        for (int s = s_begin + group; s < s_end; s += 2) {
             const int b = row / prows, m_tile = 2 * (row - b * prows) + (int)rank;
+            const int orow0 = m_tile * BLOCK_M + quarter * 32;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             if (warp == 2 && lane == 0) TR(2, 500 + acc);
-            uint32_t r[2][32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * EPI_COLS;
-            tmem_ld_32x32b_x32(taddr, r[0]);
-            tmem_ld_32x32b_x32(taddr + 32, r[1]);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * acc, 0);   // accumulator is in registers: hand it back
-            if (warp == 2 && lane == 0) TR(2, 600 + acc);
-            const int orow = m_tile * BLOCK_M + quarter * 32 + lane;
-            const int ocol = col * BLOCK_N + half * EPI_COLS;
-            if (orow < n && !(dbg & 1)) {
-                float* dst = corr + ((long long)b * n + orow) * n + ocol;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (ocol + 8 * j < n) st_global_v8(dst + 8 * j, &r[j >> 2][8 * (j & 3)], unscale);   // n % 8 == 0
+            for (int h = 0; h < 2; ++h) {
+                uint32_t r[2][32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + h * EPI_COLS;
+                tmem_ld_32x32b_x32(taddr, r[0]);
+                tmem_ld_32x32b_x32(taddr + 32, r[1]);
+                tmem_ld_wait();
+                if (h == 1) {                                             // whole accumulator is in registers: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * acc, 0);
+                    if (warp == 2 && lane == 0) TR(2, 600 + acc);
+                }
+                // write: row = lane (256 B), 16-byte chunk c stored at c ^ (row & 7)  -> conflict free
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float4 v;
+                    v.x = __uint_as_float(r[c >> 3][4 * (c & 7) + 0]) * unscale;
+                    v.y = __uint_as_float(r[c >> 3][4 * (c & 7) + 1]) * unscale;
+                    v.z = __uint_as_float(r[c >> 3][4 * (c & 7) + 2]) * unscale;
+                    v.w = __uint_as_float(r[c >> 3][4 * (c & 7) + 3]) * unscale;
+                    *reinterpret_cast<float4*>(tbuf + lane * 256 + ((c ^ (lane & 7)) << 4)) = v;
+                }
+                __syncwarp();
+                // read back transposed: instruction i covers rows 2i, 2i+1; 16 lanes x 16 B = one 256-byte row segment
+                const int ocol = col * BLOCK_N + h * EPI_COLS + (lane & 15) * 4;
+                float* dst0 = corr + ((long long)b * n + orow0) * n + ocol;
+                if (!(dbg & 1)) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int rr = 2 * i + (lane >> 4);
+                        const float4 v = *reinterpret_cast<const float4*>(tbuf + rr * 256 + (((lane & 15) ^ (rr & 7)) << 4));
+                        if (orow0 + rr < n && ocol < n) *reinterpret_cast<float4*>(dst0 + (long long)rr * n) = v;   // n % 8 == 0
+                    }
+                }
+                __syncwarp();                                             // buffer is reused by the next half
             }
             if (warp == 2 && lane == 0) TR(2, 700 + acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            if (++col == nt) { col = 0; ++row; }
+            acc_phase ^= 1;
+            col += 2;
+            while (col >= nt) { col -= nt; ++row; }
         }
     }
 
