@@ -45,13 +45,13 @@ def test_host_only_queries(lib):
 
 
 def test_sass_is_blackwell_native():
-    """the tensor-core kernel must contain tcgen05 / TMA SASS (UTCHMMA, UTMALDG, UTMASTG, LDTM)"""
+    """the tensor-core kernel must contain tcgen05 / TMA SASS (UTCHMMA, UTMALDG, UTCCP, LDTM)"""
     from macvo_b200 import build
     cuobjdump = "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", build.LIB_PATH], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTCCP", "LDTM"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", build.LIB_PATH], capture_output=True, text=True).stdout
 
