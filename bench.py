@@ -1,0 +1,295 @@
+"""Benchmark of the MAC-VO per-frame hot path (BASELINE.json metric: stereo frames/sec @640x480; corr-vol
+HBM GB/s vs roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config performant|fast]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one stereo frame through the whole hot path: FlowFormerCov frontend (correlation volume +
+12 x window lookup on the sm_100a kernels, dense layers through cuDNN/cuBLAS, CUDA graph) -> fused dense
+post-processing + keypoint scoring -> candidate selection -> per-keypoint gathers -> 2 x observation
+covariance -> two-frame pose-graph LM solve, on a seeded synthetic TartanAir-shape 640x480 sequence with the
+MACVO_Performant settings (fp32 network, 200 keypoints, mapping on). `value` keeps the images resident in
+HBM; `e2e` goes through the plugin API with pinned HOST images (H2D inside the timed region) and reads the
+optimised pose back every frame. N > 1 = N independent streams, one per GPU (BASELINE config 5:
+"replicas only", no data-path collective), value = total frames / max-over-ranks time.
+
+`--impl reference` times the reference's own CPU arithmetic (the oracle port, see oracle/) with all host
+threads on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+
+import torch  # noqa: E402
+
+METRIC = "stereo frames/sec @640x480"
+H, W = 480, 640
+CONFIGS = {
+    "performant": dict(enc_dtype="fp32", dec_dtype="fp32", num_point=200),     # Config/Experiment/MACVO/MACVO_Performant.yaml
+    "fast": dict(enc_dtype="fp16", dec_dtype="bf16", num_point=200),           # Config/Experiment/MACVO/MACVO_Fast.yaml
+}
+SEQ_LEN = 8     # distinct synthetic frames, cycled (forwards / backwards) by the timed loop
+
+
+def _dist():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi style clock / throttle sampling during the timed region (pynvml)."""
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+            "hw_power_brake": 0x80}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self) -> dict:
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm (reference arithmetic = oracle port)
+# --------------------------------------------------------------------------------------------------
+def run_cpu(cfg: dict, frames_to_time: int, warm: int) -> dict:
+    from macvo_b200 import synthetic
+    from macvo_b200.flowformer_cov import synthetic_state_dict
+    from macvo_b200.pipeline import TwoFrameOdometry
+    from oracle import pipeline_cpu as pc
+    dt = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    frames = synthetic.make_sequence(SEQ_LEN, H, W)
+    torch.manual_seed(5)
+    odo = TwoFrameOdometry(pc.CpuFrontend(synthetic_state_dict(0), dt[cfg["enc_dtype"]], dt[cfg["dec_dtype"]]),
+                           pc.CpuSelector(), pc.CpuCovariance(), pc.CpuPGO(), num_point=cfg["num_point"],
+                           map_selector=pc.CpuMapSelector())
+    odo.initialize(frames[0])
+    idx = 1
+    for _ in range(warm):
+        odo.run_pair(frames[idx % SEQ_LEN]); idx += 1
+    t0 = time.perf_counter()
+    for _ in range(frames_to_time):
+        odo.run_pair(frames[idx % SEQ_LEN]); idx += 1
+    odo.finish()
+    dt_s = time.perf_counter() - t0
+    return {"value": frames_to_time / dt_s, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{frames_to_time} frame(s) of the same 640x480 workload after {warm} warm-up, "
+                      f"{dt_s / frames_to_time:.2f} s/frame, torch CPU kernels with {cores} threads"}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def build_gpu_pipeline(cfg: dict, device: str):
+    from types import SimpleNamespace as NS
+    from macvo_b200 import plugins
+    from macvo_b200.pipeline import TwoFrameOdometry
+    fe = plugins.B200_FlowFormerCovFrontend(NS(weight="synthetic:0", device=device, enc_dtype=cfg["enc_dtype"],
+                                               dec_dtype=cfg["dec_dtype"], decoder_depth=12,
+                                               enforce_positive_disparity=False, cuda_graph=True))
+    sel = plugins.B200_CovAwareSelector_NoDepth(NS(device=device, kernel_size=7, mask_width=32, max_match_cov=100.0))
+    msel = plugins.B200_MappingPointSelector(NS(max_depth=5.0, max_depth_cov=0.005, mask_width=32))
+    cov = plugins.B200_MatchCovariance(NS(device=device, kernel_size=31, match_cov_default=0.25, min_depth_cov=0.05,
+                                          min_flow_cov=0.25))
+    pgo = plugins.B200_TwoFrame_PGO(NS(graph_type="disp", device=device, vectorize=True, parallel=False, autodiff=False))
+    return TwoFrameOdometry(fe, sel, cov, pgo, num_point=cfg["num_point"], map_selector=msel)
+
+
+def time_corr_kernel(device: str, iters: int = 10) -> dict:
+    """achieved HBM GB/s of the correlation-volume build at the workload's shape (B=2, D=256, N=4800)."""
+    from macvo_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    f1 = (torch.randn(2, 256, H // 8, W // 8, generator=g) * 0.5).to(device)
+    f2 = (torch.randn(2, 256, H // 8, W // 8, generator=g) * 0.5).to(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    for _ in range(3):
+        ops.corr_build(f1, f2)
+    times = []
+    for _ in range(iters):
+        flush.zero_()                                                      # evict L2 (126 MB) between launches
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        ops.corr_build(f1, f2)                                             # enqueued on torch's current stream
+        e.record()
+        e.synchronize()
+        times.append(s.elapsed_time(e) * 1e-3)
+    n = (H // 8) * (W // 8)
+    algo_bytes = 2 * (4 * n * n + 8 * n * 256)                             # 4 N^2 + 2*4*N*D per pair
+    return {"seconds": sum(times) / len(times), "bytes": algo_bytes}
+
+
+def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
+    rank, world, local = _dist()
+    assert torch.cuda.is_available(), "bench.py (GPU arm) needs CUDA; use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    from macvo_b200 import build, ops, synthetic
+    build.build(verbose=False)
+    ops.load_library()
+
+    frames_host = synthetic.make_sequence(SEQ_LEN, H, W, seed=1000 + rank, pin=True)
+    frames_dev = []
+    for f in frames_host:
+        import copy
+        fd = copy.copy(f)
+        fd.imageL, fd.imageR = f.imageL.to(device), f.imageR.to(device)
+        frames_dev.append(fd)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(frames, read_pose: bool):
+        torch.manual_seed(5)
+        odo = build_gpu_pipeline(cfg, device)
+        odo.initialize(frames[0])
+        period = 2 * SEQ_LEN - 2                                          # ping-pong 0,1,..,7,6,..,1,0,1,...
+        pp = lambda i: (i % period) if (i % period) < SEQ_LEN else period - (i % period)
+        seq = [frames[pp(i)] for i in range(1, warmup + steps + 1)]
+        for f in seq[:warmup]:
+            odo.run_pair(f)
+        barrier()
+        ops.LAUNCHES[0] = 0
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        last = None
+        for f in seq[warmup:]:
+            odo.run_pair(f)
+            if read_pose and odo.optimizer.get_result() is not None:
+                last = odo.optimizer.get_result().motion.cpu()            # D2H of the step's result (synchronises)
+        odo.finish()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ops.LAUNCHES[0], odo
+
+    with ClockSampler(local) as clk:
+        ms_dev, launches, _ = timed(frames_dev, read_pose=False)
+        ms_e2e, _, _ = timed(frames_host, read_pose=True)
+    corr = time_corr_kernel(device)
+
+    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "corr_tc_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    achieved = corr["bytes"] / corr["seconds"] / 1e9
+    out = {
+        "metric": METRIC, "value": world * steps / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if cfg["enc_dtype"] == "fp32" else "f16/bf16 mixed",
+        "data": "synthetic (seeded smoothed-noise TartanAir-shape stereo sequence, synthetic:0 network weights)",
+        "config": {"workload": f"640x480 synthetic stereo sequence, MACVO_{'Performant' if cfg['enc_dtype'] == 'fp32' else 'Fast'}"
+                               f" settings ({cfg['num_point']} keypoints, mapping on, decoder_depth 12), BASELINE configs[1]",
+                   "streams": world, "parallelism": "replicas only (one independent stream per GPU, no collective)",
+                   "l2": "per-frame working set (184 MB correlation volume + >1 GB activations) exceeds the 126 MB L2; "
+                         "the corr roofline loop flushes L2 with a 256 MB write between launches",
+                   "matmul_precision": "TF32 for the cuDNN/cuBLAS layers like the reference frontend (Frontend.py:275-277); "
+                                       "correlation volume fp32-class (3 x fp16 split, fp32 accumulate)"},
+        "e2e": {"value": world * steps / (ms_e2e * 1e-3), "unit": "frames/s",
+                "h2d_bytes_per_step": 4 * 3 * H * W * 4, "d2h_bytes_per_step": 7 * 8 + 2 * 8 + 3 * 4},
+        "gpu_launches": launches,
+        "clocks": clk.summary(),
+        "roofline": {"kernel": "macvo_corr_build (split pre-pass + corr_tc_kernel<3>), B=2 D=256 N=4800", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": corr["bytes"],
+                     "launch_seconds": corr["seconds"]},
+    }
+    if rank == 0 and world == 1:
+        out["cpu_baseline"] = run_cpu(cfg, frames_to_time=1, warm=0)
+    if world > 1:
+        dist.destroy_process_group()
+    return out if rank == 0 else {}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="performant", choices=list(CONFIGS))
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    cfg = CONFIGS[a.config]
+    rank, world, _ = _dist()
+    if a.impl == "reference":
+        if rank != 0:
+            return                                   # rank 0 alone runs the CPU arm
+        steps = max(1, min(a.steps, 2))              # bounded sample: ~10 s per 640x480 frame on 8 cores
+        warm = min(a.warmup, 1)
+        r = run_cpu(cfg, frames_to_time=steps, warm=warm)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": a.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "640x480 synthetic stereo sequence, MACVO_Performant settings, CPU arithmetic of the "
+                                       "reference (oracle port; the reference tree cannot travel to the GPU box)"},
+                "cpu_baseline": r, "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    out = run_gpu(cfg, a.steps, a.warmup, a.gpus)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

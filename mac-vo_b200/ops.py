@@ -21,6 +21,7 @@ PGO_ACC = 55
 
 _lib = None
 _lock = threading.Lock()
+LAUNCHES = [0]      # number of macvo_b200 kernels enqueued through this module (bench.py's `gpu_launches`)
 
 
 class MacvoB200Error(RuntimeError):
@@ -146,6 +147,7 @@ def corr_build(fmap1: Tensor, fmap2: Tensor, mode: int | None = None) -> Tensor:
     rc = lib.macvo_corr_build(f1.data_ptr(), f2.data_ptr(), out.data_ptr(), B, D, n, mode,
                               ws.data_ptr() if ws is not None else None, nbytes, _stream())
     _check(rc, "macvo_corr_build")
+    LAUNCHES[0] += (1 if mode == CORR_SIMT else 2)
     return out
 
 
@@ -163,6 +165,7 @@ def corr_lookup(cost_maps: Tensor, coords: Tensor) -> Tensor:
     out = torch.empty((B, 81, H1, W1), dtype=torch.float32, device=cm.device)
     _check(lib.macvo_corr_lookup(cm.data_ptr(), co.data_ptr(), out.data_ptr(), B, H1, W1, H2, W2, _stream()),
            "macvo_corr_lookup")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -178,8 +181,7 @@ class ScoreBuffers:
         self.nms = torch.empty((h, w), dtype=torch.uint8, device=device)
         self.cand_vals = torch.empty((h * w,), dtype=torch.float32, device=device)
         self.n_cand = torch.zeros((1,), dtype=torch.int32, device=device)
-        self.source_ptr = 0        # data_ptr of the (3,h,w) covariance map these scores belong to
-        self.source_version = -1
+        self.generation = 0        # bumped by whoever refills the buffers (host-side bookkeeping)
 
     def struct(self, score_cov_ptr) -> _ScoreT:
         return _ScoreT(score_cov_ptr, self.quality.data_ptr(), self.nms.data_ptr(), self.cand_vals.data_ptr(),
@@ -206,12 +208,12 @@ def dense_postproc(est_flow: Tensor, est_cov: Tensor, bl_fx: float, enforce_posi
     if score is not None:
         score.n_cand.zero_()
         st = score.struct(None)
-        score.source_ptr, score.source_version = flow_cov.data_ptr(), flow_cov._version
     rc = lib.macvo_dense_postproc(fl.data_ptr(), cv.data_ptr(), H, W, float(bl_fx), float(bl_fx) ** 2,
                                   depth.data_ptr(), disparity.data_ptr(), depth_cov.data_ptr(),
                                   mask.data_ptr() if mask is not None else None, flow_cov.data_ptr(),
                                   C.byref(st) if st is not None else None, _stream())
     _check(rc, "macvo_dense_postproc")
+    LAUNCHES[0] += 1
     return {"depth": depth, "disparity": disparity, "depth_cov": depth_cov,
             "disparity_uncertainty": cv[0:1, :1], "depth_mask": mask.bool() if mask is not None else None,
             "flow": fl[1:2], "flow_cov": flow_cov}
@@ -226,7 +228,8 @@ def score_only(match_cov: Tensor, score: ScoreBuffers) -> None:
     st = score.struct(mc.data_ptr())
     rc = lib.macvo_dense_postproc(None, None, H, W, 0.0, 0.0, None, None, None, None, None, C.byref(st), _stream())
     _check(rc, "macvo_dense_postproc(score)")
-    score.source_ptr, score.source_version = match_cov.data_ptr(), match_cov._version
+    LAUNCHES[0] += 1
+    score.generation += 1
 
 
 class CandidateList:
@@ -253,6 +256,7 @@ def select_candidates(score: ScoreBuffers, mask_width: int, max_match_cov: float
                                      int(mask_width), float(max_match_cov), out.idx.data_ptr(), out.n.data_ptr(),
                                      out.thresh.data_ptr(), out.status.data_ptr(), ws.data_ptr(), nbytes, _stream())
     _check(rc, "macvo_select_candidates")
+    LAUNCHES[0] += 3
 
 
 def select_mapping_candidates(depth: Tensor, depth_cov: Tensor, mask_width: int, max_depth: float,
@@ -268,6 +272,7 @@ def select_mapping_candidates(depth: Tensor, depth_cov: Tensor, mask_width: int,
                                              float(max_depth_cov), out.idx.data_ptr(), out.n.data_ptr(),
                                              ws.data_ptr(), nbytes, _stream())
     _check(rc, "macvo_select_mapping_candidates")
+    LAUNCHES[0] += 2
 
 
 def sample_candidates(cand: CandidateList, num_point: int) -> Tensor:
@@ -288,6 +293,7 @@ def sample_candidates(cand: CandidateList, num_point: int) -> Tensor:
         perm_d = perm.pin_memory().to(dev, non_blocking=True)
         _check(lib.macvo_gather_pixels(cand.idx.data_ptr(), perm_d.data_ptr(), k, cand.w, out.data_ptr(), _stream()),
                "macvo_gather_pixels")
+        LAUNCHES[0] += 1
     return out
 
 
@@ -305,6 +311,7 @@ def retrieve_pixels(pixel_uv: Tensor, scalar_map: Tensor) -> Tensor:
     out = torch.empty((Cc, K), dtype=torch.float32, device=sm.device)
     _check(lib.macvo_retrieve_pixels(kp.data_ptr(), int(kp.dtype == torch.int64), K, sm.data_ptr(), Cc, H, W,
                                      out.data_ptr(), _stream()), "macvo_retrieve_pixels")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -335,6 +342,7 @@ def match_covariance(kp: Tensor, depth_map: Tensor, flow_cov: Tensor | None, fx:
                                     min_flow_cov, min_depth_cov, match_cov_default, cov.data_ptr(),
                                     pt.data_ptr() if pt is not None else None, status.data_ptr(), _stream())
     _check(rc, "macvo_match_covariance")
+    LAUNCHES[0] += 1
     return cov, pt, status
 
 
@@ -359,6 +367,7 @@ def pgo_solve(pos_Tw: Tensor, kp2_uv: Tensor, kp2_disp: Tensor, uv_cov: Tensor, 
     rc = lib.macvo_pgo_solve(*(t.data_ptr() for t in P), K, C.cast(intr_c, C.c_void_p), pose.data_ptr(),
                              C.byref(prm), stats.data_ptr(), _stream())
     _check(rc, "macvo_pgo_solve")
+    LAUNCHES[0] += 1
     return pose, stats
 
 
@@ -373,4 +382,5 @@ def pgo_accumulate(pos_Tw: Tensor, kp2_uv: Tensor, kp2_disp: Tensor, uv_cov: Ten
     rc = lib.macvo_pgo_accumulate(*(t.data_ptr() for t in P), K, C.cast(intr_c, C.c_void_p), ps.data_ptr(),
                                   float(huber_delta), acc.data_ptr(), _stream())
     _check(rc, "macvo_pgo_accumulate")
+    LAUNCHES[0] += 1
     return acc

@@ -1,0 +1,385 @@
+"""B200 plugin classes for MAC-VO's `Module` interfaces (the drop-in boundary).
+
+    B200_FlowFormerCovFrontend       IFrontend          replaces CUDAGraph_FlowFormerCovFrontend (Frontend.py:264-353)
+    B200_CovAwareSelector_NoDepth    IKeypointSelector  replaces CovAwareSelector_NoDepth (KeypointSelector.py:349-407)
+    B200_MappingPointSelector        IKeypointSelector  replaces MappingPointSelector (KeypointSelector.py:78-100)
+    B200_MatchCovariance             ICovariance2to3    replaces MatchCovariance (Covariance/Project2to3.py:114-182)
+    B200_TwoFrame_PGO                IOptimizer         replaces TwoFrame_PGO (Optimization/TwoFramePGO/Optimizer.py:23-108)
+
+Same constructor signature (`__init__(config: SimpleNamespace)`), same `is_valid_config` contract
+(unknown keys are an error), same argument meaning and return types as the classes they replace; class
+names are new because the registry forbids duplicates. With MAC-VO importable they subclass MAC-VO's own
+interfaces (see `interfaces.py`); YAML selects them with `type: B200_...` — see INTEGRATION.md.
+
+All compute goes through `ops` (ctypes -> libmacvo_b200.so). No CPU fallback: constructing a plugin with a
+non-CUDA device raises.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from types import SimpleNamespace
+
+import torch
+
+from . import interfaces as _local
+from . import ops
+from .flowformer_cov import FlowFormerCovNet, synthetic_state_dict
+
+_REF = _local.reference_available()
+if _REF:   # subclass MAC-VO's own interfaces so that importing this module registers the plugins there
+    from DataLoader import StereoData  # type: ignore
+    from Module.Frontend.Frontend import IFrontend  # type: ignore
+    from Module.Frontend.StereoDepth import IStereoDepth  # type: ignore
+    from Module.Frontend.Matching import IMatcher  # type: ignore
+    from Module.KeypointSelector import IKeypointSelector  # type: ignore
+    from Module.Covariance.Project2to3 import ICovariance2to3  # type: ignore
+    from Module.Optimization.TwoFramePGO.Optimizer import TwoFrame_PGO as _PGOBase  # type: ignore
+    from Module.Optimization.TwoFramePGO.Graphs import GraphOutput as _RefGraphOutput  # type: ignore
+else:
+    StereoData = _local.StereoData
+    IFrontend, IStereoDepth, IMatcher = _local.IFrontend, _local.IStereoDepth, _local.IMatcher
+    IKeypointSelector, ICovariance2to3 = _local.IKeypointSelector, _local.ICovariance2to3
+    _PGOBase = _local.IOptimizer
+
+_DTYPES = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+def _require_cuda(device: str, who: str) -> torch.device:
+    if "cuda" not in str(device):
+        raise ValueError(f"{who}: the B200 plugins only run on a CUDA device (got device={device!r}); "
+                         "use the reference classes for CPU")
+    return torch.device(device)
+
+
+# ================================================================================================
+# Frontend
+# ================================================================================================
+class B200_FlowFormerCovFrontend(IFrontend):
+    """FlowFormerCov stereo + flow frontend: correlation volume and window lookup on sm_100a kernels,
+    dense post-processing + keypoint scoring fused into one pass, the whole `estimate_pair` replayed as a
+    CUDA graph (like CUDAGraph_FlowFormerCovFrontend, Frontend.py:301-353).
+
+    config: weight (checkpoint path, or "synthetic[:seed]" for the deterministic stand-in), device,
+    enc_dtype / dec_dtype in {fp32, fp16, bf16}, decoder_depth, enforce_positive_disparity,
+    cuda_graph (bool), score_kernel_size (odd int; NMS window of the fused keypoint scoring, 7 in the
+    reference configs)."""
+
+    def __init__(self, config: SimpleNamespace):
+        super().__init__(config)
+        self.device = _require_cuda(config.device, "B200_FlowFormerCovFrontend")
+        w = config.weight
+        if isinstance(w, str) and w.startswith("synthetic"):
+            sd = synthetic_state_dict(int(w.split(":")[1]) if ":" in w else 0)
+        else:
+            sd = torch.load(w, map_location="cpu", weights_only=True)
+        self.net = FlowFormerCovNet(sd, self.device, _DTYPES[config.enc_dtype], _DTYPES[config.dec_dtype],
+                                    decoder_depth=config.decoder_depth)
+        # the reference frontend enables TF32 tensor cores for the dense layers (Frontend.py:275-277)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+        torch.set_float32_matmul_precision("medium")
+        self._graph = None
+        self._static: dict = {}
+        self._score: ops.ScoreBuffers | None = None
+
+    @property
+    def provide_cov(self) -> tuple[bool, bool]:
+        return True, True
+
+    # ---- (a7) + fused (a8) scoring ---------------------------------------------------------------
+    def _postprocess(self, est_flow, est_cov, bl_fx: float):
+        H, W = est_flow.shape[-2:]
+        if self._score is None or (self._score.h, self._score.w) != (H, W):
+            self._score = ops.ScoreBuffers(H, W, self.device, int(getattr(self.config, "score_kernel_size", 7)))
+        return ops.dense_postproc(est_flow, est_cov, bl_fx, self.config.enforce_positive_disparity, score=self._score)
+
+    def _run(self, input_A, input_B, bl_fx: float):
+        est_flow, est_cov = self.net.inference(input_A, input_B)
+        return self._postprocess(est_flow.float(), est_cov.float(), bl_fx)
+
+    def _outputs(self, d: dict, clone: bool):
+        c = (lambda t: t.clone() if t is not None else None) if clone else (lambda t: t)
+        depth = IStereoDepth.Output(depth=c(d["depth"]), cov=c(d["depth_cov"]), disparity=c(d["disparity"]),
+                                    disparity_uncertainty=c(d["disparity_uncertainty"]), mask=c(d["depth_mask"]))
+        match = IMatcher.Output(flow=c(d["flow"]), cov=c(d["flow_cov"]), mask=None)
+        # let the selector plugin reuse the fused scores instead of re-reading the covariance map
+        self._score.generation += 1
+        match._b200_score = (self._score, self._score.generation, match.cov.data_ptr(), match.cov._version)  # type: ignore[attr-defined]
+        return depth, match
+
+    @torch.inference_mode()
+    def estimate_depth(self, frame: StereoData):
+        A = frame.imageL.to(self.device, non_blocking=True)
+        B = frame.imageR.to(self.device, non_blocking=True)
+        est_flow, est_cov = self.net.inference(A, B)
+        est_flow, est_cov = est_flow.float(), est_cov.float()
+        # B = 1 call: reuse the pair kernel by duplicating the slot (slot 1 outputs are ignored)
+        d = ops.dense_postproc(torch.cat([est_flow, est_flow]), torch.cat([est_cov, est_cov]),
+                               frame.frame_baseline * frame.fx, self.config.enforce_positive_disparity, score=None)
+        return IStereoDepth.Output(depth=d["depth"], cov=d["depth_cov"], disparity=d["disparity"],
+                                   disparity_uncertainty=est_cov[0:1, :1], mask=d["depth_mask"])
+
+    @torch.inference_mode()
+    def estimate_pair(self, frame_t1: StereoData, frame_t2: StereoData):
+        """-> (IStereoDepth.Output of t2, IMatcher.Output t1 -> t2); batches [t2.L, t1.L] vs [t2.R, t2.L]
+        exactly like the reference (Frontend.py:284-285)."""
+        input_A = torch.cat([frame_t2.imageL, frame_t1.imageL], dim=0)
+        input_B = torch.cat([frame_t2.imageR, frame_t2.imageL], dim=0)
+        bl_fx = frame_t2.frame_baseline * frame_t2.fx
+        if not getattr(self.config, "cuda_graph", True):
+            out = self._run(input_A.to(self.device, non_blocking=True), input_B.to(self.device, non_blocking=True), bl_fx)
+            return self._outputs(out, clone=False)
+        if self._graph is None:
+            sA = torch.empty(input_A.shape, dtype=torch.float32, device=self.device)
+            sB = torch.empty_like(sA)
+            sA.copy_(input_A)
+            sB.copy_(input_B)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):                     # warm-up: cuDNN autotune, workspace growth
+                    warm = self._run(sA, sB, bl_fx)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES[0]
+            with torch.cuda.graph(graph):
+                out = self._run(sA, sB, bl_fx)
+            self._graph = graph
+            self._static = {"A": sA, "B": sB, "out": out, "shape": tuple(input_A.shape), "bl_fx": bl_fx,
+                            "launches": ops.LAUNCHES[0] - n0}     # macvo_b200 kernels inside one replay
+            graph.replay()                             # (the reference returns its warm-up result here)
+            return self._outputs(out, clone=True)
+        st = self._static
+        assert tuple(input_A.shape) == st["shape"], f"Input shape mismatch for CUDAGraph replay: {input_A.shape} != {st['shape']}"
+        assert bl_fx == st["bl_fx"], "camera baseline * fx changed since the CUDA graph was captured"
+        st["A"].copy_(input_A, non_blocking=True)
+        st["B"].copy_(input_B, non_blocking=True)
+        self._graph.replay()
+        ops.LAUNCHES[0] += st["launches"]
+        return self._outputs(st["out"], clone=True)
+
+    @staticmethod
+    def retrieve_pixels(pixel_uv: torch.Tensor, scalar_map: torch.Tensor | None, interpolate: bool = False):
+        """(a9) gather kernel; same contract as IFrontend.retrieve_pixels (Frontend.py:104-118)."""
+        if scalar_map is None:
+            return None
+        if interpolate:
+            raise NotImplementedError("Not implemented yet")
+        if scalar_map.is_cuda and scalar_map.dtype == torch.float32 and pixel_uv.dtype in (torch.int64, torch.float32):
+            return ops.retrieve_pixels(pixel_uv.to(scalar_map.device), scalar_map)
+        return scalar_map[0, ..., pixel_uv[..., 1].long(), pixel_uv[..., 0].long()]   # e.g. the CPU colour image
+
+    @classmethod
+    def is_valid_config(cls, config: SimpleNamespace | None) -> None:
+        cls._enforce_config_spec(config, {
+            "weight": lambda s: isinstance(s, str),
+            "device": lambda s: isinstance(s, str) and "cuda" in s,
+            "dec_dtype": lambda b: b in ("fp32", "fp16", "bf16"),
+            "enc_dtype": lambda b: b in ("fp32", "fp16", "bf16"),
+            "enforce_positive_disparity": lambda b: isinstance(b, bool),
+            "decoder_depth": lambda v: isinstance(v, int),
+            "cuda_graph": lambda b: isinstance(b, bool),
+        })
+
+
+# ================================================================================================
+# Keypoint selectors
+# ================================================================================================
+class B200_CovAwareSelector_NoDepth(IKeypointSelector):
+    """Bit-exact replacement of CovAwareSelector_NoDepth.select_point (KeypointSelector.py:362-407).
+    One host round trip (the candidate count, needed for the CPU `torch.randperm`) instead of two."""
+
+    def __init__(self, config: SimpleNamespace):
+        super().__init__(config)
+        self.device = _require_cuda(config.device, "B200_CovAwareSelector_NoDepth")
+        self._score: ops.ScoreBuffers | None = None
+        self._cand: ops.CandidateList | None = None
+
+    @torch.inference_mode()
+    def select_point(self, frame, numPoint: int, depth0_est, depth1_est, match_est) -> torch.Tensor:
+        if match_est is None or match_est.cov is None:
+            raise ValueError("B200_CovAwareSelector_NoDepth needs match_est.cov (the reference falls back to a grid "
+                             "selector here; compose it with GridSelector in the YAML if that is wanted)")
+        cov = match_est.cov
+        H, W = cov.shape[-2:]
+        token = getattr(match_est, "_b200_score", None)
+        score = None
+        if token is not None:                              # scores fused into the frontend's post-processing pass
+            sc, gen, ptr, ver = token
+            if (sc.generation == gen and ptr == cov.data_ptr() and ver == cov._version
+                    and sc.ksize == self.config.kernel_size and (sc.h, sc.w) == (H, W)):
+                score = sc
+        if score is None:                                  # foreign frontend / modified map: score it ourselves
+            if self._score is None or (self._score.h, self._score.w) != (H, W):
+                self._score = ops.ScoreBuffers(H, W, self.device, self.config.kernel_size)
+            score = self._score
+            ops.score_only(cov.to(self.device), score)
+        if self._cand is None or self._cand.idx.numel() != H * W:
+            self._cand = ops.CandidateList(H, W, self.device)
+        ops.select_candidates(score, self.config.mask_width, self.config.max_match_cov, match_est.mask, self._cand)
+        return ops.sample_candidates(self._cand, numPoint)
+
+    @classmethod
+    def is_valid_config(cls, config: SimpleNamespace | None) -> None:
+        cls._enforce_config_spec(config, {
+            "device": lambda dev: isinstance(dev, str) and "cuda" in dev,
+            "mask_width": lambda m: isinstance(m, int) and m >= 0,
+            "kernel_size": lambda k: isinstance(k, int) and k > 0 and (k % 2 == 1) and k <= 15,
+            "max_match_cov": lambda c: isinstance(c, (int, float)) and c > 0.,
+        })
+
+
+class B200_MappingPointSelector(IKeypointSelector):
+    """Bit-exact replacement of MappingPointSelector.select_point (KeypointSelector.py:87-100)."""
+
+    def __init__(self, config: SimpleNamespace):
+        super().__init__(config)
+        self._cand: ops.CandidateList | None = None
+
+    @torch.inference_mode()
+    def select_point(self, frame, numPoint: int, depth0_est, depth1_est, match_est) -> torch.Tensor:
+        assert depth0_est.cov is not None
+        H, W = depth0_est.depth.shape[-2:]
+        if self._cand is None or self._cand.idx.numel() != H * W or self._cand.idx.device != depth0_est.depth.device:
+            self._cand = ops.CandidateList(H, W, depth0_est.depth.device)
+        ops.select_mapping_candidates(depth0_est.depth, depth0_est.cov, self.config.mask_width, self.config.max_depth,
+                                      self.config.max_depth_cov, self._cand)
+        return ops.sample_candidates(self._cand, numPoint)
+
+    @classmethod
+    def is_valid_config(cls, config: SimpleNamespace | None) -> None:
+        cls._enforce_config_spec(config, {
+            "max_depth": lambda v: isinstance(v, float),
+            "max_depth_cov": lambda v: isinstance(v, float),
+            "mask_width": lambda v: isinstance(v, int),
+        })
+
+
+# ================================================================================================
+# Covariance model
+# ================================================================================================
+class B200_MatchCovariance(ICovariance2to3):
+    """Replacement of MatchCovariance.estimate (Project2to3.py:124-182). Returns a CPU float64 (K,3,3)
+    tensor like the reference (its `create_3x3_matrix` assembles the result on the CPU, and
+    Odometry/MACVO.py multiplies it with CPU rotations) — filled by ONE device->host copy instead of nine."""
+
+    def __init__(self, config: SimpleNamespace):
+        super().__init__(config)
+        self.device = _require_cuda(config.device, "B200_MatchCovariance")
+        self.last_status: torch.Tensor | None = None
+
+    def estimate_device(self, frame, kp, depth_est, depth_cov, flow_cov, want_point: bool = False):
+        """Device-resident variant: (cov (K,3,3) fp64 CUDA, point (K,3) fp32 CUDA or None)."""
+        fc = flow_cov
+        if fc is not None and not (fc.is_cuda and fc.dtype == torch.float32 and fc.is_contiguous()):
+            raise ValueError("flow_cov must be a contiguous fp32 CUDA tensor (it is clamped in place, like the reference)")
+        cov, pt, status = ops.match_covariance(
+            kp.to(self.device), depth_est.depth, fc, frame.fx, frame.fy, frame.cx, frame.cy,
+            kernel_size=self.config.kernel_size, min_flow_cov=self.config.min_flow_cov,
+            min_depth_cov=self.config.min_depth_cov, match_cov_default=self.config.match_cov_default,
+            want_point=want_point)
+        self.last_status = status
+        return cov, pt
+
+    @torch.inference_mode()
+    def estimate(self, frame, kp, depth_est, depth_cov, flow_cov) -> torch.Tensor:
+        cov, _ = self.estimate_device(frame, kp, depth_est, depth_cov, flow_cov)
+        out = cov.cpu()
+        if int(self.last_status.item()) != 0:
+            raise IndexError("MatchCovariance: a keypoint's depth patch leaves the image")
+        return out
+
+    @classmethod
+    def is_valid_config(cls, config: SimpleNamespace | None) -> None:
+        cls._enforce_config_spec(config, {
+            "device": lambda dev: isinstance(dev, str) and "cuda" in dev,
+            "kernel_size": lambda k: isinstance(k, int) and k % 2 == 1 and 1 <= k <= 31,
+            "match_cov_default": lambda c: isinstance(c, (int, float)) and c > 0,
+            "min_depth_cov": lambda c: isinstance(c, (int, float)) and c > 0,
+            "min_flow_cov": lambda c: isinstance(c, (int, float)) and c > 0,
+        })
+
+
+# ================================================================================================
+# Two-frame pose-graph optimisation
+# ================================================================================================
+@dataclass
+class PGOInput:
+    """What Analytic_ReprojDisp_TwoFramePGO reads out of GraphInput (Graphs.py:76-134), as plain tensors."""
+    pos_Tw: torch.Tensor        # (K,3)  NED world points
+    kp2_uv: torch.Tensor        # (K,2)
+    kp2_disp: torch.Tensor      # (K,) or (K,1)
+    uv_cov: torch.Tensor        # (K,3)  sigma_uu, sigma_vv, sigma_uv
+    disp_cov: torch.Tensor      # (K,) or (K,1)
+    K: torch.Tensor             # (3,3)
+    baseline: float
+    init_pose: torch.Tensor     # (7,) [t, q_xyzw]
+    frame_idx: torch.Tensor | None = None
+    from_idx: torch.Tensor | None = None
+
+
+@dataclass
+class PGOOutput:
+    motion: torch.Tensor        # (1,7) float64 on the device (synchronise by reading it)
+    frame_idx: torch.Tensor | None
+    from_idx: torch.Tensor | None
+    stats: torch.Tensor | None = None
+
+
+def solve_two_frame_pgo(inp: PGOInput, device, cluster: int = 0) -> tuple[torch.Tensor, torch.Tensor]:
+    """fp32 map values -> float64 (the reference's `.to(dtype=torch.double)`, Optimizer.py:85) -> one launch."""
+    f64 = lambda t: t.detach().to(device=device, dtype=torch.float64, non_blocking=True).contiguous()
+    K = inp.K.detach().double().cpu()
+    intr = (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]),
+            float(torch.as_tensor(inp.baseline, dtype=torch.float32).double().reshape(-1)[0]))
+    return ops.pgo_solve(f64(inp.pos_Tw), f64(inp.kp2_uv), f64(inp.kp2_disp).reshape(-1), f64(inp.uv_cov),
+                         f64(inp.disp_cov).reshape(-1), intr, f64(inp.init_pose).reshape(7), cluster=cluster)
+
+
+class B200_TwoFrame_PGO(_PGOBase):
+    """Replacement of TwoFrame_PGO (graph_type "disp", analytic Jacobian): the whole Levenberg-Marquardt loop is
+    one persistent kernel launch; `start_optimize` returns immediately and `write_map` synchronises on the
+    result, which preserves the frontend / optimiser overlap MAC-VO gets from its spawned CPU process."""
+
+    @staticmethod
+    def init_context(config) -> dict:
+        if getattr(config, "graph_type", "disp") != "disp" or getattr(config, "autodiff", False):
+            raise ValueError("B200_TwoFrame_PGO implements graph_type 'disp' with the analytic Jacobian "
+                             "(the MACVO_Performant / MACVO_Fast configuration)")
+        return {"device": _require_cuda(config.device, "B200_TwoFrame_PGO"), "cluster": int(getattr(config, "cluster", 0))}
+
+    @staticmethod
+    def _optimize(context: dict, graph_data):
+        if isinstance(graph_data, PGOInput):
+            inp = graph_data
+        else:   # MAC-VO's GraphInput (Graphs.py:11-22)
+            obs, pts = graph_data.observations.data, graph_data.points.data
+            inp = PGOInput(pos_Tw=pts["pos_Tw"], kp2_uv=obs["pixel2_uv"], kp2_disp=obs["pixel2_disp"],
+                           uv_cov=obs["pixel2_uv_cov"], disp_cov=obs["pixel2_disp_cov"], K=graph_data.images_intrinsic,
+                           baseline=graph_data.baseline, init_pose=torch.as_tensor(graph_data.init_motion).reshape(-1)[:7],
+                           frame_idx=graph_data.frame_idx, from_idx=graph_data.from_idx)
+        pose, stats = solve_two_frame_pgo(inp, context["device"], context["cluster"])
+        if _REF and not isinstance(graph_data, PGOInput):
+            return context, _RefGraphOutput(motion=pose.reshape(1, 7), frame_idx=inp.frame_idx, from_idx=inp.from_idx)
+        return context, PGOOutput(motion=pose.reshape(1, 7), frame_idx=inp.frame_idx, from_idx=inp.from_idx, stats=stats)
+
+    if not _REF:
+        @classmethod
+        def is_valid_config(cls, config: SimpleNamespace | None) -> None:
+            cls._enforce_config_spec(config, {
+                "graph_type": lambda s: s in {"icp", "reproj", "disp"},
+                "device": lambda v: isinstance(v, str) and "cuda" in v,
+                "vectorize": lambda b: isinstance(b, bool),
+                "parallel": lambda b: b is False,
+                "autodiff": lambda b: isinstance(b, bool),
+            })
+
+
+PLUGINS = {
+    "frontend": B200_FlowFormerCovFrontend,
+    "keypoint": B200_CovAwareSelector_NoDepth,
+    "mappoint": B200_MappingPointSelector,
+    "cov": B200_MatchCovariance,
+    "optimizer": B200_TwoFrame_PGO,
+}
