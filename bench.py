@@ -102,7 +102,9 @@ def run_cpu(cfg: dict, frames_to_time: int, warm: int) -> dict:
     from macvo_b200.pipeline import TwoFrameOdometry
     from oracle import pipeline_cpu as pc
     dt = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
-    cores = os.cpu_count() or 1
+    # torch's CPU kernels stop scaling (and collapse from oversubscription) beyond ~16 threads on this workload:
+    # 128 threads measured 178 s/frame on the GPU box against ~9 s/frame with 8; use what the path can use
+    cores = min(os.cpu_count() or 1, int(os.environ.get("MACVO_BENCH_CPU_THREADS", 16)))
     torch.set_num_threads(cores)
     frames = synthetic.make_sequence(SEQ_LEN, H, W)
     torch.manual_seed(5)

@@ -45,6 +45,13 @@ else:
 _DTYPES = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
 
 
+def _version(t: torch.Tensor) -> int:
+    try:
+        return t._version
+    except RuntimeError:          # inference tensors do not track a version counter
+        return -1
+
+
 def _require_cuda(device: str, who: str) -> torch.device:
     if "cuda" not in str(device):
         raise ValueError(f"{who}: the B200 plugins only run on a CUDA device (got device={device!r}); "
@@ -105,7 +112,7 @@ class B200_FlowFormerCovFrontend(IFrontend):
         match = IMatcher.Output(flow=c(d["flow"]), cov=c(d["flow_cov"]), mask=None)
         # let the selector plugin reuse the fused scores instead of re-reading the covariance map
         self._score.generation += 1
-        match._b200_score = (self._score, self._score.generation, match.cov.data_ptr(), match.cov._version)  # type: ignore[attr-defined]
+        match._b200_score = (self._score, self._score.generation, match.cov.data_ptr(), _version(match.cov))  # type: ignore[attr-defined]
         return depth, match
 
     @torch.inference_mode()
@@ -207,7 +214,7 @@ class B200_CovAwareSelector_NoDepth(IKeypointSelector):
         score = None
         if token is not None:                              # scores fused into the frontend's post-processing pass
             sc, gen, ptr, ver = token
-            if (sc.generation == gen and ptr == cov.data_ptr() and ver == cov._version
+            if (sc.generation == gen and ptr == cov.data_ptr() and ver == _version(cov)
                     and sc.ksize == self.config.kernel_size and (sc.h, sc.w) == (H, W)):
                 score = sc
         if score is None:                                  # foreign frontend / modified map: score it ourselves

@@ -262,8 +262,13 @@ def lm_solve(g: GraphData, max_steps: int = 10, patience: int = 2, decreasing: f
     return pose
 
 
-def accumulate_packed(g: GraphData, pose: np.ndarray, W: np.ndarray, delta: float) -> np.ndarray:
-    """Packed accumulator used by the sharded (multi-GPU) path: [A upper 6x6 (21), b (6), loss (1)]."""
-    A, b, _, _ = normal_equations(g, pose, W, delta)
+def accumulate_packed(g: GraphData, pose: np.ndarray, delta: float = 0.1, W: np.ndarray | None = None) -> np.ndarray:
+    """The 55-entry packed accumulator of the sharded (multi-GPU) path, for a shard `g` of residual blocks:
+    [A = Js^T W Js upper 6x6 (21) | b = -Js^T W Rs (6) | G = Js^T Js upper (21) | h = Js^T Rs (6) | robust loss (1)]."""
+    if W is None:
+        W = np.stack([np.linalg.pinv(c, rcond=1e-15) for c in g.cov_blocks()]) if g.pos_Tw.shape[0] else np.zeros((0, 3, 3))
+    A, b, Js, Rs = normal_equations(g, pose, W, delta)
     iu = np.triu_indices(6)
-    return np.concatenate([A[:6, :6][iu], b[:6], [robust_loss(g, pose, delta)]])
+    G = np.einsum("kai,kaj->ij", Js, Js)
+    h = np.einsum("kai,ka->i", Js, Rs)
+    return np.concatenate([A[:6, :6][iu], b[:6], G[:6, :6][iu], h[:6], [robust_loss(g, pose, delta)]])

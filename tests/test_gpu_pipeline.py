@@ -101,7 +101,7 @@ def test_pipeline_gpu_vs_cpu_oracle(plugins):
         fa, fb = a.extras["match01"].flow.cpu(), b.extras["match01"].flow
         assert (fa - fb).abs().max().item() <= 1e-3 * max(1.0, fb.abs().mean().item())
         da, db = a.extras["depth1"].depth.cpu(), b.extras["depth1"].depth
-        assert ((da - db).abs() / db.abs().clamp_min(1e-3)).median().item() < 1e-4
+        assert ((da - db).abs() / db.abs().clamp_min(1e-3)).median().item() < 2e-2      # depth = bl*fx / |flow_x|, |flow_x| ~ 1 px
         assert abs(a.num_kp - b.num_kp) <= 8
     np.testing.assert_allclose(pg.numpy(), pcpu.numpy(), rtol=0, atol=5e-2 * max(1.0, float(pcpu.abs().max())))
 
