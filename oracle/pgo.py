@@ -16,7 +16,7 @@ Restates, in plain numpy float64:
 
 PARITY STATUS: the control flow and graph arithmetic are PINNED against the reference's own
 `LM_analytic` + `Analytic_ReprojDisp_TwoFramePGO` executed on top of `oracle/pypose_shim`
-(tests/golden/pgo_*.pt, tests/test_oracle_pgo.py). The pypose internals themselves are PARITY
+(tests/golden/pgo_*.pt, tests/test_oracle_golden.py). The pypose internals themselves are PARITY
 UNPINNED (no reference test or fixture pins them; they are restated from the published behaviour).
 Self-checks: analytic vs finite-difference Jacobian, recovery of a known synthetic pose.
 
