@@ -270,14 +270,18 @@ class FlowFormerCovNet:
                     dt = torch.float32  # MemoryDecoder.proj is not cast (covhead.py:52-58 omits it)
             else:
                 dt = self.enc_dtype
-            W[key] = t.detach().to(device=self.device, dtype=dt).contiguous()
+            t = t.detach().to(device=self.device, dtype=dt).contiguous()
+            if t.dim() == 4:        # conv filters: NHWC so that cuDNN runs its tensor-core kernels without layout round trips
+                t = t.contiguous(memory_format=torch.channels_last)
+            W[key] = t
         if missing:
             raise KeyError(f"checkpoint misses {len(missing)} tensors, e.g. {missing[:3]}")
         self.W = W
         # fused GRU gate filters (z|r share their input)
         for p in ("memory_decoder.update_block.gru.", "memory_decoder.cov_update.gru."):
             for o in "12":
-                W[p + f"convzr{o}.weight"] = torch.cat([W[p + f"convz{o}.weight"], W[p + f"convr{o}.weight"]], 0).contiguous()
+                W[p + f"convzr{o}.weight"] = torch.cat([W[p + f"convz{o}.weight"], W[p + f"convr{o}.weight"]], 0).contiguous(
+                    memory_format=torch.channels_last)
                 W[p + f"convzr{o}.bias"] = torch.cat([W[p + f"convz{o}.bias"], W[p + f"convr{o}.bias"]], 0).contiguous()
 
     def state_dict(self) -> dict[str, Tensor]:
@@ -287,6 +291,10 @@ class FlowFormerCovNet:
         return F.linear(x, self.W[p + ".weight"], self.W.get(p + ".bias"))
 
     def _conv(self, x: Tensor, p: str, stride=1, padding=0, groups=1) -> Tensor:
+        """conv2d on channels-last activations: maps stay (B, H, W, C)-strided between the convolutions, so a
+        1x1 conv is a plain GEMM and `tokens <-> map` reshapes are free views."""
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
         return F.conv2d(x, self.W[p + ".weight"], self.W.get(p + ".bias"), stride=stride, padding=padding, groups=groups)
 
     def _ln(self, x: Tensor, p: str, eps: float = 1e-5) -> Tensor:
@@ -310,13 +318,13 @@ class FlowFormerCovNet:
             x = x + self._svt_local_attn(self._ln(x, b0 + "norm1", 1e-6), (H, W), b0 + "attn.", heads)
             x = x + self._mlp(self._ln(x, b0 + "norm2", 1e-6), b0 + "mlp.")
             # PEG: depthwise 3x3 + identity
-            t = x.transpose(1, 2).reshape(B, C, H, W)
+            t = x.transpose(1, 2).reshape(B, C, H, W)          # channels-last view of the token matrix
             t = self._conv(t, p + f"pos_block.{s}.proj.0", padding=1, groups=C) + t
             x = t.flatten(2).transpose(1, 2)
             # block 1: globally sub-sampled attention
             x = x + self._svt_global_attn(self._ln(x, b1 + "norm1", 1e-6), (H, W), b1 + "attn.", heads, sr)
             x = x + self._mlp(self._ln(x, b1 + "norm2", 1e-6), b1 + "mlp.")
-            x = x.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+            x = x.reshape(B, H, W, C).permute(0, 3, 1, 2)      # (B, C, H, W) logical, channels-last in memory
         return x
 
     def _mlp(self, x: Tensor, p: str) -> Tensor:
@@ -367,14 +375,19 @@ class FlowFormerCovNet:
         x = self._conv(x, p + "proj.4", stride=2, padding=2)
         h, w = x.shape[2:]
 
+        # ffn_with_coord.0 acts on cat([x, sine(patch centre)]): the position half does not depend on the input,
+        # so it is folded into a per-position bias once per resolution and the concat disappears.
+        w0, b0 = self.W[p + "ffn_with_coord.0.weight"], self.W[p + "ffn_with_coord.0.bias"]
+
         def coord_term():
             xy = coords_grid(1, h, w, x.device, x.dtype) * 8 + 4
             enc = sine_embed(xy.view(1, 2, -1).permute(0, 2, 1), COST_INPUT_DIM)          # (1, hw, 64)
-            return enc.permute(0, 2, 1).reshape(1, COST_INPUT_DIM, h, w)
-        enc = self._memo(("pe", h, w, x.dtype), coord_term)
-        x = torch.cat([x, enc.expand(M, -1, -1, -1)], dim=1)
-        x = self._conv(F.relu(self._conv(x, p + "ffn_with_coord.0")), p + "ffn_with_coord.2")
-        return self._ln(x.flatten(2).transpose(1, 2), p + "norm")
+            return F.linear(enc, w0[:, COST_INPUT_DIM:, 0, 0], b0)                         # (1, hw, 128)
+        term = self._memo(("pe", h, w, x.dtype, x.device), coord_term)
+        t = x.permute(0, 2, 3, 1).reshape(M, h * w, COST_INPUT_DIM)                        # tokens (free view in NHWC)
+        t = F.relu(F.linear(t, w0[:, :COST_INPUT_DIM, 0, 0]) + term)
+        t = F.linear(t, self.W[p + "ffn_with_coord.2.weight"][:, :, 0, 0], self.W[p + "ffn_with_coord.2.bias"])
+        return self._ln(t, p + "norm")
 
     def _latent_layer(self, x: Tensor, p: str) -> Tensor:
         """SelfAttentionLayer over the 8 latent tokens of each source pixel (core/encoder.py:97-140)."""
@@ -387,7 +400,7 @@ class FlowFormerCovNet:
         """context_proj of the context map, tiled like `context.repeat(B//b, 1, 1, 1)` (twins.py:55-58):
         row i of the (B*8)-batch sees context[i % b] — a reference quirk that is kept."""
         b, _, H, W = context.shape
-        c = self._lin(context.view(b, -1, H * W).permute(0, 2, 1), p + "context_proj").view(b, H, W, -1)
+        c = self._lin(context.flatten(2).permute(0, 2, 1), p + "context_proj").view(b, H, W, -1)
         return c.repeat(reps, 1, 1, 1)
 
     def _vert_local_attn(self, x: Tensor, size, context: Tensor, p: str, ws: int = 7, heads: int = 8) -> Tensor:
@@ -486,7 +499,7 @@ class FlowFormerCovNet:
     def convex_upsample(flow: Tensor, mask: Tensor) -> Tensor:
         """`upsample_flow` (decoder.py:131-139): softmax over the 9 neighbours, 8x."""
         N, C, H, W = flow.shape
-        mask = mask.view(N, 9, 8, 8, H, W).softmax(dim=1)
+        mask = mask.reshape(N, 9, 8, 8, H, W).softmax(dim=1)
         up = F.unfold(8 * flow, (3, 3), padding=1).view(N, C, 9, H, W)
         out = (mask.unsqueeze(1) * up.unsqueeze(-3).unsqueeze(-3)).sum(dim=2)
         return out.permute(0, 1, 4, 2, 5, 3).reshape(N, C, 8 * H, 8 * W)
