@@ -93,6 +93,13 @@ typedef struct {
     float* cand_vals;       /* capacity h*w */
     int* n_cand;            /* 1 */
     int ksize;              /* odd, <= 15 */
+    /* depth-aware variant (CovAwareSelector.select_point, Module/KeypointSelector.py:260-334); all NULL for the
+     * NoDepth variant: quality = (depth_cov0 + depth_cov1) * (uu + vv - 2 uv); `flow_quality` receives the
+     * second factor, cand_vals its values at the NMS survivors and cand_vals2 depth_cov0 there. */
+    const float* depth_cov0; /* (h,w) */
+    const float* depth_cov1; /* (h,w) */
+    float* flow_quality;     /* h*w */
+    float* cand_vals2;       /* capacity h*w */
 } macvo_score_t;
 int macvo_dense_postproc(const float* est_flow, const float* est_cov, int h, int w, double bl_fx, double bl_fx_sq,
                          float* depth, float* disparity, float* depth_cov, uint8_t* depth_mask, float* flow_cov,
@@ -104,7 +111,8 @@ int macvo_dense_postproc(const float* est_flow, const float* est_cov, int h, int
  *      the NMS survivors), mask = nms & border & quality < threshold [& extra_mask], then the
  *      row-major ordered list of candidates (== torch.nonzero order).
  * cand_idx: capacity h*w int32 (linear pixel index row*w+col, ascending); *n_out: number written;
- * *thresh_out: the fp32 threshold; *status: 0 ok, 1 = no NMS survivor (reference raises).
+ * *thresh_out: the fp32 threshold; *status: 0 ok, 1 = no NMS survivor (torch.median of an empty tensor is NaN,
+ * python's min(max_match_cov, nan) keeps max_match_cov, and the candidate list is simply empty).
  * workspace: macvo_select_workspace_bytes(h, w) bytes.
  */
 size_t macvo_select_workspace_bytes(int h, int w);
@@ -112,6 +120,18 @@ int macvo_select_candidates(const float* quality, const uint8_t* nms, const floa
                             const uint8_t* extra_mask, int h, int w, int mask_width, double max_match_cov,
                             int* cand_idx, int* n_out, float* thresh_out, int* status, void* workspace,
                             size_t workspace_bytes, void* stream);
+
+/* (a8') CovAwareSelector.select_point candidates (Module/KeypointSelector.py:292-330): mask = nms & border
+ *      & depth0 < max_depth & depth1 < max_depth & depth_cov0 < min(max_depth_cov, 1.5 nanmedian(depth_cov0[nms]))
+ *      & flow_quality < min(max_match_cov, 1.5 nanmedian(flow_quality[nms])) [& mask_a & mask_b].
+ *      thresh_out[0] = depth-cov threshold, thresh_out[1] = flow threshold. */
+int macvo_select_candidates_depth(const float* flow_quality, const float* depth0, const float* depth1,
+                                  const float* depth_cov0, const uint8_t* nms, const float* cand_flow_quality,
+                                  const float* cand_depth_cov0, const int* n_cand, const uint8_t* mask_a,
+                                  const uint8_t* mask_b, int h, int w, int mask_width, double max_depth,
+                                  double max_depth_cov, double max_match_cov, int* cand_idx, int* n_out,
+                                  float* thresh_out, int* status, void* workspace, size_t workspace_bytes,
+                                  void* stream);
 
 /* (a8'') MappingPointSelector.select_point candidates (Module/KeypointSelector.py:87-97):
  *      depth < max_depth & depth_cov < max_depth_cov & border, row-major ordered. */

@@ -23,7 +23,9 @@ dense_score_kernel(const float* __restrict__ est_flow, const float* __restrict__
                    float bl_fx_sq, float* __restrict__ depth, float* __restrict__ disparity,
                    float* __restrict__ depth_cov, uint8_t* __restrict__ depth_mask, float* __restrict__ flow_cov,
                    const float* __restrict__ score_cov, float* __restrict__ quality, uint8_t* __restrict__ nms,
-                   float* __restrict__ cand_vals, int* __restrict__ n_cand, int radius) {
+                   float* __restrict__ cand_vals, int* __restrict__ n_cand, int radius,
+                   const float* __restrict__ dcov0, const float* __restrict__ dcov1, float* __restrict__ flow_quality,
+                   float* __restrict__ cand_vals2) {
     __shared__ float tile[TY + 2 * MAXR][TX + 2 * MAXR + 1];
     const int hw = h * w;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
@@ -65,7 +67,9 @@ dense_score_kernel(const float* __restrict__ est_flow, const float* __restrict__
         float a, b2, c;
         if (score_cov) { a = score_cov[pp]; b2 = score_cov[hw + pp]; c = score_cov[2 * hw + pp]; }
         else { a = est_cov[2 * hw + pp]; b2 = est_cov[3 * hw + pp]; c = 0.f; }
-        return __fsub_rn(__fadd_rn(a, b2), __fmul_rn(2.f, c));
+        const float fq = __fsub_rn(__fadd_rn(a, b2), __fmul_rn(2.f, c));
+        // depth-aware selector: quality = (depth_cov0 + depth_cov1) * flow quality (KeypointSelector.py:276-279)
+        return dcov0 ? __fmul_rn(__fadd_rn(dcov0[pp], dcov1[pp]), fq) : fq;
     };
     const int tw = TX + 2 * radius, th = TY + 2 * radius;
     for (int e = threadIdx.y * TX + threadIdx.x; e < tw * th; e += TX * TY) {
@@ -86,6 +90,12 @@ dense_score_kernel(const float* __restrict__ est_flow, const float* __restrict__
     const bool is_nms = !has_nan && (q == m);
     quality[p] = q;
     nms[p] = is_nms ? 1 : 0;
+    float fq_here = q, dc0_here = 0.f;
+    if (dcov0) {
+        fq_here = __fsub_rn(__fadd_rn(cuu, cvv), __fmul_rn(2.f, cuv));
+        dc0_here = dcov0[p];
+        flow_quality[p] = fq_here;
+    }
     if (is_nms) {   // warp-aggregated append (order irrelevant: only the median of the set is used)
         const unsigned mask = __activemask();
         const int lane = (threadIdx.y * TX + threadIdx.x) & 31;
@@ -93,7 +103,9 @@ dense_score_kernel(const float* __restrict__ est_flow, const float* __restrict__
         int base = 0;
         if (lane == leader) base = atomicAdd(n_cand, __popc(mask));
         base = __shfl_sync(mask, base, leader);
-        cand_vals[base + __popc(mask & ((1u << lane) - 1))] = q;
+        const int slot = base + __popc(mask & ((1u << lane) - 1));
+        cand_vals[slot] = fq_here;
+        if (dcov0) cand_vals2[slot] = dc0_here;
     }
 }
 
@@ -113,8 +125,8 @@ median_threshold_kernel(const float* __restrict__ vals, const int* __restrict__ 
     __shared__ unsigned hist[256];
     __shared__ unsigned s_prefix, s_k;
     const int n = *n_ptr;
-    if (n <= 0) {
-        if (threadIdx.x == 0) { *status = 1; *thresh_out = CUDART_NAN_F; }
+    if (n <= 0) {   // torch.median([]) = nan; python min(max, nan * 1.5) keeps max
+        if (threadIdx.x == 0) { *status = 1; *thresh_out = (float)max_match_cov; }
         return;
     }
     if (threadIdx.x == 0) { s_prefix = 0; s_k = (unsigned)((n - 1) / 2); *status = 0; }
@@ -152,16 +164,22 @@ median_threshold_kernel(const float* __restrict__ vals, const int* __restrict__ 
 
 constexpr int CHUNK = 1024;   // pixels per compaction block
 
-template <int MODE>   // 0: cov-aware (nms & border & q < thr & extra)   1: mapping (depth & depth_cov & border)
+// MODE 0: cov-aware (nms & border & q < thr & extra)   1: mapping (depth & depth_cov & border)
+// MODE 2: depth-aware cov selector: a = flow quality, b2 = depth_cov0, c/d = depth0/depth1 (< lim_a), thr[0] = depth-cov
+//         threshold, thr[1] = flow threshold, extra / extra2 = optional validity masks
+template <int MODE>
 __global__ void __launch_bounds__(256)
 flag_count_kernel(const float* __restrict__ a, const float* __restrict__ b2, const uint8_t* __restrict__ nms,
                   const uint8_t* __restrict__ extra, const float* __restrict__ thr_ptr, float lim_a, float lim_b,
-                  int h, int w, int mask_width, uint8_t* __restrict__ flags, int* __restrict__ block_counts) {
+                  int h, int w, int mask_width, uint8_t* __restrict__ flags, int* __restrict__ block_counts,
+                  const float* __restrict__ c = nullptr, const float* __restrict__ d = nullptr,
+                  const uint8_t* __restrict__ extra2 = nullptr) {
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const int hw = h * w;
-    const float thr = MODE == 0 ? *thr_ptr : 0.f;
+    const float thr = MODE == 0 ? *thr_ptr : (MODE == 2 ? thr_ptr[1] : 0.f);
+    const float thr_dc = MODE == 2 ? thr_ptr[0] : 0.f;
     int local = 0;
     for (int e = threadIdx.x; e < CHUNK; e += 256) {
         const int p = blockIdx.x * CHUNK + e;
@@ -171,7 +189,9 @@ flag_count_kernel(const float* __restrict__ a, const float* __restrict__ b2, con
         const bool border = mask_width > 0 && x >= mask_width && x < w - mask_width && y >= mask_width && y < h - mask_width;
         bool f;
         if (MODE == 0) f = border && nms[p] && (a[p] < thr) && (extra == nullptr || extra[p]);
-        else f = border && (a[p] < lim_a) && (b2[p] < lim_b);
+        else if (MODE == 1) f = border && (a[p] < lim_a) && (b2[p] < lim_b);
+        else f = border && nms[p] && (c[p] < lim_a) && (d[p] < lim_a) && (b2[p] < thr_dc) && (a[p] < thr) &&
+                 (extra == nullptr || extra[p]) && (extra2 == nullptr || extra2[p]);
         flags[p] = f ? 1 : 0;
         local += f ? 1 : 0;
     }
@@ -256,17 +276,23 @@ extern "C" int macvo_dense_postproc(const float* est_flow, const float* est_cov,
     int radius = 0;
     const float* score_cov = nullptr;
     float* quality = nullptr; uint8_t* nms = nullptr; float* cand = nullptr; int* ncand = nullptr;
+    const float *dc0 = nullptr, *dc1 = nullptr; float *fq = nullptr, *cand2 = nullptr;
     if (score) {
         if (!score->quality || !score->nms || !score->cand_vals || !score->n_cand) return MACVO_E_ARG;
         if (score->ksize < 1 || (score->ksize & 1) == 0 || score->ksize > 2 * MAXR + 1) return MACVO_E_ARG;
         radius = score->ksize / 2;
         score_cov = score->score_cov; quality = score->quality; nms = score->nms;
         cand = score->cand_vals; ncand = score->n_cand;
+        if (score->depth_cov0 || score->depth_cov1) {
+            if (!score->depth_cov0 || !score->depth_cov1 || !score->flow_quality || !score->cand_vals2) return MACVO_E_ARG;
+            dc0 = score->depth_cov0; dc1 = score->depth_cov1; fq = score->flow_quality; cand2 = score->cand_vals2;
+        }
     }
     dim3 grid(ceil_div(w, TX), ceil_div(h, TY)), block(TX, TY);
     dense_score_kernel<<<grid, block, 0, as_stream(stream)>>>(
         (depth || disparity || depth_cov || depth_mask) ? est_flow : nullptr, est_cov, h, w, (float)bl_fx,
-        (float)bl_fx_sq, depth, disparity, depth_cov, depth_mask, flow_cov, score_cov, quality, nms, cand, ncand, radius);
+        (float)bl_fx_sq, depth, disparity, depth_cov, depth_mask, flow_cov, score_cov, quality, nms, cand, ncand, radius,
+        dc0, dc1, fq, cand2);
     MACVO_LAUNCH_CHECK();
     return MACVO_OK;
 }
@@ -299,6 +325,31 @@ extern "C" int macvo_select_candidates(const float* quality, const uint8_t* nms,
     MACVO_LAUNCH_CHECK();
     flag_count_kernel<0><<<nblocks, 256, 0, st>>>(quality, nullptr, nms, extra_mask, thresh_out, 0.f, 0.f, h, w,
                                                   mask_width, flags, block_counts);
+    MACVO_LAUNCH_CHECK();
+    return run_compaction(flags, block_counts, nblocks, hw, cand_idx, n_out, st);
+}
+
+extern "C" int macvo_select_candidates_depth(const float* flow_quality, const float* depth0, const float* depth1,
+                                             const float* depth_cov0, const uint8_t* nms, const float* cand_fq,
+                                             const float* cand_dc0, const int* n_cand, const uint8_t* mask_a,
+                                             const uint8_t* mask_b, int h, int w, int mask_width, double max_depth,
+                                             double max_depth_cov, double max_match_cov, int* cand_idx, int* n_out,
+                                             float* thresh_out, int* status, void* workspace, size_t workspace_bytes,
+                                             void* stream) {
+    if (!flow_quality || !depth0 || !depth1 || !depth_cov0 || !nms || !cand_fq || !cand_dc0 || !n_cand || !cand_idx ||
+        !n_out || !thresh_out || !status || !workspace || h <= 0 || w <= 0 || mask_width < 0)
+        return MACVO_E_ARG;
+    if (workspace_bytes < macvo_select_workspace_bytes(h, w)) return MACVO_E_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    const int hw = h * w, nblocks = ceil_div(hw, CHUNK);
+    uint8_t* flags = static_cast<uint8_t*>(workspace);
+    int* block_counts = reinterpret_cast<int*>(static_cast<char*>(workspace) + align_up((size_t)hw, 256));
+    median_threshold_kernel<<<1, 1024, 0, st>>>(cand_dc0, n_cand, max_depth_cov, thresh_out, status);
+    MACVO_LAUNCH_CHECK();
+    median_threshold_kernel<<<1, 1024, 0, st>>>(cand_fq, n_cand, max_match_cov, thresh_out + 1, status);
+    MACVO_LAUNCH_CHECK();
+    flag_count_kernel<2><<<nblocks, 256, 0, st>>>(flow_quality, depth_cov0, nms, mask_a, thresh_out, (float)max_depth, 0.f,
+                                                  h, w, mask_width, flags, block_counts, depth0, depth1, mask_b);
     MACVO_LAUNCH_CHECK();
     return run_compaction(flags, block_counts, nblocks, hw, cand_idx, n_out, st);
 }

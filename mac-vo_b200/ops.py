@@ -30,7 +30,9 @@ class MacvoB200Error(RuntimeError):
 
 class _ScoreT(C.Structure):
     _fields_ = [("score_cov", C.c_void_p), ("quality", C.c_void_p), ("nms", C.c_void_p),
-                ("cand_vals", C.c_void_p), ("n_cand", C.c_void_p), ("ksize", C.c_int)]
+                ("cand_vals", C.c_void_p), ("n_cand", C.c_void_p), ("ksize", C.c_int),
+                ("depth_cov0", C.c_void_p), ("depth_cov1", C.c_void_p), ("flow_quality", C.c_void_p),
+                ("cand_vals2", C.c_void_p)]
 
 
 class _PgoParams(C.Structure):
@@ -49,6 +51,8 @@ EXPORTS = {
     "macvo_select_workspace_bytes": (C.c_size_t, [C.c_int] * 2),
     "macvo_select_candidates": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_double] + [C.c_void_p] * 5
                                 + [C.c_size_t, C.c_void_p]),
+    "macvo_select_candidates_depth": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_void_p] * 5
+                                      + [C.c_size_t, C.c_void_p]),
     "macvo_select_mapping_candidates": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 3 + [C.c_float] * 2
                                         + [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p]),
     "macvo_gather_pixels": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p] * 2),
@@ -183,9 +187,18 @@ class ScoreBuffers:
         self.n_cand = torch.zeros((1,), dtype=torch.int32, device=device)
         self.generation = 0        # bumped by whoever refills the buffers (host-side bookkeeping)
 
-    def struct(self, score_cov_ptr) -> _ScoreT:
+        self.flow_quality = None   # depth-aware variant only (allocated on first use)
+        self.cand_vals2 = None
+
+    def struct(self, score_cov_ptr, dcov0=None, dcov1=None) -> _ScoreT:
+        if dcov0 is not None and self.flow_quality is None:
+            self.flow_quality = torch.empty_like(self.quality)
+            self.cand_vals2 = torch.empty_like(self.cand_vals)
         return _ScoreT(score_cov_ptr, self.quality.data_ptr(), self.nms.data_ptr(), self.cand_vals.data_ptr(),
-                       self.n_cand.data_ptr(), self.ksize)
+                       self.n_cand.data_ptr(), self.ksize,
+                       dcov0.data_ptr() if dcov0 is not None else None, dcov1.data_ptr() if dcov1 is not None else None,
+                       self.flow_quality.data_ptr() if dcov0 is not None else None,
+                       self.cand_vals2.data_ptr() if dcov0 is not None else None)
 
 
 def dense_postproc(est_flow: Tensor, est_cov: Tensor, bl_fx: float, enforce_positive_disparity: bool = False,
@@ -230,6 +243,45 @@ def score_only(match_cov: Tensor, score: ScoreBuffers) -> None:
     _check(rc, "macvo_dense_postproc(score)")
     LAUNCHES[0] += 1
     score.generation += 1
+
+
+def score_depth_aware(match_cov: Tensor, depth_cov0: Tensor, depth_cov1: Tensor, score: ScoreBuffers) -> None:
+    """Scoring of the depth-aware selector: quality = (depth_cov0 + depth_cov1) * (uu + vv - 2 uv) + NMS."""
+    lib = load_library()
+    mc = _dev(match_cov, torch.float32, "score_depth_aware match_cov")
+    d0 = _dev(depth_cov0, torch.float32, "score_depth_aware depth_cov0")
+    d1 = _dev(depth_cov1, torch.float32, "score_depth_aware depth_cov1")
+    H, W = mc.shape[-2:]
+    score.n_cand.zero_()
+    st = score.struct(mc.data_ptr(), d0, d1)
+    rc = lib.macvo_dense_postproc(None, None, H, W, 0.0, 0.0, None, None, None, None, None, C.byref(st), _stream())
+    _check(rc, "macvo_dense_postproc(score, depth-aware)")
+    LAUNCHES[0] += 1
+    score.generation += 1
+
+
+def select_candidates_depth(score: ScoreBuffers, depth0: Tensor, depth1: Tensor, depth_cov0: Tensor, mask_width: int,
+                            max_depth: float, max_depth_cov: float, max_match_cov: float, mask_a: Tensor | None,
+                            mask_b: Tensor | None, out: "CandidateList") -> None:
+    lib = load_library()
+    h, w = score.h, score.w
+    nbytes = lib.macvo_select_workspace_bytes(h, w)
+    ws = _workspace("select", nbytes, score.quality.device)
+    u8 = lambda m: None if m is None else _dev(m.to(torch.uint8) if m.dtype != torch.uint8 else m, torch.uint8, "mask")
+    ma, mb = u8(mask_a), u8(mask_b)
+    d0, d1 = _dev(depth0, torch.float32, "depth0"), _dev(depth1, torch.float32, "depth1")
+    dc0 = _dev(depth_cov0, torch.float32, "depth_cov0")
+    if out.thresh.numel() < 2:
+        out.thresh = torch.zeros((2,), dtype=torch.float32, device=out.thresh.device)
+    rc = lib.macvo_select_candidates_depth(score.flow_quality.data_ptr(), d0.data_ptr(), d1.data_ptr(), dc0.data_ptr(),
+                                           score.nms.data_ptr(), score.cand_vals.data_ptr(), score.cand_vals2.data_ptr(),
+                                           score.n_cand.data_ptr(), ma.data_ptr() if ma is not None else None,
+                                           mb.data_ptr() if mb is not None else None, h, w, int(mask_width),
+                                           float(max_depth), float(max_depth_cov), float(max_match_cov),
+                                           out.idx.data_ptr(), out.n.data_ptr(), out.thresh.data_ptr(),
+                                           out.status.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    _check(rc, "macvo_select_candidates_depth")
+    LAUNCHES[0] += 4
 
 
 class CandidateList:
@@ -283,9 +335,7 @@ def sample_candidates(cand: CandidateList, num_point: int) -> Tensor:
     cand.host[0:1].copy_(cand.n, non_blocking=True)
     cand.host[1:2].copy_(cand.status, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    n, status = int(cand.host[0]), int(cand.host[1])
-    if status != 0:
-        raise RuntimeError("median() input tensor cannot be empty: no NMS survivor in the covariance map")
+    n = int(cand.host[0])       # host[1] = 1 flags "no NMS survivor" (then n == 0, like the reference: median([]) = nan)
     perm = torch.randperm(n)[:num_point]
     k = perm.numel()
     out = torch.empty((k, 2), dtype=torch.int64, device=dev)

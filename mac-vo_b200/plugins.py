@@ -2,6 +2,7 @@
 
     B200_FlowFormerCovFrontend       IFrontend          replaces CUDAGraph_FlowFormerCovFrontend (Frontend.py:264-353)
     B200_CovAwareSelector_NoDepth    IKeypointSelector  replaces CovAwareSelector_NoDepth (KeypointSelector.py:349-407)
+    B200_CovAwareSelector            IKeypointSelector  replaces CovAwareSelector (KeypointSelector.py:250-347)
     B200_MappingPointSelector        IKeypointSelector  replaces MappingPointSelector (KeypointSelector.py:78-100)
     B200_MatchCovariance             ICovariance2to3    replaces MatchCovariance (Covariance/Project2to3.py:114-182)
     B200_TwoFrame_PGO                IOptimizer         replaces TwoFrame_PGO (Optimization/TwoFramePGO/Optimizer.py:23-108)
@@ -237,6 +238,47 @@ class B200_CovAwareSelector_NoDepth(IKeypointSelector):
         })
 
 
+class B200_CovAwareSelector(IKeypointSelector):
+    """Bit-exact replacement of CovAwareSelector.select_point (KeypointSelector.py:260-334): the depth-aware
+    selector of Paper_Reproduce.yaml (quality = (depth_cov0 + depth_cov1) * flow quality, depth and depth-cov gates)."""
+
+    def __init__(self, config: SimpleNamespace):
+        super().__init__(config)
+        self.device = _require_cuda(config.device, "B200_CovAwareSelector")
+        self._score: ops.ScoreBuffers | None = None
+        self._cand: ops.CandidateList | None = None
+
+    @torch.inference_mode()
+    def select_point(self, frame, numPoint: int, depth0_est, depth1_est, match_est) -> torch.Tensor:
+        assert depth0_est.cov is not None
+        assert depth1_est.cov is not None
+        if match_est is None or match_est.cov is None:
+            raise ValueError("B200_CovAwareSelector needs match_est.cov")
+        if self.config.max_depth == "auto":
+            self.config.max_depth = frame.fx * frame.frame_baseline
+        H, W = match_est.cov.shape[-2:]
+        if self._score is None or (self._score.h, self._score.w) != (H, W):
+            self._score = ops.ScoreBuffers(H, W, self.device, self.config.kernel_size)
+            self._cand = ops.CandidateList(H, W, self.device)
+        dev = self.device
+        ops.score_depth_aware(match_est.cov.to(dev), depth0_est.cov.to(dev), depth1_est.cov.to(dev), self._score)
+        ops.select_candidates_depth(self._score, depth0_est.depth.to(dev), depth1_est.depth.to(dev), depth0_est.cov.to(dev),
+                                    self.config.mask_width, self.config.max_depth, self.config.max_depth_cov,
+                                    self.config.max_match_cov, depth0_est.mask, match_est.mask, self._cand)
+        return ops.sample_candidates(self._cand, numPoint)
+
+    @classmethod
+    def is_valid_config(cls, config: SimpleNamespace | None) -> None:
+        cls._enforce_config_spec(config, {
+            "device": lambda dev: isinstance(dev, str) and "cuda" in dev,
+            "mask_width": lambda m: isinstance(m, int) and m >= 0,
+            "max_depth": lambda dist: (dist == "auto") or (isinstance(dist, (int, float)) and dist > 0.),
+            "kernel_size": lambda k: isinstance(k, int) and k > 0 and (k % 2 == 1) and k <= 15,
+            "max_depth_cov": lambda c: isinstance(c, (int, float)) and c > 0.,
+            "max_match_cov": lambda c: isinstance(c, (int, float)) and c > 0.,
+        })
+
+
 class B200_MappingPointSelector(IKeypointSelector):
     """Bit-exact replacement of MappingPointSelector.select_point (KeypointSelector.py:87-100)."""
 
@@ -386,6 +428,7 @@ class B200_TwoFrame_PGO(_PGOBase):
 PLUGINS = {
     "frontend": B200_FlowFormerCovFrontend,
     "keypoint": B200_CovAwareSelector_NoDepth,
+    "keypoint_depth": B200_CovAwareSelector,
     "mappoint": B200_MappingPointSelector,
     "cov": B200_MatchCovariance,
     "optimizer": B200_TwoFrame_PGO,

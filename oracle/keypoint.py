@@ -6,6 +6,7 @@ identical):
 
 * `cov_aware_select_nodepth` <- CovAwareSelector_NoDepth.select_point  Module/KeypointSelector.py:362-407
 * `mapping_select`           <- MappingPointSelector.select_point      Module/KeypointSelector.py:87-100
+* `cov_aware_select`         <- CovAwareSelector.select_point          Module/KeypointSelector.py:260-334
 * `candidate_mask_nodepth`   — the deterministic part of the first (everything before randperm)
 
 PINNED by tests/golden/selector_*.pt (generated from the reference classes themselves).
@@ -49,6 +50,28 @@ def cov_aware_select_nodepth(match_cov: Tensor, num_point: int, kernel_size: int
                              max_match_cov: float = 100.0, match_mask: Tensor | None = None) -> Tensor:
     """-> int64 (K, 2) in (u, v) order; consumes one `torch.randperm` from the CPU default generator."""
     mask, _ = candidate_mask_nodepth(match_cov, kernel_size, mask_width, max_match_cov, match_mask)
+    return _sample(mask, num_point)
+
+
+def cov_aware_select(match_cov: Tensor, depth0: Tensor, depth0_cov: Tensor, depth1: Tensor, depth1_cov: Tensor,
+                     num_point: int, kernel_size: int = 7, mask_width: int = 32, max_depth: float = 80.0,
+                     max_depth_cov: float = 250.0, max_match_cov: float = 100.0, depth0_mask: Tensor | None = None,
+                     match_mask: Tensor | None = None) -> Tensor:
+    """CovAwareSelector.select_point (Module/KeypointSelector.py:260-334), the depth-aware variant."""
+    quality = depth0_cov + depth1_cov
+    fq = (match_cov[:, 0] + match_cov[:, 1] - 2 * match_cov[:, 2]).unsqueeze(1)
+    quality = quality * fq
+    eroded = -torch.nn.functional.max_pool2d(-quality, kernel_size=kernel_size, stride=1, padding=kernel_size // 2)
+    nms = torch.logical_and(quality == eroded, ~quality.isnan())
+    border = _border_mask(nms, mask_width)
+    depth_mask = (depth0 < max_depth) & (depth1 < max_depth)
+    thr0 = min(max_depth_cov, depth0_cov[nms].nanmedian().item() * 1.5)
+    thrf = min(max_match_cov, fq[nms].nanmedian().item() * 1.5)
+    mask = nms & border & depth_mask & (depth0_cov < thr0) & (fq < thrf)
+    if depth0_mask is not None:
+        mask = mask & depth0_mask
+    if match_mask is not None:
+        mask = mask & match_mask
     return _sample(mask, num_point)
 
 

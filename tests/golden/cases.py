@@ -99,6 +99,17 @@ def selector_inputs(H: int, W: int, variant: str, seed: int = 4) -> tuple[Tensor
     return flow, cov
 
 
+SELECTOR_DEPTH_CASES = {"depth_small": (160, 224, 64, "plain"), "depth_cfgA": (480, 640, 512, "plain"),
+                        "depth_masked": (160, 224, 128, "masked"), "depth_nan": (160, 224, 128, "nan")}
+
+
+def selector_depth_inputs(H: int, W: int, variant: str):
+    """two `estimate_pair`-like network outputs (previous / current frame) for the depth-aware selector"""
+    f0, c0 = selector_inputs(H, W, variant, seed=14)
+    f1, c1 = selector_inputs(H, W, variant, seed=4)
+    return (f0, c0), (f1, c1)
+
+
 def selector_match_mask(H: int, W: int, seed: int = 7) -> Tensor:
     return torch.rand(1, 1, H, W, generator=_gen(seed + H + W)) > 0.3
 

@@ -47,7 +47,7 @@ def main() -> None:
     from Module.Frontend.Frontend import FlowFormerCovFrontend, IFrontend
     from Module.Frontend.StereoDepth import IStereoDepth
     from Module.Frontend.Matching import IMatcher
-    from Module.KeypointSelector import CovAwareSelector_NoDepth, MappingPointSelector
+    from Module.KeypointSelector import CovAwareSelector_NoDepth, MappingPointSelector, CovAwareSelector
     from Module.Covariance.Project2to3 import MatchCovariance
     from Module.Optimization.TwoFramePGO.Optimizer import TwoFrame_PGO
     from Module.Optimization.TwoFramePGO.Graphs import GraphInput
@@ -111,6 +111,21 @@ def main() -> None:
         kp = sel.select_point(frame, num, depth, depth, match)
         mp = mapsel.select_point(frame, 2000, depth, depth, match)      # second randperm of the frame
         save(f"selector_{name}.pt", {"shape": (H, W), "num": num, "variant": variant, "kp": kp, "map_kp": mp})
+
+    dsel = CovAwareSelector(SimpleNamespace(device="cpu", kernel_size=7, mask_width=32, max_depth="auto",
+                                            max_depth_cov=250.0, max_match_cov=100.0))
+    for name, (H, W, num, variant) in cases.SELECTOR_DEPTH_CASES.items():
+        (f0, c0), (f1, c1) = cases.selector_depth_inputs(H, W, variant)
+        frame = stereo(H, W, 320.0, 0.25)
+        depth0 = FlowFormerCovFrontend.inference_2_depth(f0[0:1], c0[0:1], frame, variant == "masked")
+        depth1 = FlowFormerCovFrontend.inference_2_depth(f1[0:1], c1[0:1], frame, False)
+        match = FlowFormerCovFrontend.inference_2_match(f1[1:2], c1[1:2])
+        if variant == "masked":
+            match.mask = cases.selector_match_mask(H, W)
+            depth0.mask = ~depth0.mask          # reference contract: True = valid (StereoDepth.py:28-30)
+        torch.manual_seed(cases.SELECTOR_RNG_SEED)
+        kp = dsel.select_point(frame, num, depth0, depth1, match)
+        save(f"selector_{name}.pt", {"shape": (H, W), "num": num, "variant": variant, "kp": kp})
 
     # ---- covariance model (a10) ---------------------------------------------------------------
     covm = MatchCovariance(SimpleNamespace(device="cpu", kernel_size=31, match_cov_default=0.25,

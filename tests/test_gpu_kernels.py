@@ -184,15 +184,35 @@ def test_selector_standalone_scoring_equals_fused(ops):
     assert int(fused.n_cand.item()) == int(alone.n_cand.item()) == int(alone.nms.sum().item())
 
 
-def test_selector_empty_raises(ops):
+def test_selector_empty_nms_set_gives_no_keypoints(ops):
+    """all-NaN covariance map: no NMS survivor -> threshold = max_match_cov, 0 keypoints, no error (like the reference)"""
     H, W = 96, 128
     cov = torch.full((1, 3, H, W), float("nan"))
     score = ops.ScoreBuffers(H, W, DEV, 7)
     ops.score_only(cov.to(DEV), score)
     cand = ops.CandidateList(H, W, DEV)
     ops.select_candidates(score, 32, 100.0, None, cand)
-    with pytest.raises(RuntimeError):
-        ops.sample_candidates(cand, 10)
+    kp = ops.sample_candidates(cand, 10)
+    assert kp.shape == (0, 2) and kp.dtype == torch.int64
+    assert cand.thresh[0].item() == 100.0 and int(cand.status.item()) == 1
+
+
+@pytest.mark.parametrize("name", list(cases.SELECTOR_DEPTH_CASES))
+def test_depth_aware_selector_bit_exact(ops, golden, name):
+    """(a8') CovAwareSelector: quality = (depth_cov0 + depth_cov1) * flow quality, two medians, depth gates"""
+    g = golden(f"selector_{name}.pt")
+    H, W = g["shape"]
+    (f0, c0), (f1, c1) = cases.selector_depth_inputs(H, W, g["variant"])
+    d0 = ops.dense_postproc(f0.to(DEV), c0.to(DEV), 0.25 * 320.0, g["variant"] == "masked")
+    d1 = ops.dense_postproc(f1.to(DEV), c1.to(DEV), 0.25 * 320.0, False)
+    m0 = ~d0["depth_mask"] if g["variant"] == "masked" else None
+    mm = cases.selector_match_mask(H, W).to(DEV) if g["variant"] == "masked" else None
+    score, cand = ops.ScoreBuffers(H, W, DEV, 7), ops.CandidateList(H, W, DEV)
+    ops.score_depth_aware(d1["flow_cov"], d0["depth_cov"], d1["depth_cov"], score)
+    ops.select_candidates_depth(score, d0["depth"], d1["depth"], d0["depth_cov"], 32, 320.0 * 0.25, 250.0, 100.0, m0, mm, cand)
+    torch.manual_seed(cases.SELECTOR_RNG_SEED)
+    kp = ops.sample_candidates(cand, g["num"])
+    assert torch.equal(kp.cpu(), g["kp"]), "depth-aware keypoint indices must be bit-exact"
 
 
 # ---- (a9) retrieve_pixels ---------------------------------------------------------------------------------------

@@ -75,6 +75,32 @@ def test_selectors_bit_exact(golden, name):
     assert torch.equal(mp, g["map_kp"])
 
 
+def _depth_selector_inputs(g):
+    H, W = g["shape"]
+    (f0, c0), (f1, c1) = cases.selector_depth_inputs(H, W, g["variant"])
+    d0 = ofe.dense_postproc(f0, c0, 0.25, 320.0, g["variant"] == "masked")
+    d1 = ofe.dense_postproc(f1, c1, 0.25, 320.0)
+    m0 = ~d0["depth_mask"] if g["variant"] == "masked" else None
+    mm = cases.selector_match_mask(H, W) if g["variant"] == "masked" else None
+    return d0, d1, m0, mm
+
+
+@pytest.mark.parametrize("name", list(cases.SELECTOR_DEPTH_CASES))
+def test_depth_aware_selector_bit_exact(golden, name):
+    g = golden(f"selector_{name}.pt")
+    d0, d1, m0, mm = _depth_selector_inputs(g)
+    torch.manual_seed(cases.SELECTOR_RNG_SEED)
+    kp = okp.cov_aware_select(d1["flow_cov"], d0["depth"], d0["depth_cov"], d1["depth"], d1["depth_cov"], g["num"],
+                              7, 32, 320.0 * 0.25, 250.0, 100.0, m0, mm)
+    assert torch.equal(kp, g["kp"])
+
+
+def test_selector_empty_nms_set_gives_no_keypoints():
+    """torch.median([]) is nan and python's min(max, nan) keeps max: the reference returns 0 keypoints, no error"""
+    cov = torch.full((1, 3, 96, 128), float("nan"))
+    assert okp.cov_aware_select_nodepth(cov, 10).shape == (0, 2)
+
+
 @pytest.mark.parametrize("name", list(cases.COV_CASES))
 def test_match_covariance(golden, name):
     g = golden(f"covariance_{name}.pt")
