@@ -106,6 +106,10 @@ def run_cpu(cfg: dict, frames_to_time: int, warm: int) -> dict:
     # 128 threads measured 178 s/frame on the GPU box against ~9 s/frame with 8; use what the path can use
     cores = min(os.cpu_count() or 1, int(os.environ.get("MACVO_BENCH_CPU_THREADS", 16)))
     torch.set_num_threads(cores)
+    # the B200 frontend (like the reference's CUDA-graph frontend) sets matmul precision "medium" process-wide; the
+    # reference's CPU path never does, and on CPUs with bf16 units "medium" changes fp32 matmuls -> pin "highest"
+    prev_prec = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("highest")
     frames = synthetic.make_sequence(SEQ_LEN, H, W)
     torch.manual_seed(5)
     odo = TwoFrameOdometry(pc.CpuFrontend(synthetic_state_dict(0), dt[cfg["enc_dtype"]], dt[cfg["dec_dtype"]]),
@@ -120,6 +124,7 @@ def run_cpu(cfg: dict, frames_to_time: int, warm: int) -> dict:
         odo.run_pair(frames[idx % SEQ_LEN]); idx += 1
     odo.finish()
     dt_s = time.perf_counter() - t0
+    torch.set_float32_matmul_precision(prev_prec)
     return {"value": frames_to_time / dt_s, "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": f"{frames_to_time} frame(s) of the same 640x480 workload after {warm} warm-up, "
                       f"{dt_s / frames_to_time:.2f} s/frame, torch CPU kernels with {cores} threads"}
