@@ -203,6 +203,24 @@ int macvo_pgo_accumulate(const double* pos_Tw, const double* kp2_uv, const doubl
                          const double* disp_cov, int k, const double* intr, const double* pose, double huber_delta,
                          double* acc, void* stream);
 
+/* ---- frontend "next" rows: memory-bound layers of the cost perceiver ----------------
+ * fp32 only; replace the torch ops of Module/Network/FlowFormer/core/encoder.py:12-55 (PatchEmbed conv1 + pad),
+ * the nn.LayerNorm calls of core/attention.py / core/twins.py / core/Twins/svt_large.py, and their
+ * softmax(q k^T / sqrt(d)) v products (core/attention.py:6-29, core/twins.py:103-114,173-183).
+ */
+/* y = LayerNorm(x) over the last dim; x, y (rows, channels) contiguous; channels in {128, 256, 512}. */
+int macvo_layer_norm(const float* x, const float* weight, const float* bias, float* y, long long rows,
+                     int channels, float eps, void* stream);
+/* maps (n_maps, 1, h, w) -> out (n_maps, ho, wo, 16) [NHWC], ho = ceil8(h)/2, wo = ceil8(w)/2:
+ * ReLU(conv2d(zero-pad to multiples of 8, weight (16,1,6,6), stride 2, padding 2) + bias). */
+int macvo_patch_embed_conv1(const float* maps, const float* weight, const float* bias, float* out,
+                            long long n_maps, int h, int w, void* stream);
+/* out = softmax(q k^T / sqrt(head_dim)) v per (batch, head); q (batch | 1, nq, heads, head_dim),
+ * k, v (batch, nk, heads, head_dim), out (batch, nq, heads, head_dim); head_dim in {16, 32};
+ * q_broadcast != 0: one query set shared by every batch element. */
+int macvo_small_attention(const float* q, const float* k, const float* v, float* out, int batch, int nq, int nk,
+                          int heads, int head_dim, int q_broadcast, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,327 @@
+// Frontend "next" rows: the memory-bound glue of the FlowFormerCov cost perceiver that
+// cuDNN / ATen run far below HBM speed at these shapes (measured on B200, profiles/r01_probe_attention.log):
+//
+//   layer_norm          (9600*80, 128) fp32: ATen 1136 us for 786 MB of traffic      -> warp-per-row kernel
+//   patch_embed_conv1   1 -> 16 ch, 6x6 stride 2 over 9600 cost maps: cuDNN 3636 us  -> direct conv, map in smem,
+//                       fused zero padding (F.pad to a multiple of 8) + bias + ReLU, NHWC output
+//   small_attention     head_dim 16 / 32, <= 512 keys, fp32: SDPA (mem-efficient sm80 kernel) 0.3 - 2.8 ms per call
+//                       -> K, V of one (batch, head) staged in shared memory, one query per thread, online softmax
+//
+// They replace torch ops inside the network (Module/Network/FlowFormer/core/encoder.py:12-55 PatchEmbed,
+// core/attention.py:6-29, core/twins.py:103-114,173-183, core/Twins/svt_large.py:111-114,161-164); numerics:
+// fp32 throughout, exact erf-free ops only, parity vs torch fp32 in tests/test_gpu_nn_kernels.py.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+// ---- LayerNorm over the last dimension, one warp per row, C = 32 * VPL --------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                  float* __restrict__ y, long long rows, float eps) {
+    constexpr int C = 32 * VPL;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + row * C;
+    float v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL / 4; ++i) {                           // lane owns float4 chunks lane + 32 i
+        const float4 t = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        s += (t.x + t.y) + (t.z + t.w);
+    }
+    const float mean = warp_sum(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+    float* yr = y + row * C;
+#pragma unroll
+    for (int i = 0; i < VPL / 4; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        const float4 ww = *reinterpret_cast<const float4*>(w + c), bb = *reinterpret_cast<const float4*>(b + c);
+        float4 o;
+        o.x = (v[4 * i] - mean) * rstd * ww.x + bb.x;
+        o.y = (v[4 * i + 1] - mean) * rstd * ww.y + bb.y;
+        o.z = (v[4 * i + 2] - mean) * rstd * ww.z + bb.z;
+        o.w = (v[4 * i + 3] - mean) * rstd * ww.w + bb.w;
+        *reinterpret_cast<float4*>(yr + c) = o;
+    }
+}
+
+// ---- PatchEmbed conv1: (M,1,H,W) -> ReLU(conv 6x6 s2 p2, 16 ch) as (M, Ho, Wo, 16) NHWC -----------------
+// The reference first zero-pads H, W up to multiples of 8 (encoder.py:35-38); here out-of-range taps simply
+// read 0. One CTA per cost map: the whole map (<= 96 x 160 fp32) sits in shared memory.
+constexpr int PE_C = 16, PE_K = 6;
+__global__ void __launch_bounds__(256)
+patch_conv1_kernel(const float* __restrict__ maps, const float* __restrict__ wgt, const float* __restrict__ bias,
+                   float* __restrict__ out, int h, int w, int ho, int wo) {
+    extern __shared__ float sm[];
+    float* s_map = sm;                                   // (h + 4) x (wp) with a 2-pixel zero frame on the top / left
+    const int hp = 2 * ho + 4, wp = 2 * wo + 4;          // covers every tap of every output
+    float* s_w = sm + hp * wp;                           // [36][16]
+    const float* src = maps + (long long)blockIdx.x * h * w;
+    for (int e = threadIdx.x; e < hp * wp; e += blockDim.x) {
+        const int y = e / wp - 2, x = e % wp - 2;
+        s_map[e] = (y >= 0 && y < h && x >= 0 && x < w) ? __ldg(src + y * w + x) : 0.f;
+    }
+    for (int e = threadIdx.x; e < PE_C * 36; e += blockDim.x) {       // wgt is (16,1,6,6): -> [tap][ch]
+        const int c = e / 36, t = e % 36;
+        s_w[t * PE_C + c] = wgt[e];
+    }
+    __syncthreads();
+    float* dst = out + (long long)blockIdx.x * ho * wo * PE_C;
+    const int wo2 = wo >> 1;                                          // wo is a multiple of 4
+    for (int p = threadIdx.x; p < ho * wo2; p += blockDim.x) {        // two horizontally adjacent outputs per thread
+        const int oy = p / wo2, ox = (p % wo2) * 2;
+        float2 a0[PE_C / 2], a1[PE_C / 2];
+#pragma unroll
+        for (int c = 0; c < PE_C / 2; ++c) a0[c] = a1[c] = make_float2(bias[2 * c], bias[2 * c + 1]);
+        const float* base = s_map + (2 * oy) * wp + 2 * ox;           // tap (ky,kx) reads input (2oy-2+ky, 2ox-2+kx)
+#pragma unroll 1
+        for (int ky = 0; ky < PE_K; ++ky) {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 t = *reinterpret_cast<const float2*>(base + ky * wp + 2 * e);
+                x[2 * e] = t.x; x[2 * e + 1] = t.y;
+            }
+#pragma unroll
+            for (int kx = 0; kx < PE_K; ++kx) {
+                const float4* wv = reinterpret_cast<const float4*>(s_w + (ky * PE_K + kx) * PE_C);
+                const float2 x0 = make_float2(x[kx], x[kx]), x1 = make_float2(x[kx + 2], x[kx + 2]);
+#pragma unroll
+                for (int c4 = 0; c4 < PE_C / 4; ++c4) {
+                    const float4 ww = wv[c4];
+                    a0[2 * c4] = __ffma2_rn(x0, make_float2(ww.x, ww.y), a0[2 * c4]);
+                    a0[2 * c4 + 1] = __ffma2_rn(x0, make_float2(ww.z, ww.w), a0[2 * c4 + 1]);
+                    a1[2 * c4] = __ffma2_rn(x1, make_float2(ww.x, ww.y), a1[2 * c4]);
+                    a1[2 * c4 + 1] = __ffma2_rn(x1, make_float2(ww.z, ww.w), a1[2 * c4 + 1]);
+                }
+            }
+        }
+        float4* o = reinterpret_cast<float4*>(dst + ((long long)oy * wo + ox) * PE_C);   // 2 x 16 channels = 128 B
+#pragma unroll
+        for (int c4 = 0; c4 < PE_C / 4; ++c4) {
+            o[c4] = make_float4(fmaxf(a0[2 * c4].x, 0.f), fmaxf(a0[2 * c4].y, 0.f), fmaxf(a0[2 * c4 + 1].x, 0.f),
+                                fmaxf(a0[2 * c4 + 1].y, 0.f));
+            o[4 + c4] = make_float4(fmaxf(a1[2 * c4].x, 0.f), fmaxf(a1[2 * c4].y, 0.f), fmaxf(a1[2 * c4 + 1].x, 0.f),
+                                    fmaxf(a1[2 * c4 + 1].y, 0.f));
+        }
+    }
+}
+
+// ---- small-head attention: softmax(q k^T / sqrt(D)) v, fp32, K/V of one (batch, head) in shared memory ----
+// layouts: q (B or 1, Nq, H, D), k/v (B, Nk, H, D), out (B, Nq, H, D)  — i.e. the (tokens, heads*dim) matrices the
+// linear layers produce, no permutes. q_bstride == 0 broadcasts one query set over the batch.
+constexpr int ATT_CHUNK = 4;     // keys per online-softmax update (one rescale of the accumulator per chunk)
+
+template <int D>
+__global__ void __launch_bounds__(128)
+attn_shared_kv_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                      float* __restrict__ out, int nq, int nk, int heads, long long q_bstride, float scale) {
+    extern __shared__ float sm[];
+    const int nkp = (nk + ATT_CHUNK - 1) / ATT_CHUNK * ATT_CHUNK;
+    float* sk = sm;                 // [nkp][D], rows >= nk zero
+    float* sv = sm + nkp * D;
+    const int b = blockIdx.z, hd = blockIdx.y;
+    const long long kv_base = ((long long)b * nk * heads + hd) * D;
+    for (int e = threadIdx.x; e < nkp * (D / 4); e += blockDim.x) {
+        const int j = e / (D / 4), c = e % (D / 4);
+        float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+        if (j < nk) {
+            const long long g = kv_base + (long long)j * heads * D + c * 4;
+            kk = *reinterpret_cast<const float4*>(k + g);
+            vv = *reinterpret_cast<const float4*>(v + g);
+        }
+        *reinterpret_cast<float4*>(sk + j * D + c * 4) = kk;
+        *reinterpret_cast<float4*>(sv + j * D + c * 4) = vv;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float2 qr[D / 2], acc[D / 2];
+    const float* qp = q + (long long)b * q_bstride + ((long long)i * heads + hd) * D;
+#pragma unroll
+    for (int c = 0; c < D / 4; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(qp + 4 * c);
+        qr[2 * c] = make_float2(t.x * scale, t.y * scale);
+        qr[2 * c + 1] = make_float2(t.z * scale, t.w * scale);
+    }
+#pragma unroll
+    for (int c = 0; c < D / 2; ++c) acc[c] = make_float2(0.f, 0.f);
+    float m = -CUDART_INF_F, l = 0.f;
+    for (int j0 = 0; j0 < nkp; j0 += ATT_CHUNK) {
+        float s[ATT_CHUNK];
+#pragma unroll
+        for (int u = 0; u < ATT_CHUNK; ++u) {
+            const float4* kj = reinterpret_cast<const float4*>(sk + (j0 + u) * D);
+            float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c) {
+                const float4 kk = kj[c];
+                t = __ffma2_rn(qr[2 * c], make_float2(kk.x, kk.y), t);
+                t = __ffma2_rn(qr[2 * c + 1], make_float2(kk.z, kk.w), t);
+            }
+            s[u] = (j0 + u < nk) ? t.x + t.y : -CUDART_INF_F;
+        }
+        float mn = m;
+#pragma unroll
+        for (int u = 0; u < ATT_CHUNK; ++u) mn = fmaxf(mn, s[u]);
+        const float corr = __expf(m - mn);
+        m = mn;
+        l *= corr;
+        const float2 c2 = make_float2(corr, corr);
+#pragma unroll
+        for (int c = 0; c < D / 2; ++c) acc[c] = __fmul2_rn(acc[c], c2);
+#pragma unroll
+        for (int u = 0; u < ATT_CHUNK; ++u) {
+            const float p = __expf(s[u] - mn);
+            l += p;
+            const float2 p2 = make_float2(p, p);
+            const float4* vj = reinterpret_cast<const float4*>(sv + (j0 + u) * D);
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c) {
+                const float4 vv = vj[c];
+                acc[2 * c] = __ffma2_rn(p2, make_float2(vv.x, vv.y), acc[2 * c]);
+                acc[2 * c + 1] = __ffma2_rn(p2, make_float2(vv.z, vv.w), acc[2 * c + 1]);
+            }
+        }
+    }
+    const float inv = 1.f / l;
+    float* op = out + (((long long)b * nq + i) * heads + hd) * D;
+#pragma unroll
+    for (int c = 0; c < D / 4; ++c)
+        *reinterpret_cast<float4*>(op + 4 * c) = make_float4(acc[2 * c].x * inv, acc[2 * c].y * inv, acc[2 * c + 1].x * inv,
+                                                             acc[2 * c + 1].y * inv);
+}
+
+// few queries per batch element (perceiver input layer: 8 latent queries x 8 heads vs 80 keys per cost map; latent
+// self-attention 8 x 8; decoder cross-attention 1 x 8): ONE WARP per batch element, lane = slot * 8 + head, each lane
+// owns queries slot and slot + 4. K/V rows stream straight from global memory: the 8 head segments of a key are one
+// coalesced 512 B row, the 4 slots read identical addresses (one transaction) — the kernel is a pure HBM stream.
+constexpr int FQ_HEADS = 8, FQ_D = 16, FQ_SLOTS = 4, FQ_QPT = 2;
+__global__ void __launch_bounds__(128)
+attn_few_queries_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                        float* __restrict__ out, long long batch, int nq, int nk, long long q_bstride, float scale) {
+    const long long b = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    const int lane = threadIdx.x & 31, hd = lane & 7, slot = lane >> 3;
+    constexpr int C = FQ_HEADS * FQ_D;
+    float2 qr[FQ_QPT][FQ_D / 2], acc[FQ_QPT][FQ_D / 2];
+    float m[FQ_QPT], l[FQ_QPT];
+#pragma unroll
+    for (int t = 0; t < FQ_QPT; ++t) {
+        const int i = min(slot + FQ_SLOTS * t, nq - 1);
+        const float* qp = q + b * q_bstride + ((long long)i * FQ_HEADS + hd) * FQ_D;
+#pragma unroll
+        for (int c = 0; c < FQ_D / 4; ++c) {
+            const float4 x = *reinterpret_cast<const float4*>(qp + 4 * c);
+            qr[t][2 * c] = make_float2(x.x * scale, x.y * scale);
+            qr[t][2 * c + 1] = make_float2(x.z * scale, x.w * scale);
+        }
+#pragma unroll
+        for (int c = 0; c < FQ_D / 2; ++c) acc[t][c] = make_float2(0.f, 0.f);
+        m[t] = -CUDART_INF_F; l[t] = 0.f;
+    }
+    const float4* kp = reinterpret_cast<const float4*>(k + b * nk * C + hd * FQ_D);
+    const float4* vp = reinterpret_cast<const float4*>(v + b * nk * C + hd * FQ_D);
+#pragma unroll 2
+    for (int j = 0; j < nk; ++j) {
+        float4 kk[FQ_D / 4], vv[FQ_D / 4];
+#pragma unroll
+        for (int c = 0; c < FQ_D / 4; ++c) { kk[c] = __ldg(kp + j * (C / 4) + c); vv[c] = __ldg(vp + j * (C / 4) + c); }
+#pragma unroll
+        for (int t = 0; t < FQ_QPT; ++t) {
+            float2 sx = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < FQ_D / 4; ++c) {
+                sx = __ffma2_rn(qr[t][2 * c], make_float2(kk[c].x, kk[c].y), sx);
+                sx = __ffma2_rn(qr[t][2 * c + 1], make_float2(kk[c].z, kk[c].w), sx);
+            }
+            const float s = sx.x + sx.y;
+            const float mn = fmaxf(m[t], s);
+            const float corr = __expf(m[t] - mn), p = __expf(s - mn);
+            m[t] = mn;
+            l[t] = l[t] * corr + p;
+            const float2 c2 = make_float2(corr, corr), p2 = make_float2(p, p);
+#pragma unroll
+            for (int c = 0; c < FQ_D / 4; ++c) {
+                acc[t][2 * c] = __ffma2_rn(p2, make_float2(vv[c].x, vv[c].y), __fmul2_rn(acc[t][2 * c], c2));
+                acc[t][2 * c + 1] = __ffma2_rn(p2, make_float2(vv[c].z, vv[c].w), __fmul2_rn(acc[t][2 * c + 1], c2));
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < FQ_QPT; ++t) {
+        const int i = slot + FQ_SLOTS * t;
+        if (i >= nq) continue;
+        const float inv = 1.f / l[t];
+        float* op = out + ((b * nq + i) * FQ_HEADS + hd) * FQ_D;
+#pragma unroll
+        for (int c = 0; c < FQ_D / 4; ++c)
+            *reinterpret_cast<float4*>(op + 4 * c) = make_float4(acc[t][2 * c].x * inv, acc[t][2 * c].y * inv,
+                                                                 acc[t][2 * c + 1].x * inv, acc[t][2 * c + 1].y * inv);
+    }
+}
+
+}  // namespace
+
+extern "C" int macvo_layer_norm(const float* x, const float* weight, const float* bias, float* y, long long rows,
+                                int channels, float eps, void* stream) {
+    if (!x || !weight || !bias || !y || rows < 0) return MACVO_E_ARG;
+    if (rows == 0) return MACVO_OK;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    cudaStream_t st = as_stream(stream);
+    switch (channels) {
+        case 64: return MACVO_E_UNSUPPORTED;   // 64 = 2 floats per lane: not float4-able, left to ATen
+        case 128: layer_norm_kernel<4><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps); break;
+        case 256: layer_norm_kernel<8><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps); break;
+        case 512: layer_norm_kernel<16><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps); break;
+        default: return MACVO_E_UNSUPPORTED;
+    }
+    MACVO_LAUNCH_CHECK();
+    return MACVO_OK;
+}
+
+extern "C" int macvo_patch_embed_conv1(const float* maps, const float* weight, const float* bias, float* out,
+                                       long long n_maps, int h, int w, void* stream) {
+    if (!maps || !weight || !bias || !out || n_maps < 0 || h <= 0 || w <= 0) return MACVO_E_ARG;
+    if (n_maps == 0) return MACVO_OK;
+    const int hp8 = (h + 7) / 8 * 8, wp8 = (w + 7) / 8 * 8;
+    const int ho = hp8 / 2, wo = wp8 / 2;
+    const size_t smem = ((size_t)(2 * ho + 4) * (2 * wo + 4) + PE_C * 36) * sizeof(float);
+    if (smem > 200 * 1024) return MACVO_E_UNSUPPORTED;
+    MACVO_CUDA_TRY(cudaFuncSetAttribute(patch_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    patch_conv1_kernel<<<(unsigned)n_maps, 256, smem, as_stream(stream)>>>(maps, weight, bias, out, h, w, ho, wo);
+    MACVO_LAUNCH_CHECK();
+    return MACVO_OK;
+}
+
+extern "C" int macvo_small_attention(const float* q, const float* k, const float* v, float* out, int batch, int nq,
+                                     int nk, int heads, int head_dim, int q_broadcast, void* stream) {
+    if (!q || !k || !v || !out || batch <= 0 || nq <= 0 || nk <= 0 || heads <= 0) return MACVO_E_ARG;
+    if (head_dim != 16 && head_dim != 32) return MACVO_E_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    const float scale = 1.f / sqrtf((float)head_dim);
+    const long long qbs = q_broadcast ? 0 : (long long)nq * heads * head_dim;
+    if (nq <= FQ_SLOTS * FQ_QPT && heads == FQ_HEADS && head_dim == FQ_D) {
+        attn_few_queries_kernel<<<(unsigned)((batch + 3) / 4), 128, 0, st>>>(q, k, v, out, batch, nq, nk, qbs, scale);
+    } else {
+        const size_t smem = (size_t)2 * ((nk + ATT_CHUNK - 1) / ATT_CHUNK * ATT_CHUNK) * head_dim * sizeof(float);
+        if (smem > 200 * 1024) return MACVO_E_UNSUPPORTED;
+        dim3 grid(ceil_div(nq, 128), heads, batch);
+        if (head_dim == 16) {
+            MACVO_CUDA_TRY(cudaFuncSetAttribute(attn_shared_kv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attn_shared_kv_kernel<16><<<grid, 128, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale);
+        } else {
+            MACVO_CUDA_TRY(cudaFuncSetAttribute(attn_shared_kv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attn_shared_kv_kernel<32><<<grid, 128, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale);
+        }
+    }
+    MACVO_LAUNCH_CHECK();
+    return MACVO_OK;
+}

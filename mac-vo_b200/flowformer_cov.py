@@ -223,18 +223,6 @@ def _sdpa(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
     return F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False)
 
 
-def _explicit_mha(q: Tensor, k: Tensor, v: Tensor, heads: int) -> Tensor:
-    """`MultiHeadAttention` (core/attention.py:32-68): softmax(q k^T * scale) v with explicit ops."""
-    B, I, C = q.shape
-    J = k.shape[1]
-    d = C // heads
-    q = q.view(B, I, heads, d).permute(0, 2, 1, 3)
-    k = k.view(B, J, heads, d).permute(0, 2, 1, 3)
-    v = v.view(B, J, heads, d).permute(0, 2, 1, 3)
-    attn = (torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)).softmax(dim=-1)
-    return torch.matmul(attn, v).permute(0, 2, 1, 3).reshape(B, I, C)
-
-
 class FlowFormerCovNet:
     """Functional FlowFormerCov. `inference(image1, image2) -> (flow, cov)` like flownet.py:37-44."""
 
@@ -244,10 +232,12 @@ class FlowFormerCovNet:
                  lookup_fn: Callable[[Tensor, Tensor], Tensor] | None = None):
         self.device = torch.device(device)
         self.enc_dtype, self.dec_dtype, self.depth = enc_dtype, dec_dtype, decoder_depth
-        if corr_fn is None or lookup_fn is None:
+        self._ops = None
+        if corr_fn is None or lookup_fn is None or self.device.type == "cuda":
             from . import ops  # binds to the CUDA library; raises if it cannot be loaded
             corr_fn = corr_fn or ops.corr_build
             lookup_fn = lookup_fn or ops.corr_lookup
+            self._ops = ops if self.device.type == "cuda" else None
         self.corr_fn, self.lookup_fn = corr_fn, lookup_fn
         self.load_state_dict(state_dict)
         self._cache: dict = {}
@@ -298,7 +288,31 @@ class FlowFormerCovNet:
         return F.conv2d(x, self.W[p + ".weight"], self.W.get(p + ".bias"), stride=stride, padding=padding, groups=groups)
 
     def _ln(self, x: Tensor, p: str, eps: float = 1e-5) -> Tensor:
+        if self._native(x) and x.shape[-1] in self._ops.LAYER_NORM_CHANNELS:
+            return self._ops.layer_norm(x, self.W[p + ".weight"], self.W[p + ".bias"], eps)
         return F.layer_norm(x, (x.shape[-1],), self.W[p + ".weight"], self.W[p + ".bias"], eps)
+
+    def _native(self, x: Tensor) -> bool:
+        """fp32 CUDA activations go through csrc/nn_kernels.cu; half-precision ones (MACVO_Fast) and the CPU
+        golden-parity runs of this class keep the torch ops."""
+        return self._ops is not None and x.is_cuda and x.dtype == torch.float32
+
+    def _attn(self, q: Tensor, k: Tensor, v: Tensor, heads: int) -> Tensor:
+        """softmax(q k^T / sqrt(d)) v on (B|1, Nq, C), (B, Nk, C), (B, Nk, C) token matrices -> (B, Nq, C)."""
+        B, J, C = k.shape
+        d = C // heads
+        if self._native(k) and d in (16, 32) and 2 * J * d * 4 <= 200 * 1024:
+            return self._ops.small_attention(q, k, v, heads)
+        I = q.shape[1]
+        qh = q.reshape(q.shape[0], I, heads, d).permute(0, 2, 1, 3).expand(B, -1, -1, -1)
+        kh = k.reshape(B, J, heads, d).permute(0, 2, 1, 3)
+        vh = v.reshape(B, J, heads, d).permute(0, 2, 1, 3)
+        if I * J <= 4096:      # tiny products: explicit matmul-softmax-matmul beats the SDPA kernels
+            a = (torch.matmul(qh, kh.transpose(-1, -2)) * (d ** -0.5)).softmax(dim=-1)
+            o = torch.matmul(a, vh)
+        else:
+            o = _sdpa(qh, kh, vh)
+        return o.permute(0, 2, 1, 3).reshape(B, I, C)
 
     def _memo(self, key, fn):
         if key not in self._cache:
@@ -350,18 +364,18 @@ class FlowFormerCovNet:
         B, N, C = x.shape
         H, W = size
         xw, meta = self._to_windows(x.view(B, H, W, C), ws)
-        qkv = self._lin(xw, p + "qkv").reshape(xw.shape[0], ws * ws, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
-        o = _sdpa(qkv[0], qkv[1], qkv[2]).transpose(1, 2).reshape(xw.shape[0], ws * ws, C)
+        wq, bq = self.W[p + "qkv.weight"], self.W[p + "qkv.bias"]          # rows [q | k | v] (svt_large.py:111)
+        q, k, v = (F.linear(xw, wq[i * C:(i + 1) * C], bq[i * C:(i + 1) * C]) for i in range(3))
+        o = self._attn(q, k, v, heads)
         return self._lin(self._from_windows(o, meta, ws, H, W), p + "proj")
 
     def _svt_global_attn(self, x: Tensor, size, p: str, heads: int, sr: int) -> Tensor:
         B, N, C = x.shape
-        d = C // heads
-        q = self._lin(x, p + "q").reshape(B, N, heads, d).permute(0, 2, 1, 3)
+        q = self._lin(x, p + "q")
         t = self._conv(x.permute(0, 2, 1).reshape(B, C, *size), p + "sr", stride=sr)
         t = self._ln(t.reshape(B, C, -1).permute(0, 2, 1), p + "norm")
-        kv = self._lin(t, p + "kv").reshape(B, -1, 2, heads, d).permute(2, 0, 3, 1, 4)
-        o = _sdpa(q, kv[0], kv[1]).transpose(1, 2).reshape(B, N, C)
+        wkv, bkv = self.W[p + "kv.weight"], self.W[p + "kv.bias"]          # rows [k | v] (svt_large.py:161)
+        o = self._attn(q, F.linear(t, wkv[:C], bkv[:C]), F.linear(t, wkv[C:], bkv[C:]), heads)
         return self._lin(o, p + "proj")
 
     # ---- cost perceiver encoder (core/encoder.py:194-244) -------------------------------------
@@ -369,8 +383,11 @@ class FlowFormerCovNet:
         """(M, 1, H2, W2) -> (M, h*w, 128) tokens  (PatchEmbed, core/encoder.py:12-55)."""
         p = "memory_encoder.cost_perceiver_encoder.patch_embed."
         M, _, H2, W2 = cost_maps.shape
-        x = F.pad(cost_maps, (0, (8 - W2 % 8) % 8, 0, (8 - H2 % 8) % 8))
-        x = F.relu(self._conv(x, p + "proj.0", stride=2, padding=2))
+        if self._native(cost_maps) and (H2 + 7) // 8 * 8 * ((W2 + 7) // 8 * 8) <= 96 * 160:
+            x = self._ops.patch_embed_conv1(cost_maps, self.W[p + "proj.0.weight"], self.W[p + "proj.0.bias"])
+        else:
+            x = F.pad(cost_maps, (0, (8 - W2 % 8) % 8, 0, (8 - H2 % 8) % 8))
+            x = F.relu(self._conv(x, p + "proj.0", stride=2, padding=2))
         x = F.relu(self._conv(x, p + "proj.2", stride=2, padding=2))
         x = self._conv(x, p + "proj.4", stride=2, padding=2)
         h, w = x.shape[2:]
@@ -392,7 +409,7 @@ class FlowFormerCovNet:
     def _latent_layer(self, x: Tensor, p: str) -> Tensor:
         """SelfAttentionLayer over the 8 latent tokens of each source pixel (core/encoder.py:97-140)."""
         y = self._ln(x, p + "norm1")
-        a = _explicit_mha(self._lin(y, p + "q"), self._lin(y, p + "k"), self._lin(y, p + "v"), 8)
+        a = self._attn(self._lin(y, p + "q"), self._lin(y, p + "k"), self._lin(y, p + "v"), 8)
         x = x + self._lin(a, p + "proj")
         return x + self._lin(F.gelu(self._lin(self._ln(x, p + "norm2"), p + "ffn.0")), p + "ffn.3")
 
@@ -413,12 +430,7 @@ class FlowFormerCovNet:
         enc = self._memo(("win", ws, C + VERT_C_DIM, x.dtype, x.device), lambda: sine_embed(
             coords_grid(1, ws, ws, x.device, x.dtype).view(1, 2, -1).permute(0, 2, 1), C + VERT_C_DIM))
         qkw = qkw + enc
-        d = C // heads
-        nwin = xw.shape[0]
-        q = self._lin(qkw, p + "q").reshape(nwin, ws * ws, heads, d).transpose(1, 2)
-        k = self._lin(qkw, p + "k").reshape(nwin, ws * ws, heads, d).transpose(1, 2)
-        v = self._lin(xw, p + "v").reshape(nwin, ws * ws, heads, d).transpose(1, 2)
-        o = _sdpa(q.contiguous(), k.contiguous(), v.contiguous()).transpose(1, 2).reshape(nwin, ws * ws, C)
+        o = self._attn(self._lin(qkw, p + "q"), self._lin(qkw, p + "k"), self._lin(xw, p + "v"), heads)
         return self._lin(self._from_windows(o, meta, ws, H, W), p + "proj")
 
     def _vert_global_attn(self, x: Tensor, size, context: Tensor, p: str, sr: int = 4, heads: int = 8) -> Tensor:
@@ -430,20 +442,17 @@ class FlowFormerCovNet:
         pr, pb = (sr - W % sr) % sr, (sr - H % sr) % sr
         xg, qk = F.pad(xg, (0, 0, 0, pr, 0, pb)), F.pad(qk, (0, 0, 0, pr, 0, pb))
         Hp, Wp = H + pb, W + pr
-        d = C // heads
         Cq = C + VERT_C_DIM
         enc_full = self._memo(("full", Hp, Wp, Cq, x.dtype, x.device), lambda: sine_embed(
             coords_grid(1, Hp, Wp, x.device, x.dtype).view(1, 2, -1).permute(0, 2, 1), Cq))
-        q = self._lin(qk.reshape(Bt, Hp * Wp, Cq) + enc_full, p + "q").reshape(Bt, Hp * Wp, heads, d).permute(0, 2, 1, 3)
+        q = self._lin(qk.reshape(Bt, Hp * Wp, Cq) + enc_full, p + "q")
         v_in = self._conv(xg.permute(0, 3, 1, 2), p + "sr_value", stride=sr).reshape(Bt, C, -1).permute(0, 2, 1)
         k_in = self._conv(qk.permute(0, 3, 1, 2), p + "sr_key", stride=sr).reshape(Bt, C, -1).permute(0, 2, 1)
         v_in, k_in = self._ln(v_in, p + "norm"), self._ln(k_in, p + "norm")
         enc_sub = self._memo(("sub", Hp // sr, Wp // sr, sr, C, x.dtype, x.device), lambda: sine_embed(
             coords_grid(1, Hp // sr, Wp // sr, x.device, x.dtype).view(1, 2, -1).permute(0, 2, 1) * sr, C))
-        M = k_in.shape[1]
-        k = self._lin(k_in + enc_sub, p + "k").reshape(Bt, M, heads, d).permute(0, 2, 1, 3)
-        v = self._lin(v_in, p + "v").reshape(Bt, M, heads, d).permute(0, 2, 1, 3)
-        o = _sdpa(q, k, v).transpose(1, 2).reshape(Bt, Hp, Wp, C)[:, :H, :W, :].reshape(Bt, N, C)
+        o = self._attn(q, self._lin(k_in + enc_sub, p + "k"), self._lin(v_in, p + "v"), heads)
+        o = o.view(Bt, Hp, Wp, C)[:, :H, :W, :].reshape(Bt, N, C)
         return self._lin(o, p + "proj")
 
     def _vert_block(self, x: Tensor, size, context: Tensor, p: str, local: bool) -> Tensor:
@@ -461,10 +470,8 @@ class FlowFormerCovNet:
         p = c + "input_layer."
         lat = self.W[c + "latent_tokens"]                        # (1, 8, 128)
         M = tokens.shape[0]
-        q = self._lin(self._ln(lat, p + "norm1"), p + "q").view(1, LATENT_TOKENS, 8, 16).permute(0, 2, 1, 3).expand(M, -1, -1, -1)
-        k = self._lin(tokens, p + "k").view(M, -1, 8, 16).permute(0, 2, 1, 3)
-        v = self._lin(tokens, p + "v").view(M, -1, 8, 16).permute(0, 2, 1, 3)
-        a = _sdpa(q, k, v).permute(0, 2, 1, 3).reshape(M, LATENT_TOKENS, LATENT_DIM)
+        q = self._lin(self._ln(lat, p + "norm1"), p + "q")       # (1, 8, 128): shared by every source pixel
+        a = self._attn(q, self._lin(tokens, p + "k"), self._lin(tokens, p + "v"), 8)
         x = lat + self._lin(a, p + "proj")
         x = x + self._lin(F.gelu(self._lin(self._ln(x, p + "norm2"), p + "ffn.0")), p + "ffn.3")
         short_cut = x
@@ -532,7 +539,7 @@ class FlowFormerCovNet:
             # cross attention of each pixel's query to its 8 cost-memory tokens (decoder.py:56-76)
             enc = sine_embed(coords1.to(dd).permute(0, 2, 3, 1).reshape(B * N, 1, 2), QUERY_DIM)
             q = self._lin(self._ln(query, ca + "norm1") + enc, ca + "q")
-            a = _explicit_mha(q, key, value, 8)
+            a = self._attn(q, key, value, 8)
             g = query + self._lin(torch.cat([a, query], dim=2), ca + "proj")
             g = g + self._lin(F.gelu(self._lin(self._ln(g, ca + "norm2"), ca + "ffn.0")), ca + "ffn.3")
             cost_global = g.view(B, H1, W1, QUERY_DIM).permute(0, 3, 1, 2)

@@ -63,6 +63,9 @@ EXPORTS = {
                         + [C.c_void_p] * 2),
     "macvo_pgo_accumulate": (C.c_int, [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2 + [C.c_double]
                              + [C.c_void_p] * 2),
+    "macvo_layer_norm": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
+    "macvo_patch_embed_conv1": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "macvo_small_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 6 + [C.c_void_p]),
 }
 
 
@@ -434,3 +437,54 @@ def pgo_accumulate(pos_Tw: Tensor, kp2_uv: Tensor, kp2_disp: Tensor, uv_cov: Ten
     _check(rc, "macvo_pgo_accumulate")
     LAUNCHES[0] += 1
     return acc
+
+
+# ---- frontend "next" rows: memory-bound perceiver layers (csrc/nn_kernels.cu) ------------------------------
+LAYER_NORM_CHANNELS = (128, 256, 512)
+
+
+def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5) -> Tensor:
+    """nn.LayerNorm over the last dim of a contiguous fp32 CUDA tensor (warp-per-row kernel)."""
+    x = _dev(x, torch.float32, "layer_norm x")
+    c = x.shape[-1]
+    if c not in LAYER_NORM_CHANNELS:
+        raise MacvoB200Error(f"layer_norm: channels {c} not in {LAYER_NORM_CHANNELS}")
+    y = torch.empty_like(x)
+    rc = load_library().macvo_layer_norm(x.data_ptr(), _dev(weight, torch.float32, "ln weight").data_ptr(),
+                                         _dev(bias, torch.float32, "ln bias").data_ptr(), y.data_ptr(),
+                                         x.numel() // c, c, float(eps), _stream())
+    _check(rc, "macvo_layer_norm")
+    LAUNCHES[0] += 1
+    return y
+
+
+def patch_embed_conv1(maps: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+    """(M,1,H,W) cost maps -> ReLU(conv 6x6/2 (+ pad to x8)) as a logical (M,16,Ho,Wo) channels_last tensor."""
+    maps = _dev(maps, torch.float32, "patch_embed maps")
+    m, one, h, w = maps.shape
+    if one != 1 or tuple(weight.shape) != (16, 1, 6, 6):
+        raise MacvoB200Error("patch_embed_conv1: expects (M,1,H,W) maps and a (16,1,6,6) weight")
+    ho, wo = (h + 7) // 8 * 4, (w + 7) // 8 * 4
+    out = torch.empty(m, ho, wo, 16, dtype=torch.float32, device=maps.device)
+    rc = load_library().macvo_patch_embed_conv1(maps.data_ptr(), _dev(weight, torch.float32, "w").data_ptr(),
+                                                _dev(bias, torch.float32, "b").data_ptr(), out.data_ptr(),
+                                                m, h, w, _stream())
+    _check(rc, "macvo_patch_embed_conv1")
+    LAUNCHES[0] += 1
+    return out.permute(0, 3, 1, 2)
+
+
+def small_attention(q: Tensor, k: Tensor, v: Tensor, heads: int) -> Tensor:
+    """softmax(q k^T / sqrt(d)) v with q (B|1, Nq, heads*d), k/v (B, Nk, heads*d) -> (B, Nq, heads*d); d in {16, 32}."""
+    q, k, v = (_dev(t, torch.float32, "attention operand") for t in (q, k, v))
+    b, nk, c = k.shape
+    d = c // heads
+    nq = q.shape[1]
+    if q.shape[0] not in (1, b) or q.shape[2] != c or v.shape != k.shape or d * heads != c:
+        raise MacvoB200Error(f"small_attention: bad shapes q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)}")
+    out = torch.empty(b, nq, c, dtype=torch.float32, device=k.device)
+    rc = load_library().macvo_small_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, nq, nk,
+                                              heads, d, int(q.shape[0] == 1 and b > 1), _stream())
+    _check(rc, "macvo_small_attention")
+    LAUNCHES[0] += 1
+    return out

@@ -1,0 +1,86 @@
+"""Parity of the perceiver-layer kernels (csrc/nn_kernels.cu) against the torch fp32 ops they replace
+(Module/Network/FlowFormer/core/encoder.py:12-55, core/attention.py:6-29, core/twins.py:103-114,173-183).
+Floating point: tolerance 1e-5 relative to the output scale (different summation order, __expf)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from macvo_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    return ops
+
+
+@pytest.mark.parametrize("rows,c", [(1, 128), (7, 128), (4801, 128), (300, 256), (65, 512), (9600 * 8, 128)])
+def test_layer_norm(ops, rows, c):
+    g = torch.Generator().manual_seed(rows + c)
+    x = (torch.randn(rows, c, generator=g) * 3 + 1.5).to(DEV)
+    w, b = torch.randn(c, generator=g).to(DEV), torch.randn(c, generator=g).to(DEV)
+    for eps in (1e-5, 1e-6):
+        ref = F.layer_norm(x.double(), (c,), w.double(), b.double(), eps)
+        got = ops.layer_norm(x, w, b, eps)
+        assert (got.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    with pytest.raises(ops.MacvoB200Error):
+        ops.layer_norm(x[:, :64].contiguous(), w[:64], b[:64])
+
+
+@pytest.mark.parametrize("m,h,w", [(3, 8, 8), (5, 12, 16), (4, 60, 80), (2, 13, 17), (2, 90, 160)])
+def test_patch_embed_conv1(ops, m, h, w):
+    g = torch.Generator().manual_seed(m * h + w)
+    maps = torch.randn(m, 1, h, w, generator=g).to(DEV)
+    wt, b = (torch.randn(16, 1, 6, 6, generator=g) * 0.2).to(DEV), torch.randn(16, generator=g).to(DEV)
+    x = F.pad(maps, (0, (8 - w % 8) % 8, 0, (8 - h % 8) % 8))
+    ref = F.relu(F.conv2d(x.double(), wt.double(), b.double(), stride=2, padding=2))
+    got = ops.patch_embed_conv1(maps, wt, b)
+    assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert (got.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+def _ref_attention(q, k, v, heads):
+    B, J, C = k.shape
+    d = C // heads
+    qh = q.double().reshape(q.shape[0], -1, heads, d).permute(0, 2, 1, 3).expand(B, -1, -1, -1)
+    kh, vh = (t.double().reshape(B, J, heads, d).permute(0, 2, 1, 3) for t in (k, v))
+    a = (qh @ kh.transpose(-1, -2) * d ** -0.5).softmax(-1)
+    return (a @ vh).permute(0, 2, 1, 3).reshape(B, -1, C)
+
+
+# (batch, nq, nk, heads, head_dim, broadcast q): perceiver input layer / latent self-attention / decoder cross
+# attention (few-queries kernel), windowed 7x7, vertical + SVT global attention (shared-K/V kernel)
+ATTN_CASES = [(37, 8, 80, 8, 16, True), (50, 8, 8, 8, 16, False), (33, 1, 8, 8, 16, False),
+              (12, 49, 49, 8, 16, False), (9, 49, 49, 4, 32, False), (3, 1000, 300, 8, 16, False),
+              (2, 700, 300, 4, 32, False), (2, 130, 75, 8, 32, False), (1, 5, 513, 8, 16, False),
+              (5, 6, 21, 4, 32, False), (7, 3, 10, 8, 16, False), (2, 9, 30, 8, 16, False)]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_small_attention(ops, case):
+    b, nq, nk, heads, d, bc = case
+    g = torch.Generator().manual_seed(sum(case[:5]))
+    q = (torch.randn(1 if bc else b, nq, heads * d, generator=g) * 1.5).to(DEV)
+    k = (torch.randn(b, nk, heads * d, generator=g) * 1.5).to(DEV)
+    v = torch.randn(b, nk, heads * d, generator=g).to(DEV)
+    ref = _ref_attention(q, k, v, heads)
+    got = ops.small_attention(q, k, v, heads)
+    assert got.shape == ref.shape
+    assert (got.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+def test_network_native_layers_match_torch_layers(ops):
+    """the whole network with csrc/nn_kernels.cu vs the same network on the torch ops (fp32, TF32 off)"""
+    from macvo_b200.flowformer_cov import FlowFormerCovNet, synthetic_state_dict
+    g = torch.Generator().manual_seed(3)
+    i1, i2 = torch.rand(1, 3, 96, 128, generator=g).to(DEV), torch.rand(1, 3, 96, 128, generator=g).to(DEV)
+    net = FlowFormerCovNet(synthetic_state_dict(0), DEV, decoder_depth=4)
+    f1, c1 = net.inference(i1, i2)
+    net._ops = None
+    f0, c0 = net.inference(i1, i2)
+    assert (f1 - f0).abs().max().item() <= 2e-4 * max(1.0, f0.abs().max().item())
+    assert ((c1 - c0).abs() / c0.abs().clamp_min(1e-6)).max().item() <= 1e-3
