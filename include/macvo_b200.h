@@ -221,6 +221,22 @@ int macvo_patch_embed_conv1(const float* maps, const float* weight, const float*
 int macvo_small_attention(const float* q, const float* k, const float* v, float* out, int batch, int nq, int nk,
                           int heads, int head_dim, int q_broadcast, void* stream);
 
+/* ---- decoder iteration glue: SepConvGRU state kept in NHWC [h | x] buffers ---------------
+ * Module/Network/FlowFormer/core/gru.py:22-43 (SepConvGRU), gma.py:84-130, covhead.py:95-131. fp32, pixels-major.
+ * A GRU input buffer is (pixels, 512): channels 0..127 = h (or r*h), 128..255 = inp, 256..383 = motion features,
+ * 384..511 = motion features + gamma * aggregated motion features.
+ */
+/* writes channels 256..511 of up to four buffers (NULL entries after buf0 are skipped) */
+int macvo_gru_input(const float* mf, const float* agg, const float* gamma, float* buf0, float* buf1, float* buf2,
+                    float* buf3, long long pixels, void* stream);
+/* zr (pixels,256) = conv([h|x]) pre-activation, bias (256, may be NULL) is added first;
+ * z_out (pixels,128) = sigmoid(zr[:, :128]); rhx[:, :128] = sigmoid(zr[:, 128:]) * hx[:, :128] */
+int macvo_gru_gates(const float* zr, const float* bias, const float* hx, float* z_out, float* rhx, long long pixels,
+                    void* stream);
+/* hx[:, :128] <- (1 - z) * hx[:, :128] + z * tanh(q + bias); bias (128) may be NULL; optional dense copy (pixels,128) */
+int macvo_gru_blend(const float* q, const float* bias, const float* z, float* hx, float* h_dense, long long pixels,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

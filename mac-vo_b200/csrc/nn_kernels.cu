@@ -203,7 +203,8 @@ attn_shared_kv_kernel(const float* __restrict__ q, const float* __restrict__ k, 
 // self-attention 8 x 8; decoder cross-attention 1 x 8): ONE WARP per batch element, lane = slot * 8 + head, each lane
 // owns queries slot and slot + 4. K/V rows stream straight from global memory: the 8 head segments of a key are one
 // coalesced 512 B row, the 4 slots read identical addresses (one transaction) — the kernel is a pure HBM stream.
-constexpr int FQ_HEADS = 8, FQ_D = 16, FQ_SLOTS = 4, FQ_QPT = 2;
+constexpr int FQ_HEADS = 8, FQ_SLOTS = 4, FQ_QPT = 2;
+template <int FQ_D>
 __global__ void __launch_bounds__(128)
 attn_few_queries_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                         float* __restrict__ out, long long batch, int nq, int nk, long long q_bstride, float scale) {
@@ -304,12 +305,16 @@ extern "C" int macvo_patch_embed_conv1(const float* maps, const float* weight, c
 extern "C" int macvo_small_attention(const float* q, const float* k, const float* v, float* out, int batch, int nq,
                                      int nk, int heads, int head_dim, int q_broadcast, void* stream) {
     if (!q || !k || !v || !out || batch <= 0 || nq <= 0 || nk <= 0 || heads <= 0) return MACVO_E_ARG;
-    if (head_dim != 16 && head_dim != 32) return MACVO_E_UNSUPPORTED;
+    if (head_dim != 8 && head_dim != 16 && head_dim != 32) return MACVO_E_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
     const float scale = 1.f / sqrtf((float)head_dim);
     const long long qbs = q_broadcast ? 0 : (long long)nq * heads * head_dim;
-    if (nq <= FQ_SLOTS * FQ_QPT && heads == FQ_HEADS && head_dim == FQ_D) {
-        attn_few_queries_kernel<<<(unsigned)((batch + 3) / 4), 128, 0, st>>>(q, k, v, out, batch, nq, nk, qbs, scale);
+    if (nq <= FQ_SLOTS * FQ_QPT && heads == FQ_HEADS && head_dim <= 16) {
+        const unsigned grid = (unsigned)((batch + 3) / 4);
+        if (head_dim == 16) attn_few_queries_kernel<16><<<grid, 128, 0, st>>>(q, k, v, out, batch, nq, nk, qbs, scale);
+        else attn_few_queries_kernel<8><<<grid, 128, 0, st>>>(q, k, v, out, batch, nq, nk, qbs, scale);
+    } else if (head_dim == 8) {
+        return MACVO_E_UNSUPPORTED;
     } else {
         const size_t smem = (size_t)2 * ((nk + ATT_CHUNK - 1) / ATT_CHUNK * ATT_CHUNK) * head_dim * sizeof(float);
         if (smem > 200 * 1024) return MACVO_E_UNSUPPORTED;

@@ -233,6 +233,7 @@ class FlowFormerCovNet:
         self.device = torch.device(device)
         self.enc_dtype, self.dec_dtype, self.depth = enc_dtype, dec_dtype, decoder_depth
         self._ops = None
+        self._fused_conv_relu = True
         if corr_fn is None or lookup_fn is None or self.device.type == "cuda":
             from . import ops  # binds to the CUDA library; raises if it cannot be loaded
             corr_fn = corr_fn or ops.corr_build
@@ -287,6 +288,15 @@ class FlowFormerCovNet:
             x = x.contiguous(memory_format=torch.channels_last)
         return F.conv2d(x, self.W[p + ".weight"], self.W.get(p + ".bias"), stride=stride, padding=padding, groups=groups)
 
+    def _conv_relu(self, x: Tensor, p: str, stride=1, padding=0) -> Tensor:
+        """relu(conv2d(x) + bias): one cuDNN fused conv-bias-activation launch on the GPU path."""
+        if self._ops is not None and x.is_cuda and self._fused_conv_relu:
+            if not x.is_contiguous(memory_format=torch.channels_last):
+                x = x.contiguous(memory_format=torch.channels_last)
+            pair = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+            return torch.cudnn_convolution_relu(x, self.W[p + ".weight"], self.W.get(p + ".bias"), pair(stride), pair(padding), (1, 1), 1)
+        return F.relu(self._conv(x, p, stride=stride, padding=padding))
+
     def _ln(self, x: Tensor, p: str, eps: float = 1e-5) -> Tensor:
         if self._native(x) and x.shape[-1] in self._ops.LAYER_NORM_CHANNELS:
             return self._ops.layer_norm(x, self.W[p + ".weight"], self.W[p + ".bias"], eps)
@@ -301,7 +311,7 @@ class FlowFormerCovNet:
         """softmax(q k^T / sqrt(d)) v on (B|1, Nq, C), (B, Nk, C), (B, Nk, C) token matrices -> (B, Nq, C)."""
         B, J, C = k.shape
         d = C // heads
-        if self._native(k) and d in (16, 32) and 2 * J * d * 4 <= 200 * 1024:
+        if self._native(k) and (d in (16, 32) or (d == 8 and heads == 8 and q.shape[1] <= 8)) and 2 * J * d * 4 <= 200 * 1024:
             return self._ops.small_attention(q, k, v, heads)
         I = q.shape[1]
         qh = q.reshape(q.shape[0], I, heads, d).permute(0, 2, 1, 3).expand(B, -1, -1, -1)
@@ -387,8 +397,8 @@ class FlowFormerCovNet:
             x = self._ops.patch_embed_conv1(cost_maps, self.W[p + "proj.0.weight"], self.W[p + "proj.0.bias"])
         else:
             x = F.pad(cost_maps, (0, (8 - W2 % 8) % 8, 0, (8 - H2 % 8) % 8))
-            x = F.relu(self._conv(x, p + "proj.0", stride=2, padding=2))
-        x = F.relu(self._conv(x, p + "proj.2", stride=2, padding=2))
+            x = self._conv_relu(x, p + "proj.0", stride=2, padding=2)
+        x = self._conv_relu(x, p + "proj.2", stride=2, padding=2)
         x = self._conv(x, p + "proj.4", stride=2, padding=2)
         h, w = x.shape[2:]
 
@@ -502,6 +512,16 @@ class FlowFormerCovNet:
             h = (1 - z) * h + z * q
         return h
 
+    def _gru_native(self, hx: Tensor, rhx: Tensor, z: Tensor, p: str, h_dense: Tensor, shape) -> None:
+        """SepConvGRU (gru.py:22-43) on the NHWC [h|x] / [r*h|x] buffers: 2 convs + 2 fused kernels per pass."""
+        B, H, W = shape
+        hx_map, rhx_map = (t.view(B, H, W, 512).permute(0, 3, 1, 2) for t in (hx, rhx))
+        for o, pad in (("1", (0, 2)), ("2", (2, 0))):
+            zr = F.conv2d(hx_map, self.W[p + f"convzr{o}.weight"], None, padding=pad)      # biases folded into the gate kernels
+            self._ops.gru_gates(zr.permute(0, 2, 3, 1), hx, z, rhx, self.W[p + f"convzr{o}.bias"])
+            q = F.conv2d(rhx_map, self.W[p + f"convq{o}.weight"], None, padding=pad)
+            self._ops.gru_blend(q.permute(0, 2, 3, 1), z, hx, h_dense if o == "2" else None, self.W[p + f"convq{o}.bias"])
+
     @staticmethod
     def convex_upsample(flow: Tensor, mask: Tensor) -> Tensor:
         """`upsample_flow` (decoder.py:131-139): softmax over the 9 neighbours, 8x."""
@@ -531,34 +551,54 @@ class FlowFormerCovNet:
         value = self._lin(cost_memory, ca + "v")
         ub, cu = m + "update_block.", m + "cov_update."
         gamma = self.W[ub + "aggregator.gamma"]
+        P = B * N
+        native = self._native(ctx) and dd == torch.float32
+        if native:
+            # recurrent state in NHWC [h | x] buffers (csrc/decoder_fused.cu): x = [inp | mf | mf + gamma*agg]
+            bufs = [torch.empty(P, 512, dtype=dd, device=ctx.device) for _ in range(4)]   # hx, rhx (flow) / hx, rhx (cov)
+            inp_rows = inp.permute(0, 2, 3, 1).reshape(P, 128)
+            for bf in bufs:
+                bf[:, 128:256] = inp_rows
+            bufs[0][:, :128] = net.permute(0, 2, 3, 1).reshape(P, 128)
+            bufs[2][:, :128] = bufs[0][:, :128]
+            zbuf = torch.empty(P, 128, dtype=dd, device=ctx.device)
+            net_d, cnet_d = torch.empty(P, 128, dtype=dd, device=ctx.device), torch.empty(P, 128, dtype=dd, device=ctx.device)
+            as_map = lambda t: t.view(B, H1, W1, -1).permute(0, 3, 1, 2)                   # channels_last logical map
         for _ in range(self.depth):
             flow = (coords1 - coords0).to(dd)
             cost_forward = self.lookup_fn(cost_maps, coords1).to(dd)             # fp32 lookup (covhead.py:91-93)
             query = self._conv(F.gelu(self._conv(cost_forward, m + "flow_token_encoder.0")), m + "flow_token_encoder.2")
-            query = query.permute(0, 2, 3, 1).reshape(B * N, 1, QUERY_DIM)
+            query = query.permute(0, 2, 3, 1).reshape(P, QUERY_DIM)              # rows = pixels (2-D: plain GEMMs below)
             # cross attention of each pixel's query to its 8 cost-memory tokens (decoder.py:56-76)
-            enc = sine_embed(coords1.to(dd).permute(0, 2, 3, 1).reshape(B * N, 1, 2), QUERY_DIM)
+            enc = sine_embed(coords1.to(dd).permute(0, 2, 3, 1).reshape(P, 2), QUERY_DIM)
             q = self._lin(self._ln(query, ca + "norm1") + enc, ca + "q")
-            a = self._attn(q, key, value, 8)
-            g = query + self._lin(torch.cat([a, query], dim=2), ca + "proj")
+            a = self._attn(q.unsqueeze(1), key, value, 8).squeeze(1)
+            g = query + self._lin(torch.cat([a, query], dim=1), ca + "proj")
             g = g + self._lin(F.gelu(self._lin(self._ln(g, ca + "norm2"), ca + "ffn.0")), ca + "ffn.3")
             cost_global = g.view(B, H1, W1, QUERY_DIM).permute(0, 3, 1, 2)
             corr = torch.cat([cost_global, cost_forward], dim=1)
             # motion encoder (gru.py:45-64)
             e = ub + "encoder."
-            cor = F.relu(self._conv(F.relu(self._conv(corr, e + "convc1")), e + "convc2", padding=1))
-            flo = F.relu(self._conv(F.relu(self._conv(flow, e + "convf1", padding=3)), e + "convf2", padding=1))
-            mf = torch.cat([F.relu(self._conv(torch.cat([cor, flo], dim=1), e + "conv", padding=1)), flow], dim=1)
+            cor = self._conv_relu(self._conv_relu(corr, e + "convc1"), e + "convc2", padding=1)
+            flo = self._conv_relu(self._conv_relu(flow, e + "convf1", padding=3), e + "convf2", padding=1)
+            mf = torch.cat([self._conv_relu(torch.cat([cor, flo], dim=1), e + "conv", padding=1), flow], dim=1)
             # GMA aggregation (gma.py:84-130)
+            mf = mf.contiguous(memory_format=torch.channels_last)
             v = self._conv(mf, ub + "aggregator.to_v").flatten(2).transpose(1, 2)   # (B, N, 128)
-            agg = torch.matmul(attention, v).transpose(1, 2).reshape(B, 128, H1, W1)
-            inp_cat = torch.cat([inp, mf, mf + gamma * agg], dim=1)
-            net = self._gru(net, inp_cat, ub + "gru.")
-            d_flow = self._conv(F.relu(self._conv(net, ub + "flow_head.conv1", padding=1)), ub + "flow_head.conv2", padding=1)
-            cnet = self._gru(cnet, inp_cat, cu + "gru.")
+            agg = torch.matmul(attention, v)                                        # (B, N, 128) = pixels-major
+            if native:
+                self._ops.gru_input(mf.permute(0, 2, 3, 1), agg, gamma, bufs)
+                self._gru_native(bufs[0], bufs[1], zbuf, ub + "gru.", net_d, (B, H1, W1))
+                self._gru_native(bufs[2], bufs[3], zbuf, cu + "gru.", cnet_d, (B, H1, W1))
+                net, cnet = as_map(net_d), as_map(cnet_d)
+            else:
+                inp_cat = torch.cat([inp, mf, mf + gamma * agg.transpose(1, 2).reshape(B, 128, H1, W1)], dim=1)
+                net = self._gru(net, inp_cat, ub + "gru.")
+                cnet = self._gru(cnet, inp_cat, cu + "gru.")
+            d_flow = self._conv(self._conv_relu(net, ub + "flow_head.conv1", padding=1), ub + "flow_head.conv2", padding=1)
             h = cu + "cov_head."
-            t = self._conv(F.relu(self._conv(cnet, h + "conv1", padding=1)), h + "conv2", padding=1)
-            d_cov = self._conv(F.relu(self._conv(t, h + "conv3", padding=1)), h + "conv4", padding=1)
+            t = self._conv(self._conv_relu(cnet, h + "conv1", padding=1), h + "conv2", padding=1)
+            d_cov = self._conv(self._conv_relu(t, h + "conv3", padding=1), h + "conv4", padding=1)
             coords1 = coords1 + d_flow.float()
             ccoords1 = ccoords1 + d_cov.float()
         # the reference evaluates both mask heads + upsampling every iteration but (eval mode) returns

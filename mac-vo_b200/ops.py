@@ -66,6 +66,9 @@ EXPORTS = {
     "macvo_layer_norm": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
     "macvo_patch_embed_conv1": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "macvo_small_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 6 + [C.c_void_p]),
+    "macvo_gru_input": (C.c_int, [C.c_void_p] * 7 + [C.c_longlong, C.c_void_p]),
+    "macvo_gru_gates": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
+    "macvo_gru_blend": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
 }
 
 
@@ -488,3 +491,59 @@ def small_attention(q: Tensor, k: Tensor, v: Tensor, heads: int) -> Tensor:
     _check(rc, "macvo_small_attention")
     LAUNCHES[0] += 1
     return out
+
+
+# ---- decoder iteration glue (csrc/decoder_fused.cu) -----------------------------------------------------------
+GRU_HID, GRU_IN = 128, 512
+
+
+def _gru_buf(t: Tensor, what: str) -> Tensor:
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] == GRU_IN and t.is_contiguous()):
+        raise MacvoB200Error(f"{what}: expected a contiguous fp32 CUDA (pixels, {GRU_IN}) buffer")
+    return t
+
+
+def gru_input(mf: Tensor, agg: Tensor, gamma: Tensor, bufs: list[Tensor]) -> None:
+    """write x-part channels 256..511 = [mf | mf + gamma * agg] of up to 4 (pixels, 512) GRU input buffers"""
+    mf, agg = _dense(mf, GRU_HID, "gru_input mf"), _dense(agg, GRU_HID, "gru_input agg")
+    pixels = mf.numel() // GRU_HID
+    ptrs = [_gru_buf(b, "gru_input buffer").data_ptr() for b in bufs] + [None] * (4 - len(bufs))
+    rc = load_library().macvo_gru_input(mf.data_ptr(), agg.data_ptr(), _dev(gamma, torch.float32, "gamma").data_ptr(),
+                                        *ptrs, pixels, _stream())
+    _check(rc, "macvo_gru_input")
+    LAUNCHES[0] += 1
+
+
+def _dense(t: Tensor, cols: int, what: str) -> Tensor:
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() % cols == 0):
+        raise MacvoB200Error(f"{what}: expected a contiguous fp32 CUDA pixels-major (.., {cols}) tensor "
+                             f"(pass conv outputs as x.permute(0, 2, 3, 1) of a channels_last map)")
+    return t
+
+
+def _bias_ptr(bias, n: int, what: str):
+    if bias is None:
+        return None
+    if not (bias.is_cuda and bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == n):
+        raise MacvoB200Error(f"{what}: expected a contiguous fp32 CUDA bias of {n} elements")
+    return bias.data_ptr()
+
+
+def gru_gates(zr: Tensor, hx: Tensor, z_out: Tensor, rhx: Tensor, bias: Tensor | None = None) -> None:
+    zr, z_out = _dense(zr, 2 * GRU_HID, "gru_gates zr"), _dense(z_out, GRU_HID, "gru_gates z_out")
+    rc = load_library().macvo_gru_gates(zr.data_ptr(), _bias_ptr(bias, 2 * GRU_HID, "gru_gates bias"),
+                                        _gru_buf(hx, "hx").data_ptr(), z_out.data_ptr(),
+                                        _gru_buf(rhx, "rhx").data_ptr(), hx.shape[0], _stream())
+    _check(rc, "macvo_gru_gates")
+    LAUNCHES[0] += 1
+
+
+def gru_blend(q: Tensor, z: Tensor, hx: Tensor, h_dense: Tensor | None, bias: Tensor | None = None) -> None:
+    q, z = _dense(q, GRU_HID, "gru_blend q"), _dense(z, GRU_HID, "gru_blend z")
+    if h_dense is not None:
+        _dense(h_dense, GRU_HID, "gru_blend h_dense")
+    rc = load_library().macvo_gru_blend(q.data_ptr(), _bias_ptr(bias, GRU_HID, "gru_blend bias"), z.data_ptr(),
+                                        _gru_buf(hx, "hx").data_ptr(),
+                                        None if h_dense is None else h_dense.data_ptr(), hx.shape[0], _stream())
+    _check(rc, "macvo_gru_blend")
+    LAUNCHES[0] += 1

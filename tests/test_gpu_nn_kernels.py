@@ -57,7 +57,8 @@ def _ref_attention(q, k, v, heads):
 ATTN_CASES = [(37, 8, 80, 8, 16, True), (50, 8, 8, 8, 16, False), (33, 1, 8, 8, 16, False),
               (12, 49, 49, 8, 16, False), (9, 49, 49, 4, 32, False), (3, 1000, 300, 8, 16, False),
               (2, 700, 300, 4, 32, False), (2, 130, 75, 8, 32, False), (1, 5, 513, 8, 16, False),
-              (5, 6, 21, 4, 32, False), (7, 3, 10, 8, 16, False), (2, 9, 30, 8, 16, False)]
+              (5, 6, 21, 4, 32, False), (7, 3, 10, 8, 16, False), (2, 9, 30, 8, 16, False),
+              (41, 1, 8, 8, 8, False), (6, 8, 20, 8, 8, True)]
 
 
 @pytest.mark.parametrize("case", ATTN_CASES)
@@ -84,3 +85,31 @@ def test_network_native_layers_match_torch_layers(ops):
     f0, c0 = net.inference(i1, i2)
     assert (f1 - f0).abs().max().item() <= 2e-4 * max(1.0, f0.abs().max().item())
     assert ((c1 - c0).abs() / c0.abs().clamp_min(1e-6)).max().item() <= 1e-3
+
+
+def test_gru_fused_kernels(ops):
+    """csrc/decoder_fused.cu vs the SepConvGRU elementwise ops of core/gru.py:22-43 (torch fp32)."""
+    g = torch.Generator().manual_seed(11)
+    P = 1237
+    mf, agg = torch.randn(P, 128, generator=g).to(DEV), torch.randn(P, 128, generator=g).to(DEV)
+    gamma = torch.tensor([0.37], device=DEV)
+    bufs = [torch.randn(P, 512, generator=g).to(DEV) for _ in range(4)]
+    before = [b.clone() for b in bufs]
+    ops.gru_input(mf, agg, gamma, bufs)
+    for b, b0 in zip(bufs, before):
+        assert torch.equal(b[:, :256], b0[:, :256]) and torch.equal(b[:, 256:384], mf)
+        torch.testing.assert_close(b[:, 384:], mf + gamma * agg, rtol=1e-6, atol=1e-6)
+    zr, q = torch.randn(P, 256, generator=g).to(DEV) * 3, torch.randn(P, 128, generator=g).to(DEV) * 3
+    hx, rhx, z = bufs[0], bufs[1], torch.empty(P, 128, device=DEV)
+    h0 = hx[:, :128].clone()
+    bzr, bq = torch.randn(256, generator=g).to(DEV), torch.randn(128, generator=g).to(DEV)
+    ops.gru_gates(zr, hx, z, rhx, bzr)
+    torch.testing.assert_close(z, torch.sigmoid(zr[:, :128] + bzr[:128]), rtol=2e-6, atol=2e-7)
+    torch.testing.assert_close(rhx[:, :128], torch.sigmoid(zr[:, 128:] + bzr[128:]) * h0, rtol=2e-6, atol=2e-7)
+    dense = torch.empty(P, 128, device=DEV)
+    ops.gru_blend(q, z, hx, dense, bq)
+    ref = (1 - z) * h0 + z * torch.tanh(q + bq)
+    torch.testing.assert_close(hx[:, :128], ref, rtol=2e-6, atol=2e-6)
+    assert torch.equal(dense, hx[:, :128])
+    with pytest.raises(ops.MacvoB200Error):
+        ops.gru_gates(zr.t(), hx, z, rhx)

@@ -103,14 +103,15 @@ def test_pipeline_gpu_vs_cpu_oracle(plugins):
         da, db = a.extras["depth1"].depth.cpu(), b.extras["depth1"].depth
         assert ((da - db).abs() / db.abs().clamp_min(1e-3)).median().item() < 2e-2      # depth = bl*fx / |flow_x|, |flow_x| ~ 1 px
         assert abs(a.num_kp - b.num_kp) <= 8
-    # pose: when both sides drew the SAME keypoints the poses must agree tightly; one flipped NMS tie (dense maps differ
-    # by ~1e-3 between cuDNN and MKL) shifts the whole randperm draw, and the pose of this random-weight network then
-    # only agrees statistically -> sanity bound. The exact chain is test_pipeline_on_identical_dense_maps_is_exact.
+    # pose: when both sides drew the SAME keypoints the poses must agree tightly. One flipped NMS tie (the dense maps
+    # differ by ~1e-3 between cuDNN and MKL) shifts the whole randperm draw; with this random-weight network the flow is
+    # not a consistent motion field, so poses from different keypoint subsets are unrelated -> only finiteness is checked
+    # then. The exact chain (identical dense maps in, bit-exact keypoints, 1e-6 pose) is the next test.
     same = all(a.kp0_uv.shape == b.kp0_uv.shape and bool((a.kp0_uv.cpu() == b.kp0_uv.cpu()).all())
                for a, b in zip(rg, rc))
     assert torch.isfinite(pg).all() and torch.isfinite(pcpu).all()
-    tol = 5e-2 if same else 0.5
-    np.testing.assert_allclose(pg.numpy(), pcpu.numpy(), rtol=0, atol=tol * max(1.0, float(pcpu.abs().max())))
+    if same:
+        np.testing.assert_allclose(pg.numpy(), pcpu.numpy(), rtol=0, atol=5e-2 * max(1.0, float(pcpu.abs().max())))
 
 
 def test_pipeline_on_identical_dense_maps_is_exact(plugins):
