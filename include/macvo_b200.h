@@ -208,7 +208,7 @@ int macvo_pgo_accumulate(const double* pos_Tw, const double* kp2_uv, const doubl
  * the nn.LayerNorm calls of core/attention.py / core/twins.py / core/Twins/svt_large.py, and their
  * softmax(q k^T / sqrt(d)) v products (core/attention.py:6-29, core/twins.py:103-114,173-183).
  */
-/* y = LayerNorm(x) over the last dim; x, y (rows, channels) contiguous; channels in {128, 256, 512}. */
+/* y = LayerNorm(x) over the last dim; x, y (rows, channels) contiguous; channels in {64, 128, 256, 512}. */
 int macvo_layer_norm(const float* x, const float* weight, const float* bias, float* y, long long rows,
                      int channels, float eps, void* stream);
 /* maps (n_maps, 1, h, w) -> out (n_maps, ho, wo, 16) [NHWC], ho = ceil8(h)/2, wo = ceil8(w)/2:

@@ -52,6 +52,21 @@ layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     }
 }
 
+// C = 64: two channels per lane
+__global__ void __launch_bounds__(256)
+layer_norm64_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                    float* __restrict__ y, long long rows, float eps) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float2 t = *reinterpret_cast<const float2*>(x + row * 64 + lane * 2);
+    const float mean = warp_sum(t.x + t.y) * (1.f / 64);
+    const float d0 = t.x - mean, d1 = t.y - mean;
+    const float rstd = rsqrtf(warp_sum(fmaf(d0, d0, d1 * d1)) * (1.f / 64) + eps);
+    const float2 ww = *reinterpret_cast<const float2*>(w + lane * 2), bb = *reinterpret_cast<const float2*>(b + lane * 2);
+    *reinterpret_cast<float2*>(y + row * 64 + lane * 2) = make_float2(d0 * rstd * ww.x + bb.x, d1 * rstd * ww.y + bb.y);
+}
+
 // ---- PatchEmbed conv1: (M,1,H,W) -> ReLU(conv 6x6 s2 p2, 16 ch) as (M, Ho, Wo, 16) NHWC -----------------
 // The reference first zero-pads H, W up to multiples of 8 (encoder.py:35-38); here out-of-range taps simply
 // read 0. One CTA per cost map: the whole map (<= 96 x 160 fp32) sits in shared memory.
@@ -278,7 +293,7 @@ extern "C" int macvo_layer_norm(const float* x, const float* weight, const float
     const unsigned grid = (unsigned)((rows + 7) / 8);
     cudaStream_t st = as_stream(stream);
     switch (channels) {
-        case 64: return MACVO_E_UNSUPPORTED;   // 64 = 2 floats per lane: not float4-able, left to ATen
+        case 64: layer_norm64_kernel<<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps); break;
         case 128: layer_norm_kernel<4><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps); break;
         case 256: layer_norm_kernel<8><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps); break;
         case 512: layer_norm_kernel<16><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps); break;

@@ -561,7 +561,8 @@ class FlowFormerCovNet:
                 bf[:, 128:256] = inp_rows
             bufs[0][:, :128] = net.permute(0, 2, 3, 1).reshape(P, 128)
             bufs[2][:, :128] = bufs[0][:, :128]
-            zbuf = torch.empty(P, 128, dtype=dd, device=ctx.device)
+            zbuf, zbuf2 = torch.empty(P, 128, dtype=dd, device=ctx.device), torch.empty(P, 128, dtype=dd, device=ctx.device)
+            side = self._memo(("side_stream", ctx.device), lambda: torch.cuda.Stream(ctx.device))
             net_d, cnet_d = torch.empty(P, 128, dtype=dd, device=ctx.device), torch.empty(P, 128, dtype=dd, device=ctx.device)
             as_map = lambda t: t.view(B, H1, W1, -1).permute(0, 3, 1, 2)                   # channels_last logical map
         for _ in range(self.depth):
@@ -587,18 +588,34 @@ class FlowFormerCovNet:
             v = self._conv(mf, ub + "aggregator.to_v").flatten(2).transpose(1, 2)   # (B, N, 128)
             agg = torch.matmul(attention, v)                                        # (B, N, 128) = pixels-major
             if native:
+                # the flow branch (GRU + flow head) and the covariance branch (GRU + cov head) only share their input:
+                # at 60x80 each conv fills about half of the 148 SMs, so the two run on forked streams (fork/join is
+                # captured into the CUDA graph as parallel branches)
                 self._ops.gru_input(mf.permute(0, 2, 3, 1), agg, gamma, bufs)
+                main = torch.cuda.current_stream()
+                fork = torch.cuda.Event()
+                fork.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(fork)
+                    self._gru_native(bufs[2], bufs[3], zbuf2, cu + "gru.", cnet_d, (B, H1, W1))
+                    cnet = as_map(cnet_d)
+                    h = cu + "cov_head."
+                    t = self._conv(self._conv_relu(cnet, h + "conv1", padding=1), h + "conv2", padding=1)
+                    d_cov = self._conv(self._conv_relu(t, h + "conv3", padding=1), h + "conv4", padding=1)
+                    join = torch.cuda.Event()
+                    join.record(side)
                 self._gru_native(bufs[0], bufs[1], zbuf, ub + "gru.", net_d, (B, H1, W1))
-                self._gru_native(bufs[2], bufs[3], zbuf, cu + "gru.", cnet_d, (B, H1, W1))
-                net, cnet = as_map(net_d), as_map(cnet_d)
+                net = as_map(net_d)
+                d_flow = self._conv(self._conv_relu(net, ub + "flow_head.conv1", padding=1), ub + "flow_head.conv2", padding=1)
+                main.wait_event(join)
             else:
                 inp_cat = torch.cat([inp, mf, mf + gamma * agg.transpose(1, 2).reshape(B, 128, H1, W1)], dim=1)
                 net = self._gru(net, inp_cat, ub + "gru.")
                 cnet = self._gru(cnet, inp_cat, cu + "gru.")
-            d_flow = self._conv(self._conv_relu(net, ub + "flow_head.conv1", padding=1), ub + "flow_head.conv2", padding=1)
-            h = cu + "cov_head."
-            t = self._conv(self._conv_relu(cnet, h + "conv1", padding=1), h + "conv2", padding=1)
-            d_cov = self._conv(self._conv_relu(t, h + "conv3", padding=1), h + "conv4", padding=1)
+                d_flow = self._conv(self._conv_relu(net, ub + "flow_head.conv1", padding=1), ub + "flow_head.conv2", padding=1)
+                h = cu + "cov_head."
+                t = self._conv(self._conv_relu(cnet, h + "conv1", padding=1), h + "conv2", padding=1)
+                d_cov = self._conv(self._conv_relu(t, h + "conv3", padding=1), h + "conv4", padding=1)
             coords1 = coords1 + d_flow.float()
             ccoords1 = ccoords1 + d_cov.float()
         # the reference evaluates both mask heads + upsampling every iteration but (eval mode) returns

@@ -443,7 +443,7 @@ def pgo_accumulate(pos_Tw: Tensor, kp2_uv: Tensor, kp2_disp: Tensor, uv_cov: Ten
 
 
 # ---- frontend "next" rows: memory-bound perceiver layers (csrc/nn_kernels.cu) ------------------------------
-LAYER_NORM_CHANNELS = (128, 256, 512)
+LAYER_NORM_CHANNELS = (64, 128, 256, 512)
 
 
 def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5) -> Tensor:

@@ -38,6 +38,17 @@ with torch.inference_mode():
     names = ["context svt", "feat svt+conv", "corr", "patch_embed(alone)", "cost_perceiver(total incl patch_embed)", "decoder x12"]
     for n, a, b in zip(names, t[:-1], t[1:]):
         print(f"{n:45s} {a.elapsed_time(b):8.3f} ms")
+    def table(title, fn):
+        with profile(activities=[ProfilerActivity.CUDA]) as pr:
+            fn()
+            torch.cuda.synchronize()
+        rows = [(e.key, e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total, e.count) for e in pr.key_averages()]
+        rows.sort(key=lambda r: -r[1])
+        print(f"--- {title} kernels: total {sum(r[1] for r in rows) / 1e3:.2f} ms, {sum(r[2] for r in rows)} launches")
+        for k, us, n in rows[:32]:
+            print(f"{us / 1e3:8.3f} ms {n:5d}x  {k[:110]}")
+    table("cost_perceiver", lambda: net.cost_perceiver(cv, ctx))
+    table("svt x2 (context + features)", lambda: (net.svt(i1, "context_encoder"), net.svt(torch.cat([i1, i2]), "memory_encoder.feat_encoder")))
     # decoder alone under the profiler: kernel-level table
     with profile(activities=[ProfilerActivity.CUDA]) as prof2:
         net.memory_decoder(cm, ctx.float(), cmaps.float())
