@@ -217,9 +217,11 @@ int macvo_patch_embed_conv1(const float* maps, const float* weight, const float*
                             long long n_maps, int h, int w, void* stream);
 /* out = softmax(q k^T / sqrt(head_dim)) v per (batch, head); q (batch | 1, nq, heads, head_dim),
  * k, v (batch, nk, heads, head_dim), out (batch, nq, heads, head_dim); head_dim in {16, 32};
- * q_broadcast != 0: one query set shared by every batch element. */
+ * q_broadcast != 0: one query set shared by every batch element. head_dim 8 only for nq <= 8, heads == 8.
+ * allow_tf32 != 0: products with nq >= 16 run on the tensor cores in TF32 (fp32 accumulate, fp32 softmax), the
+ * precision the reference runs its attention bmm's at (Frontend.py:275-277); 0 = fp32 FMA throughout. */
 int macvo_small_attention(const float* q, const float* k, const float* v, float* out, int batch, int nq, int nk,
-                          int heads, int head_dim, int q_broadcast, void* stream);
+                          int heads, int head_dim, int q_broadcast, int allow_tf32, void* stream);
 
 /* ---- decoder iteration glue: SepConvGRU state kept in NHWC [h | x] buffers ---------------
  * Module/Network/FlowFormer/core/gru.py:22-43 (SepConvGRU), gma.py:84-130, covhead.py:95-131. fp32, pixels-major.

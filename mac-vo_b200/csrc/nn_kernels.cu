@@ -214,6 +214,118 @@ attn_shared_kv_kernel(const float* __restrict__ q, const float* __restrict__ k, 
                                                              acc[2 * c + 1].y * inv);
 }
 
+// ---- tensor-core variant (TF32 mma.sync m16n8k8, fp32 accumulate): used when the caller allows TF32 matmuls, like
+// the reference frontend does for its attention bmm's (Frontend.py:275-277). One warp = 16 queries; K, V of the
+// (batch, head) in shared memory (tf32-rounded, row stride D + 4 -> conflict-free fragment loads); flash-style online
+// softmax over blocks of 32 keys. The P tile comes out of the QK^T mma in the accumulator layout (columns 2t, 2t+1)
+// and is fed straight back as the A operand of the PV mma by declaring A-column t <-> key 2t, t+4 <-> key 2t+1 and
+// loading V's B fragment with the same key permutation: no shuffles, no shared-memory round trip.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+               float* __restrict__ out, int nq, int nk, int heads, long long q_bstride, float scale) {
+    extern __shared__ float sm[];
+    constexpr int ST = D + 4, KS = D / 8;
+    const int nkp = (nk + 31) / 32 * 32;
+    uint32_t* sk = reinterpret_cast<uint32_t*>(sm);      // [nkp][ST] tf32 bit patterns, rows >= nk zero
+    uint32_t* sv = sk + nkp * ST;
+    const int b = blockIdx.z, hd = blockIdx.y;
+    const long long kv_base = ((long long)b * nk * heads + hd) * D;
+    for (int e = threadIdx.x; e < nkp * (D / 4); e += blockDim.x) {
+        const int j = e / (D / 4), c = (e % (D / 4)) * 4;
+        float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+        if (j < nk) {
+            const long long g = kv_base + (long long)j * heads * D + c;
+            kk = *reinterpret_cast<const float4*>(k + g);
+            vv = *reinterpret_cast<const float4*>(v + g);
+        }
+        *reinterpret_cast<uint4*>(sk + j * ST + c) = make_uint4(to_tf32(kk.x), to_tf32(kk.y), to_tf32(kk.z), to_tf32(kk.w));
+        *reinterpret_cast<uint4*>(sv + j * ST + c) = make_uint4(to_tf32(vv.x), to_tf32(vv.y), to_tf32(vv.z), to_tf32(vv.w));
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int q0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 16;
+    if (q0 >= nq) return;
+    const int r0 = q0 + g, r1 = q0 + g + 8;
+    const float* qb = q + (long long)b * q_bstride + (long long)hd * D;
+    const float* q0p = qb + (long long)min(r0, nq - 1) * heads * D;
+    const float* q1p = qb + (long long)min(r1, nq - 1) * heads * D;
+    uint32_t a[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        a[ks][0] = to_tf32(q0p[ks * 8 + t] * scale);
+        a[ks][1] = to_tf32(q1p[ks * 8 + t] * scale);
+        a[ks][2] = to_tf32(q0p[ks * 8 + t + 4] * scale);
+        a[ks][3] = to_tf32(q1p[ks * 8 + t + 4] * scale);
+    }
+    float acc[KS][4];
+#pragma unroll
+    for (int nd = 0; nd < KS; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+    for (int kb = 0; kb < nkp; kb += 32) {
+        float s[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            const uint32_t* kr = sk + (kb + nt * 8 + g) * ST + t;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) mma_tf32(s[nt], a[ks], kr[ks * 8], kr[ks * 8 + 4]);
+        }
+        if (kb + 32 > nk) {                                  // ragged tail: keys >= nk do not take part
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int key = kb + nt * 8 + 2 * t;
+                if (key >= nk) s[nt][0] = s[nt][2] = -CUDART_INF_F;
+                if (key + 1 >= nk) s[nt][1] = s[nt][3] = -CUDART_INF_F;
+            }
+        }
+        float x0 = s[0][0], x1 = s[0][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            x0 = fmaxf(x0, fmaxf(s[nt][0], s[nt][1]));
+            x1 = fmaxf(x1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+        const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
+        const float c0 = __expf(m0 - n0), c1 = __expf(m1 - n1);
+        m0 = n0; m1 = n1;
+        l0 *= c0; l1 *= c1;
+#pragma unroll
+        for (int nd = 0; nd < KS; ++nd) { acc[nd][0] *= c0; acc[nd][1] *= c0; acc[nd][2] *= c1; acc[nd][3] *= c1; }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const float p00 = __expf(s[nt][0] - n0), p01 = __expf(s[nt][1] - n0);
+            const float p10 = __expf(s[nt][2] - n1), p11 = __expf(s[nt][3] - n1);
+            l0 += p00 + p01; l1 += p10 + p11;
+            const uint32_t pa[4] = {to_tf32(p00), to_tf32(p10), to_tf32(p01), to_tf32(p11)};   // A cols t <-> key 2t, t+4 <-> 2t+1
+            const uint32_t* vr = sv + (kb + nt * 8 + 2 * t) * ST + g;
+#pragma unroll
+            for (int nd = 0; nd < KS; ++nd) mma_tf32(acc[nd], pa, vr[nd * 8], vr[ST + nd * 8]);
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    float* ob = out + ((long long)b * nq * heads + hd) * D;
+#pragma unroll
+    for (int nd = 0; nd < KS; ++nd) {
+        if (r0 < nq) *reinterpret_cast<float2*>(ob + (long long)r0 * heads * D + nd * 8 + 2 * t) = make_float2(acc[nd][0] * i0, acc[nd][1] * i0);
+        if (r1 < nq) *reinterpret_cast<float2*>(ob + (long long)r1 * heads * D + nd * 8 + 2 * t) = make_float2(acc[nd][2] * i1, acc[nd][3] * i1);
+    }
+}
+
 // few queries per batch element (perceiver input layer: 8 latent queries x 8 heads vs 80 keys per cost map; latent
 // self-attention 8 x 8; decoder cross-attention 1 x 8): ONE WARP per batch element, lane = slot * 8 + head, each lane
 // owns queries slot and slot + 4. K/V rows stream straight from global memory: the 8 head segments of a key are one
@@ -318,7 +430,7 @@ extern "C" int macvo_patch_embed_conv1(const float* maps, const float* weight, c
 }
 
 extern "C" int macvo_small_attention(const float* q, const float* k, const float* v, float* out, int batch, int nq,
-                                     int nk, int heads, int head_dim, int q_broadcast, void* stream) {
+                                     int nk, int heads, int head_dim, int q_broadcast, int allow_tf32, void* stream) {
     if (!q || !k || !v || !out || batch <= 0 || nq <= 0 || nk <= 0 || heads <= 0) return MACVO_E_ARG;
     if (head_dim != 8 && head_dim != 16 && head_dim != 32) return MACVO_E_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
@@ -330,6 +442,18 @@ extern "C" int macvo_small_attention(const float* q, const float* k, const float
         else attn_few_queries_kernel<8><<<grid, 128, 0, st>>>(q, k, v, out, batch, nq, nk, qbs, scale);
     } else if (head_dim == 8) {
         return MACVO_E_UNSUPPORTED;
+    } else if (allow_tf32 && nq >= 16) {
+        const size_t smem = (size_t)2 * ((nk + 31) / 32 * 32) * (head_dim + 4) * sizeof(float);
+        if (smem > 200 * 1024) return MACVO_E_UNSUPPORTED;
+        const int warps = nq > 64 ? 8 : 4;
+        dim3 grid(ceil_div(nq, 16 * warps), heads, batch);
+        if (head_dim == 16) {
+            MACVO_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attn_tc_kernel<16><<<grid, 32 * warps, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale);
+        } else {
+            MACVO_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attn_tc_kernel<32><<<grid, 32 * warps, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale);
+        }
     } else {
         const size_t smem = (size_t)2 * ((nk + ATT_CHUNK - 1) / ATT_CHUNK * ATT_CHUNK) * head_dim * sizeof(float);
         if (smem > 200 * 1024) return MACVO_E_UNSUPPORTED;

@@ -65,7 +65,7 @@ EXPORTS = {
                              + [C.c_void_p] * 2),
     "macvo_layer_norm": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
     "macvo_patch_embed_conv1": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
-    "macvo_small_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 6 + [C.c_void_p]),
+    "macvo_small_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
     "macvo_gru_input": (C.c_int, [C.c_void_p] * 7 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_gates": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_blend": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
@@ -477,8 +477,11 @@ def patch_embed_conv1(maps: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     return out.permute(0, 3, 1, 2)
 
 
-def small_attention(q: Tensor, k: Tensor, v: Tensor, heads: int) -> Tensor:
-    """softmax(q k^T / sqrt(d)) v with q (B|1, Nq, heads*d), k/v (B, Nk, heads*d) -> (B, Nq, heads*d); d in {16, 32}."""
+def small_attention(q: Tensor, k: Tensor, v: Tensor, heads: int, allow_tf32: bool | None = None) -> Tensor:
+    """softmax(q k^T / sqrt(d)) v with q (B|1, Nq, heads*d), k/v (B, Nk, heads*d) -> (B, Nq, heads*d); d in {8, 16, 32}.
+    allow_tf32=None follows torch.backends.cuda.matmul.allow_tf32 (what the torch bmm it replaces would do)."""
+    if allow_tf32 is None:
+        allow_tf32 = bool(torch.backends.cuda.matmul.allow_tf32)
     q, k, v = (_dev(t, torch.float32, "attention operand") for t in (q, k, v))
     b, nk, c = k.shape
     d = c // heads
@@ -487,7 +490,7 @@ def small_attention(q: Tensor, k: Tensor, v: Tensor, heads: int) -> Tensor:
         raise MacvoB200Error(f"small_attention: bad shapes q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)}")
     out = torch.empty(b, nq, c, dtype=torch.float32, device=k.device)
     rc = load_library().macvo_small_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, nq, nk,
-                                              heads, d, int(q.shape[0] == 1 and b > 1), _stream())
+                                              heads, d, int(q.shape[0] == 1 and b > 1), int(allow_tf32), _stream())
     _check(rc, "macvo_small_attention")
     LAUNCHES[0] += 1
     return out

@@ -32,4 +32,6 @@ for name, (B, nq, nk, heads, d, bc) in {"input_layer": (9600, 8, 80, 8, 16, True
         "vert_global": (16, 4800, 300, 8, 16, False), "svt_s0_local": (4 * 18 * 23, 49, 49, 4, 32, False),
         "svt_s0_global": (4, 19200, 300, 4, 32, False), "svt_s1_global": (4, 4800, 300, 8, 32, False)}.items():
     q = torch.randn(1 if bc else B, nq, heads * d, device=dev); k = torch.randn(B, nk, heads * d, device=dev); v = torch.randn_like(k)
-    print("attn %-14s torch-sdpa %.1f us  native %.1f us" % (name, t(lambda: sd(q, k, v, heads)), t(lambda: ops.small_attention(q, k, v, heads))))
+    print("attn %-14s torch-sdpa %.1f us  native fp32 %.1f us  native tf32 %.1f us" % (
+        name, t(lambda: sd(q, k, v, heads)), t(lambda: ops.small_attention(q, k, v, heads, False)),
+        t(lambda: ops.small_attention(q, k, v, heads, True))))
