@@ -67,6 +67,10 @@ int macvo_corr_build(const float* fmap1, const float* fmap2, float* corr, int ba
 int macvo_corr_lookup(const float* cost_maps, const float* coords, float* out, int batch, int h1, int w1, int h2,
                       int w2, void* stream);
 
+/* same lookup with the output as (batch*h1*w1, 81) pixels-major rows (NHWC view of the map above) */
+int macvo_corr_lookup_rows(const float* cost_maps, const float* coords, float* out, int batch, int h1, int w1, int h2,
+                           int w2, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (a7)+(a8 scoring) fused dense post-processing of one `estimate_pair` + keypoint scoring —
  *      replaces FlowFormerCovFrontend.inference_2_depth / inference_2_match
@@ -238,6 +242,10 @@ int macvo_gru_gates(const float* zr, const float* bias, const float* hx, float* 
 /* hx[:, :128] <- (1 - z) * hx[:, :128] + z * tanh(q + bias); bias (128) may be NULL; optional dense copy (pixels,128) */
 int macvo_gru_blend(const float* q, const float* bias, const float* z, float* hx, float* h_dense, long long pixels,
                     void* stream);
+/* out (pixels,64) = LayerNorm_64(query) + LinearPositionEmbeddingSine(coords)  (decoder.py:56-66, attention.py:71-101);
+ * coords (batch, 2, n1) [x, y]; freq: the 16 fp32 frequencies k*pi/200. */
+int macvo_query_prep(const float* query, const float* ln_weight, const float* ln_bias, const float* coords,
+                     const float* freq, float* out, int batch, int n1, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,7 @@ constexpr int FP = 12;         // staged footprint edge (9 window + 1 bilinear +
 constexpr int FPS = FP * FP + 1; // padded row: odd stride -> conflict-free lane-per-query reads
 constexpr int THREADS = 256;
 
+template <bool NHWC>
 __global__ void __launch_bounds__(THREADS)
 corr_lookup_kernel(const float* __restrict__ cost_maps, const float* __restrict__ coords, float* __restrict__ out,
                    int batch, int h1, int w1, int h2, int w2) {
@@ -110,7 +111,8 @@ corr_lookup_kernel(const float* __restrict__ cost_maps, const float* __restrict_
             acc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00, nw), __fmul_rn(v01, ne)), __fmul_rn(v10, sw)),
                             __fmul_rn(v11, se));
         }
-        out[((long long)b * 81 + c) * n1 + p] = acc;
+        if (NHWC) out[q * 81 + c] = acc;                       // pixels-major rows for the decoder's token MLP
+        else out[((long long)b * 81 + c) * n1 + p] = acc;
     }
 }
 
@@ -121,7 +123,18 @@ extern "C" int macvo_corr_lookup(const float* cost_maps, const float* coords, fl
     if (!cost_maps || !coords || !out || batch <= 0 || h1 <= 0 || w1 <= 0 || h2 <= 1 || w2 <= 1) return MACVO_E_ARG;
     const long long total = (long long)batch * h1 * w1;
     const int grid = (int)((total + QPB - 1) / QPB);
-    corr_lookup_kernel<<<grid, THREADS, 0, as_stream(stream)>>>(cost_maps, coords, out, batch, h1, w1, h2, w2);
+    corr_lookup_kernel<false><<<grid, THREADS, 0, as_stream(stream)>>>(cost_maps, coords, out, batch, h1, w1, h2, w2);
+    MACVO_LAUNCH_CHECK();
+    return MACVO_OK;
+}
+
+// same lookup, output (batch*h1*w1, 81) pixels-major (the NHWC view of the reference's (batch, 81, h1, w1) map)
+extern "C" int macvo_corr_lookup_rows(const float* cost_maps, const float* coords, float* out, int batch, int h1, int w1,
+                                      int h2, int w2, void* stream) {
+    if (!cost_maps || !coords || !out || batch <= 0 || h1 <= 0 || w1 <= 0 || h2 <= 1 || w2 <= 1) return MACVO_E_ARG;
+    const long long total = (long long)batch * h1 * w1;
+    const int grid = (int)((total + QPB - 1) / QPB);
+    corr_lookup_kernel<true><<<grid, THREADS, 0, as_stream(stream)>>>(cost_maps, coords, out, batch, h1, w1, h2, w2);
     MACVO_LAUNCH_CHECK();
     return MACVO_OK;
 }

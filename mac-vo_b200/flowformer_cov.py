@@ -565,14 +565,27 @@ class FlowFormerCovNet:
             side = self._memo(("side_stream", ctx.device), lambda: torch.cuda.Stream(ctx.device))
             net_d, cnet_d = torch.empty(P, 128, dtype=dd, device=ctx.device), torch.empty(P, 128, dtype=dd, device=ctx.device)
             as_map = lambda t: t.view(B, H1, W1, -1).permute(0, 3, 1, 2)                   # channels_last logical map
+        fast_tokens = native and QUERY_DIM == 64 and self.lookup_fn is self._ops.corr_lookup
+        if fast_tokens:
+            fte0_w, fte0_b = self.W[m + "flow_token_encoder.0.weight"].flatten(1), self.W[m + "flow_token_encoder.0.bias"]
+            fte2_w, fte2_b = self.W[m + "flow_token_encoder.2.weight"].flatten(1), self.W[m + "flow_token_encoder.2.bias"]
+            freq16 = torch.arange(QUERY_DIM // 4, device=ctx.device, dtype=dd) * (1 / 200) * torch.pi   # as sine_embed builds it
         for _ in range(self.depth):
             flow = (coords1 - coords0).to(dd)
-            cost_forward = self.lookup_fn(cost_maps, coords1).to(dd)             # fp32 lookup (covhead.py:91-93)
-            query = self._conv(F.gelu(self._conv(cost_forward, m + "flow_token_encoder.0")), m + "flow_token_encoder.2")
-            query = query.permute(0, 2, 3, 1).reshape(P, QUERY_DIM)              # rows = pixels (2-D: plain GEMMs below)
-            # cross attention of each pixel's query to its 8 cost-memory tokens (decoder.py:56-76)
-            enc = sine_embed(coords1.to(dd).permute(0, 2, 3, 1).reshape(P, 2), QUERY_DIM)
-            q = self._lin(self._ln(query, ca + "norm1") + enc, ca + "q")
+            if native and fast_tokens:
+                # pixels-major rows end to end: lookup -> token MLP (two GEMMs with fused bias) -> fused LN + sine embedding
+                cf = self._ops.corr_lookup(cost_maps, coords1, rows=True)                     # (P, 81)
+                query = F.linear(F.gelu(F.linear(cf, fte0_w, fte0_b)), fte2_w, fte2_b)        # (P, 64)
+                qin = self._ops.query_prep(query, self.W[ca + "norm1.weight"], self.W[ca + "norm1.bias"], coords1, freq16)
+                cost_forward = cf.view(B, H1, W1, 81).permute(0, 3, 1, 2)                     # channels_last view
+            else:
+                cost_forward = self.lookup_fn(cost_maps, coords1).to(dd)         # fp32 lookup (covhead.py:91-93)
+                query = self._conv(F.gelu(self._conv(cost_forward, m + "flow_token_encoder.0")), m + "flow_token_encoder.2")
+                query = query.permute(0, 2, 3, 1).reshape(P, QUERY_DIM)          # rows = pixels (2-D: plain GEMMs below)
+                # cross attention of each pixel's query to its 8 cost-memory tokens (decoder.py:56-76)
+                enc = sine_embed(coords1.to(dd).permute(0, 2, 3, 1).reshape(P, 2), QUERY_DIM)
+                qin = self._ln(query, ca + "norm1") + enc
+            q = self._lin(qin, ca + "q")
             a = self._attn(q.unsqueeze(1), key, value, 8).squeeze(1)
             g = query + self._lin(torch.cat([a, query], dim=1), ca + "proj")
             g = g + self._lin(F.gelu(self._lin(self._ln(g, ca + "norm2"), ca + "ffn.0")), ca + "ffn.3")

@@ -46,6 +46,7 @@ EXPORTS = {
     "macvo_corr_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "macvo_corr_build": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     "macvo_corr_lookup": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
+    "macvo_corr_lookup_rows": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
     "macvo_dense_postproc": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_double] * 2 + [C.c_void_p] * 5
                              + [C.POINTER(_ScoreT), C.c_void_p]),
     "macvo_select_workspace_bytes": (C.c_size_t, [C.c_int] * 2),
@@ -66,6 +67,7 @@ EXPORTS = {
     "macvo_layer_norm": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
     "macvo_patch_embed_conv1": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "macvo_small_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
+    "macvo_query_prep": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "macvo_gru_input": (C.c_int, [C.c_void_p] * 7 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_gates": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_blend": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
@@ -164,17 +166,18 @@ def corr_build(fmap1: Tensor, fmap2: Tensor, mode: int | None = None) -> Tensor:
 # ------------------------------------------------------------------------------------------------
 # (a5) window lookup
 # ------------------------------------------------------------------------------------------------
-def corr_lookup(cost_maps: Tensor, coords: Tensor) -> Tensor:
-    """cost_maps (B*H1*W1, 1, H2, W2) fp32, coords (B,2,H1,W1) fp32 -> (B,81,H1,W1) fp32 (decoder.py:141-153)."""
+def corr_lookup(cost_maps: Tensor, coords: Tensor, rows: bool = False) -> Tensor:
+    """cost_maps (B*H1*W1, 1, H2, W2) fp32, coords (B,2,H1,W1) fp32 -> (B,81,H1,W1) fp32 (decoder.py:141-153);
+    rows=True: the same values as (B*H1*W1, 81) pixels-major rows (the NHWC view)."""
     lib = load_library()
     cm = _dev(cost_maps, torch.float32, "corr_lookup cost_maps")
     co = _dev(coords, torch.float32, "corr_lookup coords")
     B, _, H1, W1 = co.shape
     H2, W2 = cm.shape[-2:]
     assert cm.shape[0] == B * H1 * W1, "one cost map per query pixel"
-    out = torch.empty((B, 81, H1, W1), dtype=torch.float32, device=cm.device)
-    _check(lib.macvo_corr_lookup(cm.data_ptr(), co.data_ptr(), out.data_ptr(), B, H1, W1, H2, W2, _stream()),
-           "macvo_corr_lookup")
+    out = torch.empty((B * H1 * W1, 81) if rows else (B, 81, H1, W1), dtype=torch.float32, device=cm.device)
+    fn = lib.macvo_corr_lookup_rows if rows else lib.macvo_corr_lookup
+    _check(fn(cm.data_ptr(), co.data_ptr(), out.data_ptr(), B, H1, W1, H2, W2, _stream()), "macvo_corr_lookup")
     LAUNCHES[0] += 1
     return out
 
@@ -550,3 +553,18 @@ def gru_blend(q: Tensor, z: Tensor, hx: Tensor, h_dense: Tensor | None, bias: Te
                                         None if h_dense is None else h_dense.data_ptr(), hx.shape[0], _stream())
     _check(rc, "macvo_gru_blend")
     LAUNCHES[0] += 1
+
+
+def query_prep(query: Tensor, ln_weight: Tensor, ln_bias: Tensor, coords: Tensor, freq: Tensor, eps: float = 1e-5) -> Tensor:
+    """LayerNorm_64(query (P,64)) + sine position embedding of coords (B,2,H,W) -> (P,64)  (decoder.py:56-66)"""
+    query = _dense(query, 64, "query_prep query")
+    co = _dev(coords, torch.float32, "query_prep coords")
+    B, _, H, W = co.shape
+    if query.numel() != B * H * W * 64 or freq.numel() != 16:
+        raise MacvoB200Error("query_prep: expects query (B*H*W, 64) and 16 frequencies")
+    out = torch.empty_like(query)
+    rc = load_library().macvo_query_prep(query.data_ptr(), _bias_ptr(ln_weight, 64, "ln weight"), _bias_ptr(ln_bias, 64, "ln bias"),
+                                         co.data_ptr(), _bias_ptr(freq, 16, "freq"), out.data_ptr(), B, H * W, float(eps), _stream())
+    _check(rc, "macvo_query_prep")
+    LAUNCHES[0] += 1
+    return out

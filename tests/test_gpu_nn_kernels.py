@@ -116,3 +116,29 @@ def test_gru_fused_kernels(ops):
     assert torch.equal(dense, hx[:, :128])
     with pytest.raises(ops.MacvoB200Error):
         ops.gru_gates(zr.t(), hx, z, rhx)
+
+
+def test_lookup_rows_equals_lookup_map(ops):
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import cases
+    cm, co = cases.lookup_inputs(2, 12, 16)
+    a = ops.corr_lookup(cm.to(DEV), co.to(DEV))
+    b = ops.corr_lookup(cm.to(DEV), co.to(DEV), rows=True)
+    assert b.shape == (2 * 12 * 16, 81)
+    assert torch.equal(a.permute(0, 2, 3, 1).reshape(-1, 81), b)          # same arithmetic, other layout: bit-exact
+
+
+def test_query_prep(ops):
+    """LayerNorm(query) + LinearPositionEmbeddingSine(coords) (decoder.py:56-66, attention.py:71-101) vs torch ops"""
+    from macvo_b200.flowformer_cov import sine_embed
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 2, 9, 13
+    P = B * H * W
+    query = torch.randn(P, 64, generator=g).to(DEV) * 2
+    w, b = torch.randn(64, generator=g).to(DEV), torch.randn(64, generator=g).to(DEV)
+    coords = (torch.rand(B, 2, H, W, generator=g) * 90 - 5).to(DEV)
+    freq = torch.arange(16, device=DEV, dtype=torch.float32) * (1 / 200) * torch.pi
+    ref = F.layer_norm(query, (64,), w, b) + sine_embed(coords.permute(0, 2, 3, 1).reshape(P, 2), 64)
+    got = ops.query_prep(query, w, b, coords, freq)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=2e-5)
