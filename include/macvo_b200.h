@@ -219,6 +219,9 @@ int macvo_layer_norm(const float* x, const float* weight, const float* bias, flo
  * ReLU(conv2d(zero-pad to multiples of 8, weight (16,1,6,6), stride 2, padding 2) + bias). */
 int macvo_patch_embed_conv1(const float* maps, const float* weight, const float* bias, float* out,
                             long long n_maps, int h, int w, void* stream);
+/* in place x[r, :] = relu(x[r, :] + term[r % period, :]); x (rows, channels), term (period, channels), channels % 4 == 0
+ * (PatchEmbed.ffn_with_coord.0 with its position input folded into a per-position bias, encoder.py:40-52) */
+int macvo_add_rows_relu(float* x, const float* term, long long rows, int period, int channels, void* stream);
 /* out = softmax(q k^T / sqrt(head_dim)) v per (batch, head); q (batch | 1, nq, heads, head_dim),
  * k, v (batch, nk, heads, head_dim), out (batch, nq, heads, head_dim); head_dim in {16, 32};
  * q_broadcast != 0: one query set shared by every batch element. head_dim 8 only for nq <= 8, heads == 8.
@@ -226,6 +229,14 @@ int macvo_patch_embed_conv1(const float* maps, const float* weight, const float*
  * precision the reference runs its attention bmm's at (Frontend.py:275-277); 0 = fp32 FMA throughout. */
 int macvo_small_attention(const float* q, const float* k, const float* v, float* out, int batch, int nq, int nk,
                           int heads, int head_dim, int q_broadcast, int allow_tf32, void* stream);
+
+/* extended form: row strides ldq / ldk / ldv in floats (0 = heads*head_dim, must be multiples of 4) so a fused [q|k|v]
+ * projection output is consumed in place, and optional additive terms q_add (add_period, nq, heads*head_dim) /
+ * k_add (add_period, nk, heads*head_dim) added to q / k on load, batch b using slice b % add_period — the
+ * context + position half of the vertical attention's projections (core/twins.py:46-66, 120-150). */
+int macvo_small_attention_ex(const float* q, const float* k, const float* v, float* out, int batch, int nq, int nk,
+                             int heads, int head_dim, int q_broadcast, int allow_tf32, int ldq, int ldk, int ldv,
+                             const float* q_add, const float* k_add, int add_period, void* stream);
 
 /* ---- decoder iteration glue: SepConvGRU state kept in NHWC [h | x] buffers ---------------
  * Module/Network/FlowFormer/core/gru.py:22-43 (SepConvGRU), gma.py:84-130, covhead.py:95-131. fp32, pixels-major.

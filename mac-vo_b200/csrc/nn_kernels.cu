@@ -67,36 +67,55 @@ layer_norm64_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     *reinterpret_cast<float2*>(y + row * 64 + lane * 2) = make_float2(d0 * rstd * ww.x + bb.x, d1 * rstd * ww.y + bb.y);
 }
 
+// x[r, :] = relu(x[r, :] + term[r % period, :]) in place: PatchEmbed's ffn_with_coord.0 after the position half of its
+// input has been folded into a per-patch-position bias (encoder.py:40-52); channels % 4 == 0.
+__global__ void __launch_bounds__(256)
+add_rows_relu_kernel(float* __restrict__ x, const float* __restrict__ term, long long rows, int period, int c4) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * c4) return;
+    const long long r = e / c4;
+    const int c = (int)(e % c4);
+    float4 v = reinterpret_cast<float4*>(x)[e];
+    const float4 t = __ldg(reinterpret_cast<const float4*>(term) + (r % period) * c4 + c);
+    v.x = fmaxf(v.x + t.x, 0.f); v.y = fmaxf(v.y + t.y, 0.f); v.z = fmaxf(v.z + t.z, 0.f); v.w = fmaxf(v.w + t.w, 0.f);
+    reinterpret_cast<float4*>(x)[e] = v;
+}
+
 // ---- PatchEmbed conv1: (M,1,H,W) -> ReLU(conv 6x6 s2 p2, 16 ch) as (M, Ho, Wo, 16) NHWC -----------------
 // The reference first zero-pads H, W up to multiples of 8 (encoder.py:35-38); here out-of-range taps simply
 // read 0. One CTA per cost map: the whole map (<= 96 x 160 fp32) sits in shared memory.
 constexpr int PE_C = 16, PE_K = 6;
-__global__ void __launch_bounds__(256)
-patch_conv1_kernel(const float* __restrict__ maps, const float* __restrict__ wgt, const float* __restrict__ bias,
-                   float* __restrict__ out, int h, int w, int ho, int wo) {
+// filter taps [tap][channel] + bias in constant memory: with the tap loops fully unrolled every FFMA takes its weight
+// as a constant-bank operand — no shared-memory traffic for the 576 weights (the first version was LSU-bound on them)
+__constant__ float c_pe_w[PE_K * PE_K * PE_C + PE_C];
+__device__ float g_pe_pack[PE_K * PE_K * PE_C + PE_C];       // staging for the repacked filter
+
+__global__ void pe_pack_weights_kernel(const float* __restrict__ wgt, const float* __restrict__ bias, float* __restrict__ packed) {
+    const int e = threadIdx.x + blockIdx.x * blockDim.x;
+    if (e < PE_C * 36) { const int c = e / 36, t = e % 36; packed[t * PE_C + c] = wgt[e]; }      // (16,1,6,6) -> [tap][ch]
+    else if (e < PE_C * 36 + PE_C) packed[e] = bias[e - PE_C * 36];
+}
+
+__global__ void __launch_bounds__(320)
+patch_conv1_kernel(const float* __restrict__ maps, float* __restrict__ out, int h, int w, int ho, int wo) {
     extern __shared__ float sm[];
-    float* s_map = sm;                                   // (h + 4) x (wp) with a 2-pixel zero frame on the top / left
+    float* s_map = sm;                                   // (2 ho + 4) x (2 wo + 4): 2-pixel zero frame on the top / left
     const int hp = 2 * ho + 4, wp = 2 * wo + 4;          // covers every tap of every output
-    float* s_w = sm + hp * wp;                           // [36][16]
     const float* src = maps + (long long)blockIdx.x * h * w;
     for (int e = threadIdx.x; e < hp * wp; e += blockDim.x) {
         const int y = e / wp - 2, x = e % wp - 2;
         s_map[e] = (y >= 0 && y < h && x >= 0 && x < w) ? __ldg(src + y * w + x) : 0.f;
-    }
-    for (int e = threadIdx.x; e < PE_C * 36; e += blockDim.x) {       // wgt is (16,1,6,6): -> [tap][ch]
-        const int c = e / 36, t = e % 36;
-        s_w[t * PE_C + c] = wgt[e];
     }
     __syncthreads();
     float* dst = out + (long long)blockIdx.x * ho * wo * PE_C;
     const int wo2 = wo >> 1;                                          // wo is a multiple of 4
     for (int p = threadIdx.x; p < ho * wo2; p += blockDim.x) {        // two horizontally adjacent outputs per thread
         const int oy = p / wo2, ox = (p % wo2) * 2;
-        float2 a0[PE_C / 2], a1[PE_C / 2];
+        float a0[PE_C], a1[PE_C];
 #pragma unroll
-        for (int c = 0; c < PE_C / 2; ++c) a0[c] = a1[c] = make_float2(bias[2 * c], bias[2 * c + 1]);
+        for (int c = 0; c < PE_C; ++c) a0[c] = a1[c] = c_pe_w[PE_K * PE_K * PE_C + c];
         const float* base = s_map + (2 * oy) * wp + 2 * ox;           // tap (ky,kx) reads input (2oy-2+ky, 2ox-2+kx)
-#pragma unroll 1
+#pragma unroll
         for (int ky = 0; ky < PE_K; ++ky) {
             float x[8];
 #pragma unroll
@@ -105,26 +124,19 @@ patch_conv1_kernel(const float* __restrict__ maps, const float* __restrict__ wgt
                 x[2 * e] = t.x; x[2 * e + 1] = t.y;
             }
 #pragma unroll
-            for (int kx = 0; kx < PE_K; ++kx) {
-                const float4* wv = reinterpret_cast<const float4*>(s_w + (ky * PE_K + kx) * PE_C);
-                const float2 x0 = make_float2(x[kx], x[kx]), x1 = make_float2(x[kx + 2], x[kx + 2]);
+            for (int kx = 0; kx < PE_K; ++kx)
 #pragma unroll
-                for (int c4 = 0; c4 < PE_C / 4; ++c4) {
-                    const float4 ww = wv[c4];
-                    a0[2 * c4] = __ffma2_rn(x0, make_float2(ww.x, ww.y), a0[2 * c4]);
-                    a0[2 * c4 + 1] = __ffma2_rn(x0, make_float2(ww.z, ww.w), a0[2 * c4 + 1]);
-                    a1[2 * c4] = __ffma2_rn(x1, make_float2(ww.x, ww.y), a1[2 * c4]);
-                    a1[2 * c4 + 1] = __ffma2_rn(x1, make_float2(ww.z, ww.w), a1[2 * c4 + 1]);
+                for (int c = 0; c < PE_C; ++c) {
+                    const float wv = c_pe_w[(ky * PE_K + kx) * PE_C + c];
+                    a0[c] = fmaf(x[kx], wv, a0[c]);
+                    a1[c] = fmaf(x[kx + 2], wv, a1[c]);
                 }
-            }
         }
         float4* o = reinterpret_cast<float4*>(dst + ((long long)oy * wo + ox) * PE_C);   // 2 x 16 channels = 128 B
 #pragma unroll
         for (int c4 = 0; c4 < PE_C / 4; ++c4) {
-            o[c4] = make_float4(fmaxf(a0[2 * c4].x, 0.f), fmaxf(a0[2 * c4].y, 0.f), fmaxf(a0[2 * c4 + 1].x, 0.f),
-                                fmaxf(a0[2 * c4 + 1].y, 0.f));
-            o[4 + c4] = make_float4(fmaxf(a1[2 * c4].x, 0.f), fmaxf(a1[2 * c4].y, 0.f), fmaxf(a1[2 * c4 + 1].x, 0.f),
-                                    fmaxf(a1[2 * c4 + 1].y, 0.f));
+            o[c4] = make_float4(fmaxf(a0[4 * c4], 0.f), fmaxf(a0[4 * c4 + 1], 0.f), fmaxf(a0[4 * c4 + 2], 0.f), fmaxf(a0[4 * c4 + 3], 0.f));
+            o[4 + c4] = make_float4(fmaxf(a1[4 * c4], 0.f), fmaxf(a1[4 * c4 + 1], 0.f), fmaxf(a1[4 * c4 + 2], 0.f), fmaxf(a1[4 * c4 + 3], 0.f));
         }
     }
 }
@@ -132,25 +144,38 @@ patch_conv1_kernel(const float* __restrict__ maps, const float* __restrict__ wgt
 // ---- small-head attention: softmax(q k^T / sqrt(D)) v, fp32, K/V of one (batch, head) in shared memory ----
 // layouts: q (B or 1, Nq, H, D), k/v (B, Nk, H, D), out (B, Nq, H, D)  — i.e. the (tokens, heads*dim) matrices the
 // linear layers produce, no permutes. q_bstride == 0 broadcasts one query set over the batch.
+// optional operand layout + additive position terms of the shared-K/V kernels:
+//   row strides (floats) of q / k / v so that a fused [q|k|v] projection output can be consumed in place, and
+//   q_add (period, nq, heads*D), k_add (period, nk, heads*D) added to q / k on load, batch b using slice b % period
+//   (the position / context half of a projection whose input was cat([x, context]) + position encoding).
+struct AttnExtra {
+    int ldq, ldk, ldv, period;
+    const float* q_add;
+    const float* k_add;
+};
+
 constexpr int ATT_CHUNK = 4;     // keys per online-softmax update (one rescale of the accumulator per chunk)
 
 template <int D>
 __global__ void __launch_bounds__(128)
 attn_shared_kv_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                      float* __restrict__ out, int nq, int nk, int heads, long long q_bstride, float scale) {
+                      float* __restrict__ out, int nq, int nk, int heads, long long q_bstride, float scale, AttnExtra ex) {
     extern __shared__ float sm[];
     const int nkp = (nk + ATT_CHUNK - 1) / ATT_CHUNK * ATT_CHUNK;
     float* sk = sm;                 // [nkp][D], rows >= nk zero
     float* sv = sm + nkp * D;
     const int b = blockIdx.z, hd = blockIdx.y;
-    const long long kv_base = ((long long)b * nk * heads + hd) * D;
+    const float* kadd = ex.k_add ? ex.k_add + ((long long)(b % ex.period) * nk * heads + hd) * D : nullptr;
     for (int e = threadIdx.x; e < nkp * (D / 4); e += blockDim.x) {
         const int j = e / (D / 4), c = e % (D / 4);
         float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
         if (j < nk) {
-            const long long g = kv_base + (long long)j * heads * D + c * 4;
-            kk = *reinterpret_cast<const float4*>(k + g);
-            vv = *reinterpret_cast<const float4*>(v + g);
+            kk = *reinterpret_cast<const float4*>(k + ((long long)b * nk + j) * ex.ldk + hd * D + c * 4);
+            vv = *reinterpret_cast<const float4*>(v + ((long long)b * nk + j) * ex.ldv + hd * D + c * 4);
+            if (kadd) {
+                const float4 t = *reinterpret_cast<const float4*>(kadd + (long long)j * heads * D + c * 4);
+                kk.x += t.x; kk.y += t.y; kk.z += t.z; kk.w += t.w;
+            }
         }
         *reinterpret_cast<float4*>(sk + j * D + c * 4) = kk;
         *reinterpret_cast<float4*>(sv + j * D + c * 4) = vv;
@@ -159,10 +184,12 @@ attn_shared_kv_kernel(const float* __restrict__ q, const float* __restrict__ k, 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     float2 qr[D / 2], acc[D / 2];
-    const float* qp = q + (long long)b * q_bstride + ((long long)i * heads + hd) * D;
+    const float* qp = q + (long long)b * q_bstride + (long long)i * ex.ldq + hd * D;
+    const float* qa = ex.q_add ? ex.q_add + (((long long)(b % ex.period) * nq + i) * heads + hd) * D : nullptr;
 #pragma unroll
     for (int c = 0; c < D / 4; ++c) {
-        const float4 t = *reinterpret_cast<const float4*>(qp + 4 * c);
+        float4 t = *reinterpret_cast<const float4*>(qp + 4 * c);
+        if (qa) { const float4 u = *reinterpret_cast<const float4*>(qa + 4 * c); t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
         qr[2 * c] = make_float2(t.x * scale, t.y * scale);
         qr[2 * c + 1] = make_float2(t.z * scale, t.w * scale);
     }
@@ -234,21 +261,24 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 template <int D>
 __global__ void __launch_bounds__(256)
 attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-               float* __restrict__ out, int nq, int nk, int heads, long long q_bstride, float scale) {
+               float* __restrict__ out, int nq, int nk, int heads, long long q_bstride, float scale, AttnExtra ex) {
     extern __shared__ float sm[];
     constexpr int ST = D + 4, KS = D / 8;
     const int nkp = (nk + 31) / 32 * 32;
     uint32_t* sk = reinterpret_cast<uint32_t*>(sm);      // [nkp][ST] tf32 bit patterns, rows >= nk zero
     uint32_t* sv = sk + nkp * ST;
     const int b = blockIdx.z, hd = blockIdx.y;
-    const long long kv_base = ((long long)b * nk * heads + hd) * D;
+    const float* kadd = ex.k_add ? ex.k_add + ((long long)(b % ex.period) * nk * heads + hd) * D : nullptr;
     for (int e = threadIdx.x; e < nkp * (D / 4); e += blockDim.x) {
         const int j = e / (D / 4), c = (e % (D / 4)) * 4;
         float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
         if (j < nk) {
-            const long long g = kv_base + (long long)j * heads * D + c;
-            kk = *reinterpret_cast<const float4*>(k + g);
-            vv = *reinterpret_cast<const float4*>(v + g);
+            kk = *reinterpret_cast<const float4*>(k + ((long long)b * nk + j) * ex.ldk + hd * D + c);
+            vv = *reinterpret_cast<const float4*>(v + ((long long)b * nk + j) * ex.ldv + hd * D + c);
+            if (kadd) {
+                const float4 u = *reinterpret_cast<const float4*>(kadd + (long long)j * heads * D + c);
+                kk.x += u.x; kk.y += u.y; kk.z += u.z; kk.w += u.w;
+            }
         }
         *reinterpret_cast<uint4*>(sk + j * ST + c) = make_uint4(to_tf32(kk.x), to_tf32(kk.y), to_tf32(kk.z), to_tf32(kk.w));
         *reinterpret_cast<uint4*>(sv + j * ST + c) = make_uint4(to_tf32(vv.x), to_tf32(vv.y), to_tf32(vv.z), to_tf32(vv.w));
@@ -259,15 +289,23 @@ attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
     if (q0 >= nq) return;
     const int r0 = q0 + g, r1 = q0 + g + 8;
     const float* qb = q + (long long)b * q_bstride + (long long)hd * D;
-    const float* q0p = qb + (long long)min(r0, nq - 1) * heads * D;
-    const float* q1p = qb + (long long)min(r1, nq - 1) * heads * D;
+    const int c0r = min(r0, nq - 1), c1r = min(r1, nq - 1);
+    const float* q0p = qb + (long long)c0r * ex.ldq;
+    const float* q1p = qb + (long long)c1r * ex.ldq;
+    const float* qa = ex.q_add ? ex.q_add + ((long long)(b % ex.period) * nq * heads + hd) * D : nullptr;
     uint32_t a[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-        a[ks][0] = to_tf32(q0p[ks * 8 + t] * scale);
-        a[ks][1] = to_tf32(q1p[ks * 8 + t] * scale);
-        a[ks][2] = to_tf32(q0p[ks * 8 + t + 4] * scale);
-        a[ks][3] = to_tf32(q1p[ks * 8 + t + 4] * scale);
+        float x0 = q0p[ks * 8 + t], x1 = q1p[ks * 8 + t], x2 = q0p[ks * 8 + t + 4], x3 = q1p[ks * 8 + t + 4];
+        if (qa) {
+            const float* a0p = qa + (long long)c0r * heads * D + ks * 8 + t;
+            const float* a1p = qa + (long long)c1r * heads * D + ks * 8 + t;
+            x0 += a0p[0]; x1 += a1p[0]; x2 += a0p[4]; x3 += a1p[4];
+        }
+        a[ks][0] = to_tf32(x0 * scale);
+        a[ks][1] = to_tf32(x1 * scale);
+        a[ks][2] = to_tf32(x2 * scale);
+        a[ks][3] = to_tf32(x3 * scale);
     }
     float acc[KS][4];
 #pragma unroll
@@ -421,22 +459,36 @@ extern "C" int macvo_patch_embed_conv1(const float* maps, const float* weight, c
     if (n_maps == 0) return MACVO_OK;
     const int hp8 = (h + 7) / 8 * 8, wp8 = (w + 7) / 8 * 8;
     const int ho = hp8 / 2, wo = wp8 / 2;
-    const size_t smem = ((size_t)(2 * ho + 4) * (2 * wo + 4) + PE_C * 36) * sizeof(float);
+    const size_t smem = (size_t)(2 * ho + 4) * (2 * wo + 4) * sizeof(float);
     if (smem > 200 * 1024) return MACVO_E_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    // weights -> constant bank (a 2.4 KB device-to-device copy node; stays valid under CUDA-graph replay)
+    float* packed = nullptr;
+    MACVO_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&packed), g_pe_pack));
+    pe_pack_weights_kernel<<<3, 256, 0, st>>>(weight, bias, packed);
+    MACVO_LAUNCH_CHECK();
+    MACVO_CUDA_TRY(cudaMemcpyToSymbolAsync(c_pe_w, packed, sizeof(float) * (PE_K * PE_K * PE_C + PE_C), 0,
+                                           cudaMemcpyDeviceToDevice, st));
     MACVO_CUDA_TRY(cudaFuncSetAttribute(patch_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    patch_conv1_kernel<<<(unsigned)n_maps, 256, smem, as_stream(stream)>>>(maps, weight, bias, out, h, w, ho, wo);
+    const int items = ho * (wo / 2);
+    patch_conv1_kernel<<<(unsigned)n_maps, items % 320 == 0 ? 320 : 256, smem, st>>>(maps, out, h, w, ho, wo);
     MACVO_LAUNCH_CHECK();
     return MACVO_OK;
 }
 
-extern "C" int macvo_small_attention(const float* q, const float* k, const float* v, float* out, int batch, int nq,
-                                     int nk, int heads, int head_dim, int q_broadcast, int allow_tf32, void* stream) {
+extern "C" int macvo_small_attention_ex(const float* q, const float* k, const float* v, float* out, int batch, int nq,
+                                        int nk, int heads, int head_dim, int q_broadcast, int allow_tf32, int ldq, int ldk,
+                                        int ldv, const float* q_add, const float* k_add, int add_period, void* stream) {
     if (!q || !k || !v || !out || batch <= 0 || nq <= 0 || nk <= 0 || heads <= 0) return MACVO_E_ARG;
     if (head_dim != 8 && head_dim != 16 && head_dim != 32) return MACVO_E_UNSUPPORTED;
+    const int c = heads * head_dim;
+    AttnExtra ex{ldq > 0 ? ldq : c, ldk > 0 ? ldk : c, ldv > 0 ? ldv : c, add_period > 0 ? add_period : 1, q_add, k_add};
+    const bool plain = ex.ldq == c && ex.ldk == c && ex.ldv == c && !q_add && !k_add;
+    if ((ex.ldq | ex.ldk | ex.ldv) & 3) return MACVO_E_ARG;
     cudaStream_t st = as_stream(stream);
     const float scale = 1.f / sqrtf((float)head_dim);
-    const long long qbs = q_broadcast ? 0 : (long long)nq * heads * head_dim;
-    if (nq <= FQ_SLOTS * FQ_QPT && heads == FQ_HEADS && head_dim <= 16) {
+    const long long qbs = q_broadcast ? 0 : (long long)nq * ex.ldq;
+    if (plain && nq <= FQ_SLOTS * FQ_QPT && heads == FQ_HEADS && head_dim <= 16) {
         const unsigned grid = (unsigned)((batch + 3) / 4);
         if (head_dim == 16) attn_few_queries_kernel<16><<<grid, 128, 0, st>>>(q, k, v, out, batch, nq, nk, qbs, scale);
         else attn_few_queries_kernel<8><<<grid, 128, 0, st>>>(q, k, v, out, batch, nq, nk, qbs, scale);
@@ -449,10 +501,10 @@ extern "C" int macvo_small_attention(const float* q, const float* k, const float
         dim3 grid(ceil_div(nq, 16 * warps), heads, batch);
         if (head_dim == 16) {
             MACVO_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attn_tc_kernel<16><<<grid, 32 * warps, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale);
+            attn_tc_kernel<16><<<grid, 32 * warps, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale, ex);
         } else {
             MACVO_CUDA_TRY(cudaFuncSetAttribute(attn_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attn_tc_kernel<32><<<grid, 32 * warps, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale);
+            attn_tc_kernel<32><<<grid, 32 * warps, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale, ex);
         }
     } else {
         const size_t smem = (size_t)2 * ((nk + ATT_CHUNK - 1) / ATT_CHUNK * ATT_CHUNK) * head_dim * sizeof(float);
@@ -460,12 +512,27 @@ extern "C" int macvo_small_attention(const float* q, const float* k, const float
         dim3 grid(ceil_div(nq, 128), heads, batch);
         if (head_dim == 16) {
             MACVO_CUDA_TRY(cudaFuncSetAttribute(attn_shared_kv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attn_shared_kv_kernel<16><<<grid, 128, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale);
+            attn_shared_kv_kernel<16><<<grid, 128, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale, ex);
         } else {
             MACVO_CUDA_TRY(cudaFuncSetAttribute(attn_shared_kv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attn_shared_kv_kernel<32><<<grid, 128, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale);
+            attn_shared_kv_kernel<32><<<grid, 128, smem, st>>>(q, k, v, out, nq, nk, heads, qbs, scale, ex);
         }
     }
+    MACVO_LAUNCH_CHECK();
+    return MACVO_OK;
+}
+
+extern "C" int macvo_small_attention(const float* q, const float* k, const float* v, float* out, int batch, int nq,
+                                     int nk, int heads, int head_dim, int q_broadcast, int allow_tf32, void* stream) {
+    return macvo_small_attention_ex(q, k, v, out, batch, nq, nk, heads, head_dim, q_broadcast, allow_tf32, 0, 0, 0, nullptr,
+                                    nullptr, 0, stream);
+}
+
+extern "C" int macvo_add_rows_relu(float* x, const float* term, long long rows, int period, int channels, void* stream) {
+    if (!x || !term || rows < 0 || period <= 0 || channels <= 0 || (channels & 3)) return MACVO_E_ARG;
+    if (rows == 0) return MACVO_OK;
+    const long long n = rows * (channels / 4);
+    add_rows_relu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, term, rows, period, channels / 4);
     MACVO_LAUNCH_CHECK();
     return MACVO_OK;
 }

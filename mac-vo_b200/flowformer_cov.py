@@ -399,7 +399,11 @@ class FlowFormerCovNet:
             x = F.pad(cost_maps, (0, (8 - W2 % 8) % 8, 0, (8 - H2 % 8) % 8))
             x = self._conv_relu(x, p + "proj.0", stride=2, padding=2)
         x = self._conv_relu(x, p + "proj.2", stride=2, padding=2)
-        x = self._conv(x, p + "proj.4", stride=2, padding=2)
+        native = self._native(x)
+        # proj.4 has no activation after it, so its bias b4 only enters through ffn_with_coord.0: W0x (x + b4) — on the
+        # native path it is folded into the per-position term and the conv runs bias-free (saves a 0.13 ms bias pass)
+        x = F.conv2d(x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last),
+                     self.W[p + "proj.4.weight"], None if native else self.W[p + "proj.4.bias"], stride=2, padding=2)
         h, w = x.shape[2:]
 
         # ffn_with_coord.0 acts on cat([x, sine(patch centre)]): the position half does not depend on the input,
@@ -409,10 +413,14 @@ class FlowFormerCovNet:
         def coord_term():
             xy = coords_grid(1, h, w, x.device, x.dtype) * 8 + 4
             enc = sine_embed(xy.view(1, 2, -1).permute(0, 2, 1), COST_INPUT_DIM)          # (1, hw, 64)
-            return F.linear(enc, w0[:, COST_INPUT_DIM:, 0, 0], b0)                         # (1, hw, 128)
-        term = self._memo(("pe", h, w, x.dtype, x.device), coord_term)
+            term = F.linear(enc, w0[:, COST_INPUT_DIM:, 0, 0], b0)                         # (1, hw, 128)
+            if native:
+                term = term + F.linear(self.W[p + "proj.4.bias"], w0[:, :COST_INPUT_DIM, 0, 0])
+            return term.contiguous()
+        term = self._memo(("pe", h, w, x.dtype, x.device, native), coord_term)
         t = x.permute(0, 2, 3, 1).reshape(M, h * w, COST_INPUT_DIM)                        # tokens (free view in NHWC)
-        t = F.relu(F.linear(t, w0[:, :COST_INPUT_DIM, 0, 0]) + term)
+        t = F.linear(t, w0[:, :COST_INPUT_DIM, 0, 0])
+        t = self._ops.add_rows_relu_(t, term[0]) if native else F.relu(t + term)
         t = F.linear(t, self.W[p + "ffn_with_coord.2.weight"][:, :, 0, 0], self.W[p + "ffn_with_coord.2.bias"])
         return self._ln(t, p + "norm")
 
@@ -430,7 +438,36 @@ class FlowFormerCovNet:
         c = self._lin(context.flatten(2).permute(0, 2, 1), p + "context_proj").view(b, H, W, -1)
         return c.repeat(reps, 1, 1, 1)
 
+    def _vert_local_attn_native(self, x: Tensor, size, context: Tensor, p: str, ws: int, heads: int) -> Tensor:
+        """Same function as `_vert_local_attn` with the projections split by linearity:
+            q = Wq (cat[x, ctx] + enc) + bq = Wq[:, :C] x  +  (Wq[:, C:] ctx + Wq enc + bq)
+        The second term only depends on (image index % 2, position): it is built once per layer on 2 x Hp x Wp tokens and
+        added inside the attention kernel; x goes through ONE [q|k|v] GEMM whose output the kernel reads in place. Removes the
+        192-channel concat, its window copy, the encoding add and two thirds of the GEMM launches (core/twins.py:46-114)."""
+        Bt, N, C = x.shape
+        H, W = size
+        b = context.shape[0]
+        wq, wk = self.W[p + "q.weight"], self.W[p + "k.weight"]
+        enc = self._memo(("win", ws, C + VERT_C_DIM, x.dtype, x.device), lambda: sine_embed(
+            coords_grid(1, ws, ws, x.device, x.dtype).view(1, 2, -1).permute(0, 2, 1), C + VERT_C_DIM))      # (1, 49, 192)
+        cproj = self._lin(context.flatten(2).permute(0, 2, 1), p + "context_proj").view(b, H, W, -1)            # (b, H, W, 64)
+        cw, meta = self._to_windows(cproj, ws)                                                                 # (b*nwin, 49, 64), zero padded
+        w_qk_c = torch.cat([wq[:, C:], wk[:, C:]], 0)                                                          # (2C, 64)
+        w_qk = torch.cat([wq, wk], 0)
+        b_qk = torch.cat([self.W[p + "q.bias"], self.W[p + "k.bias"]], 0)
+        terms = F.linear(cw, w_qk_c) + F.linear(enc, w_qk, b_qk)                                               # (b*nwin, 49, 2C)
+        q_add, k_add = terms[..., :C].contiguous(), terms[..., C:].contiguous()
+        w_x = self._memo(("vloc_w", p), lambda: torch.cat([wq[:, :C], wk[:, :C], self.W[p + "v.weight"]], 0).contiguous())
+        b_x = self._memo(("vloc_b", p), lambda: torch.cat([torch.zeros(2 * C, device=x.device, dtype=x.dtype), self.W[p + "v.bias"]], 0))
+        xw, meta = self._to_windows(x.view(Bt, H, W, C), ws)                                                   # (Bt*nwin, 49, C)
+        qkv = F.linear(xw, w_x, b_x)
+        # window n = image * nwin + wi; images repeat the b contexts cyclically -> additive slice = n % (b * nwin)
+        o = self._ops.fused_qkv_attention(qkv, heads, q_add, k_add)
+        return self._lin(self._from_windows(o, meta, ws, H, W), p + "proj")
+
     def _vert_local_attn(self, x: Tensor, size, context: Tensor, p: str, ws: int = 7, heads: int = 8) -> Tensor:
+        if self._native(x) and (x.shape[-1] // heads) in (16, 32):
+            return self._vert_local_attn_native(x, size, context, p, ws, heads)
         Bt, N, C = x.shape
         H, W = size
         ctx = self._context_tokens(context, p, Bt // context.shape[0])
@@ -443,7 +480,38 @@ class FlowFormerCovNet:
         o = self._attn(self._lin(qkw, p + "q"), self._lin(qkw, p + "k"), self._lin(xw, p + "v"), heads)
         return self._lin(self._from_windows(o, meta, ws, H, W), p + "proj")
 
+    def _vert_global_attn_native(self, x: Tensor, size, context: Tensor, p: str, sr: int, heads: int) -> Tensor:
+        """`_vert_global_attn` for H, W multiples of sr, projections split by linearity like the local variant:
+        q = Wq[:, :C] x + T_q[image % b], and the strided key conv sr_key(cat[x, ctx]) = conv_x(x) + conv_c(ctx)[image % b]
+        (core/twins.py:120-183). No 192-channel concat, no encoding add over the full map."""
+        Bt, N, C = x.shape
+        H, W = size
+        b = context.shape[0]
+        Cq = C + VERT_C_DIM
+        wq = self.W[p + "q.weight"]
+        cproj = self._lin(context.flatten(2).permute(0, 2, 1), p + "context_proj")                              # (b, N, 64)
+        enc_full = self._memo(("full", H, W, Cq, x.dtype, x.device), lambda: sine_embed(
+            coords_grid(1, H, W, x.device, x.dtype).view(1, 2, -1).permute(0, 2, 1), Cq))
+        q_add = (F.linear(cproj, wq[:, C:]) + F.linear(enc_full, wq, self.W[p + "q.bias"])).contiguous()        # (b, N, C)
+        q = F.linear(x, wq[:, :C])
+        xg = x.view(Bt, H, W, C).permute(0, 3, 1, 2)
+        wsk = self.W[p + "sr_key.weight"]
+        wk_x = self._memo(("vglob_wkx", p), lambda: wsk[:, :C].contiguous(memory_format=torch.channels_last))
+        wk_c = self._memo(("vglob_wkc", p), lambda: wsk[:, C:].contiguous(memory_format=torch.channels_last))
+        k_ctx = F.conv2d(cproj.view(b, H, W, -1).permute(0, 3, 1, 2), wk_c, self.W[p + "sr_key.bias"], stride=sr)  # (b, C, h, w)
+        k_in = F.conv2d(xg, wk_x, None, stride=sr).permute(0, 2, 3, 1)                                          # (Bt, h, w, C) rows
+        M = k_in.shape[1] * k_in.shape[2]
+        k_in = (k_in.reshape(Bt // b, b, M, C) + k_ctx.permute(0, 2, 3, 1).reshape(1, b, M, C)).view(Bt, M, C)  # image i: ctx i % b
+        v_in = self._conv(xg, p + "sr_value", stride=sr).reshape(Bt, C, -1).permute(0, 2, 1)
+        v_in, k_in = self._ln(v_in, p + "norm"), self._ln(k_in, p + "norm")
+        enc_sub = self._memo(("sub", H // sr, W // sr, sr, C, x.dtype, x.device), lambda: sine_embed(
+            coords_grid(1, H // sr, W // sr, x.device, x.dtype).view(1, 2, -1).permute(0, 2, 1) * sr, C))
+        o = self._ops.attention_with_terms(q, self._lin(k_in + enc_sub, p + "k"), self._lin(v_in, p + "v"), heads, q_add)
+        return self._lin(o, p + "proj")
+
     def _vert_global_attn(self, x: Tensor, size, context: Tensor, p: str, sr: int = 4, heads: int = 8) -> Tensor:
+        if self._native(x) and size[0] % sr == 0 and size[1] % sr == 0 and (x.shape[-1] // heads) in (16, 32):
+            return self._vert_global_attn_native(x, size, context, p, sr, heads)
         Bt, N, C = x.shape
         H, W = size
         ctx = self._context_tokens(context, p, Bt // context.shape[0])

@@ -66,8 +66,10 @@ EXPORTS = {
                              + [C.c_void_p] * 2),
     "macvo_layer_norm": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
     "macvo_patch_embed_conv1": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "macvo_add_rows_relu": (C.c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "macvo_small_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
     "macvo_query_prep": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "macvo_small_attention_ex": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 10 + [C.c_void_p] * 2 + [C.c_int, C.c_void_p]),
     "macvo_gru_input": (C.c_int, [C.c_void_p] * 7 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_gates": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_blend": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
@@ -566,5 +568,64 @@ def query_prep(query: Tensor, ln_weight: Tensor, ln_bias: Tensor, coords: Tensor
     rc = load_library().macvo_query_prep(query.data_ptr(), _bias_ptr(ln_weight, 64, "ln weight"), _bias_ptr(ln_bias, 64, "ln bias"),
                                          co.data_ptr(), _bias_ptr(freq, 16, "freq"), out.data_ptr(), B, H * W, float(eps), _stream())
     _check(rc, "macvo_query_prep")
+    LAUNCHES[0] += 1
+    return out
+
+
+def add_rows_relu_(x: Tensor, term: Tensor) -> Tensor:
+    """in place relu(x + term[row % period]) on x (rows, C) / (M, period, C) with term (period, C)"""
+    c = x.shape[-1]
+    _dense(x, c, "add_rows_relu x")
+    term = _dense(term, c, "add_rows_relu term")
+    rc = load_library().macvo_add_rows_relu(x.data_ptr(), term.data_ptr(), x.numel() // c, term.numel() // c, c, _stream())
+    _check(rc, "macvo_add_rows_relu")
+    LAUNCHES[0] += 1
+    return x
+
+
+def fused_qkv_attention(qkv: Tensor, heads: int, q_add: Tensor | None = None, k_add: Tensor | None = None,
+                        allow_tf32: bool | None = None) -> Tensor:
+    """attention on a fused projection output qkv (B, N, 3*C) = [q | k | v] consumed in place (self-attention, Nq = Nk = N);
+    q_add / k_add (period, N, C): additive terms, batch b uses slice b % period. -> (B, N, C)"""
+    qkv = _dev(qkv, torch.float32, "fused_qkv_attention qkv")
+    b, n, c3 = qkv.shape
+    c = c3 // 3
+    if allow_tf32 is None:
+        allow_tf32 = bool(torch.backends.cuda.matmul.allow_tf32)
+    period = 0
+    for t in (q_add, k_add):
+        if t is not None:
+            _dense(t, c, "fused_qkv_attention additive term")
+            if t.shape[-2] != n:
+                raise MacvoB200Error("fused_qkv_attention: additive terms must be (period, N, C)")
+            period = t.numel() // (n * c)
+    out = torch.empty(b, n, c, dtype=torch.float32, device=qkv.device)
+    base = qkv.data_ptr()
+    rc = load_library().macvo_small_attention_ex(base, base + 4 * c, base + 8 * c, out.data_ptr(), b, n, n, heads, c // heads,
+                                                 0, int(allow_tf32), c3, c3, c3,
+                                                 None if q_add is None else q_add.data_ptr(),
+                                                 None if k_add is None else k_add.data_ptr(), period, _stream())
+    _check(rc, "macvo_small_attention_ex")
+    LAUNCHES[0] += 1
+    return out
+
+
+def attention_with_terms(q: Tensor, k: Tensor, v: Tensor, heads: int, q_add: Tensor | None = None,
+                         allow_tf32: bool | None = None) -> Tensor:
+    """small_attention with q_add (period, Nq, C) added to q on load (batch b uses slice b % period)"""
+    q, k, v = (_dev(t, torch.float32, "attention operand") for t in (q, k, v))
+    b, nk, c = k.shape
+    nq = q.shape[1]
+    if allow_tf32 is None:
+        allow_tf32 = bool(torch.backends.cuda.matmul.allow_tf32)
+    period = 0
+    if q_add is not None:
+        _dense(q_add, c, "attention_with_terms q_add")
+        period = q_add.numel() // (nq * c)
+    out = torch.empty(b, nq, c, dtype=torch.float32, device=k.device)
+    rc = load_library().macvo_small_attention_ex(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, nq, nk, heads,
+                                                 c // heads, 0, int(allow_tf32), 0, 0, 0,
+                                                 None if q_add is None else q_add.data_ptr(), None, period, _stream())
+    _check(rc, "macvo_small_attention_ex")
     LAUNCHES[0] += 1
     return out

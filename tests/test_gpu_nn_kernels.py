@@ -142,3 +142,22 @@ def test_query_prep(ops):
     ref = F.layer_norm(query, (64,), w, b) + sine_embed(coords.permute(0, 2, 3, 1).reshape(P, 2), 64)
     got = ops.query_prep(query, w, b, coords, freq)
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("tf32", [False, True])
+def test_fused_qkv_attention_with_additive_terms(ops, tf32):
+    """[q|k|v] consumed in place + q_add / k_add slices (b % period) == plain attention on the summed operands"""
+    g = torch.Generator().manual_seed(21)
+    B, N, heads, d, period = 12, 49, 8, 16, 4
+    C = heads * d
+    qkv = torch.randn(B, N, 3 * C, generator=g).to(DEV)
+    qa, ka = torch.randn(period, N, C, generator=g).to(DEV), torch.randn(period, N, C, generator=g).to(DEV)
+    idx = torch.arange(B, device=DEV) % period
+    ref = _ref_attention(qkv[..., :C] + qa[idx], qkv[..., C:2 * C] + ka[idx], qkv[..., 2 * C:], heads)
+    got = ops.fused_qkv_attention(qkv, heads, qa, ka, allow_tf32=tf32)
+    assert (got.double() - ref).abs().max().item() <= (4e-3 if tf32 else 2e-5) * ref.abs().max().item()
+    q, k, v = torch.randn(6, 200, C, generator=g).to(DEV), torch.randn(6, 75, C, generator=g).to(DEV), torch.randn(6, 75, C, generator=g).to(DEV)
+    qa2 = torch.randn(2, 200, C, generator=g).to(DEV)
+    ref = _ref_attention(q + qa2[torch.arange(6, device=DEV) % 2], k, v, heads)
+    got = ops.attention_with_terms(q, k, v, heads, qa2, allow_tf32=tf32)
+    assert (got.double() - ref).abs().max().item() <= (4e-3 if tf32 else 2e-5) * ref.abs().max().item()
