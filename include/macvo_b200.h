@@ -238,6 +238,13 @@ int macvo_small_attention_ex(const float* q, const float* k, const float* v, flo
                              int heads, int head_dim, int q_broadcast, int allow_tf32, int ldq, int ldk, int ldv,
                              const float* q_add, const float* k_add, int add_period, void* stream);
 
+/* Perceiver input layer, fused (core/encoder.py:150-191): 8 shared latent queries x 8 heads (head_dim 16) attend to
+ * the nk token rows of every cost map WITHOUT materialising K and V:  tokens (n_maps, nk, 128) fp32;
+ * ut (64, 128) = rows h*8+i of Wk[h]^T q[i,h] / sqrt(16); wv (128,128), bv (128) = the value projection;
+ * out (n_maps, 8, 128) = softmax(...) V in the layout of `MultiHeadAttention`'s output. TF32 tensor cores. */
+int macvo_latent_pool(const float* tokens, const float* ut, const float* wv, const float* bv, float* out,
+                      long long n_maps, int nk, void* stream);
+
 /* ---- decoder iteration glue: SepConvGRU state kept in NHWC [h | x] buffers ---------------
  * Module/Network/FlowFormer/core/gru.py:22-43 (SepConvGRU), gma.py:84-130, covhead.py:95-131. fp32, pixels-major.
  * A GRU input buffer is (pixels, 512): channels 0..127 = h (or r*h), 128..255 = inp, 256..383 = motion features,

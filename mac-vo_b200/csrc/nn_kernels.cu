@@ -364,6 +364,117 @@ attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
     }
 }
 
+// ---- perceiver input layer, fused (core/encoder.py:150-191, attention.py:32-68) ---------------------------------------
+// 8 learned latents cross-attend to the 80 patch tokens of every cost map. With q shared by all maps, linearity gives
+//     score[i,h,j] = q[i,h] . (Wk[h] t_j + bk[h]) = (Wk[h]^T q[i,h]) . t_j + const     (const drops out of the softmax)
+//     out[i,h]     = sum_j p_j (Wv[h] t_j + bv[h]) = Wv[h] (sum_j p_j t_j) + bv[h]
+// so neither K nor V (2 x 393 MB at 640x480, plus their two GEMMs) is ever materialised: one CTA per cost map runs a
+// 64-"query" (row = h*8+i of U^T = Wk^T q, pre-scaled), 128-dim attention whose keys AND values are the token rows,
+// then projects the pooled tokens with Wv. TF32 mma.sync, fp32 softmax/accumulate; tokens are read exactly once.
+constexpr int LP_D = 128, LP_ROWS = 64, LP_HEADS = 8, LP_HD = 16;
+__global__ void __launch_bounds__(128)
+latent_pool_kernel(const float* __restrict__ tokens, const float* __restrict__ ut, const float* __restrict__ wv,
+                   const float* __restrict__ bv, float* __restrict__ out, int nk) {
+    extern __shared__ float sm[];
+    constexpr int ST = LP_D + 4, KS = LP_D / 8;
+    const int nkp = (nk + 31) / 32 * 32;
+    uint32_t* st = reinterpret_cast<uint32_t*>(sm);                  // [nkp][ST] tf32 tokens, rows >= nk zero
+    const long long b = blockIdx.x;
+    const float* tb = tokens + b * nk * LP_D;
+    for (int e = threadIdx.x; e < nkp * (LP_D / 4); e += blockDim.x) {
+        const int j = e / (LP_D / 4), c = (e % (LP_D / 4)) * 4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < nk) t = __ldg(reinterpret_cast<const float4*>(tb + (long long)j * LP_D + c));
+        *reinterpret_cast<uint4*>(st + j * ST + c) = make_uint4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int r0 = warp * 16 + g, r1 = r0 + 8;                        // rows of U^T: head 2*warp (i = g) and head 2*warp+1
+    uint32_t a[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        a[ks][0] = to_tf32(__ldg(ut + r0 * LP_D + ks * 8 + t));
+        a[ks][1] = to_tf32(__ldg(ut + r1 * LP_D + ks * 8 + t));
+        a[ks][2] = to_tf32(__ldg(ut + r0 * LP_D + ks * 8 + t + 4));
+        a[ks][3] = to_tf32(__ldg(ut + r1 * LP_D + ks * 8 + t + 4));
+    }
+    __syncthreads();
+    float acc[KS][4];
+#pragma unroll
+    for (int nd = 0; nd < KS; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+    for (int kb = 0; kb < nkp; kb += 32) {
+        float s[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            const uint32_t* kr = st + (kb + nt * 8 + g) * ST + t;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) mma_tf32(s[nt], a[ks], kr[ks * 8], kr[ks * 8 + 4]);
+        }
+        if (kb + 32 > nk) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int key = kb + nt * 8 + 2 * t;
+                if (key >= nk) s[nt][0] = s[nt][2] = -CUDART_INF_F;
+                if (key + 1 >= nk) s[nt][1] = s[nt][3] = -CUDART_INF_F;
+            }
+        }
+        float x0 = s[0][0], x1 = s[0][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            x0 = fmaxf(x0, fmaxf(s[nt][0], s[nt][1]));
+            x1 = fmaxf(x1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+        const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
+        const float c0 = __expf(m0 - n0), c1 = __expf(m1 - n1);
+        m0 = n0; m1 = n1;
+        l0 *= c0; l1 *= c1;
+#pragma unroll
+        for (int nd = 0; nd < KS; ++nd) { acc[nd][0] *= c0; acc[nd][1] *= c0; acc[nd][2] *= c1; acc[nd][3] *= c1; }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const float p00 = __expf(s[nt][0] - n0), p01 = __expf(s[nt][1] - n0);
+            const float p10 = __expf(s[nt][2] - n1), p11 = __expf(s[nt][3] - n1);
+            l0 += p00 + p01; l1 += p10 + p11;
+            const uint32_t pa[4] = {to_tf32(p00), to_tf32(p10), to_tf32(p01), to_tf32(p11)};
+            const uint32_t* vr = st + (kb + nt * 8 + 2 * t) * ST + g;
+#pragma unroll
+            for (int nd = 0; nd < KS; ++nd) mma_tf32(acc[nd], pa, vr[nd * 8], vr[ST + nd * 8]);
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    // pooled tokens z (16 rows x 128) sit in the accumulator layout (row g / g+8, channels 8 nd + 2t, +1). Output
+    // projection out = Wv[h] z + bv[h]: rows g belong to head h0 = 2*warp, rows g+8 to h1 = h0 + 1, so two mma chains run
+    // over the same A fragments (channel permutation trick: A col t <-> channel 2t, t+4 <-> 2t+1), one per head's weights.
+    const int h0 = 2 * warp, h1 = h0 + 1;
+    float o0[2][4], o1[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) { o0[nt][0] = o0[nt][1] = o0[nt][2] = o0[nt][3] = 0.f; o1[nt][0] = o1[nt][1] = o1[nt][2] = o1[nt][3] = 0.f; }
+#pragma unroll
+    for (int nd = 0; nd < KS; ++nd) {
+        const uint32_t za[4] = {to_tf32(acc[nd][0] * i0), to_tf32(acc[nd][2] * i1), to_tf32(acc[nd][1] * i0), to_tf32(acc[nd][3] * i1)};
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {                       // B[k = channel][n = d] = Wv[h*16 + nt*8 + g][8 nd + 2t (+1)]
+            const float* w0 = wv + (long long)(h0 * LP_HD + nt * 8 + g) * LP_D + nd * 8 + 2 * t;
+            const float* w1 = wv + (long long)(h1 * LP_HD + nt * 8 + g) * LP_D + nd * 8 + 2 * t;
+            mma_tf32(o0[nt], za, to_tf32(__ldg(w0)), to_tf32(__ldg(w0 + 1)));
+            mma_tf32(o1[nt], za, to_tf32(__ldg(w1)), to_tf32(__ldg(w1 + 1)));
+        }
+    }
+    // o0: rows g (latent i = g) of head h0 in c0,c1; o1: rows g+8 (latent i = g) of head h1 in c2,c3
+    float* ob = out + (b * 8 + g) * (LP_HEADS * LP_HD);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+        const int d = nt * 8 + 2 * t;
+        *reinterpret_cast<float2*>(ob + h0 * LP_HD + d) = make_float2(o0[nt][0] + __ldg(bv + h0 * LP_HD + d), o0[nt][1] + __ldg(bv + h0 * LP_HD + d + 1));
+        *reinterpret_cast<float2*>(ob + h1 * LP_HD + d) = make_float2(o1[nt][2] + __ldg(bv + h1 * LP_HD + d), o1[nt][3] + __ldg(bv + h1 * LP_HD + d + 1));
+    }
+}
+
 // few queries per batch element (perceiver input layer: 8 latent queries x 8 heads vs 80 keys per cost map; latent
 // self-attention 8 x 8; decoder cross-attention 1 x 8): ONE WARP per batch element, lane = slot * 8 + head, each lane
 // owns queries slot and slot + 4. K/V rows stream straight from global memory: the 8 head segments of a key are one
@@ -533,6 +644,18 @@ extern "C" int macvo_add_rows_relu(float* x, const float* term, long long rows, 
     if (rows == 0) return MACVO_OK;
     const long long n = rows * (channels / 4);
     add_rows_relu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, term, rows, period, channels / 4);
+    MACVO_LAUNCH_CHECK();
+    return MACVO_OK;
+}
+
+extern "C" int macvo_latent_pool(const float* tokens, const float* ut, const float* wv, const float* bv, float* out,
+                                 long long n_maps, int nk, void* stream) {
+    if (!tokens || !ut || !wv || !bv || !out || n_maps < 0 || nk <= 0) return MACVO_E_ARG;
+    if (n_maps == 0) return MACVO_OK;
+    const size_t smem = (size_t)((nk + 31) / 32 * 32) * (LP_D + 4) * sizeof(float);
+    if (smem > 200 * 1024) return MACVO_E_UNSUPPORTED;
+    MACVO_CUDA_TRY(cudaFuncSetAttribute(latent_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    latent_pool_kernel<<<(unsigned)n_maps, 128, smem, as_stream(stream)>>>(tokens, ut, wv, bv, out, nk);
     MACVO_LAUNCH_CHECK();
     return MACVO_OK;
 }

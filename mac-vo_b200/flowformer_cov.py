@@ -549,7 +549,11 @@ class FlowFormerCovNet:
         lat = self.W[c + "latent_tokens"]                        # (1, 8, 128)
         M = tokens.shape[0]
         q = self._lin(self._ln(lat, p + "norm1"), p + "q")       # (1, 8, 128): shared by every source pixel
-        a = self._attn(q, self._lin(tokens, p + "k"), self._lin(tokens, p + "v"), 8)
+        if self._native(tokens) and torch.backends.cuda.matmul.allow_tf32 and LATENT_DIM == 128 and LATENT_TOKENS == 8:
+            # K and V are never built: scores and pooling run on the token rows themselves (csrc/nn_kernels.cu)
+            a = self._ops.latent_pool(tokens, q[0], self.W[p + "k.weight"], self.W[p + "v.weight"], self.W[p + "v.bias"])
+        else:
+            a = self._attn(q, self._lin(tokens, p + "k"), self._lin(tokens, p + "v"), 8)
         x = lat + self._lin(a, p + "proj")
         x = x + self._lin(F.gelu(self._lin(self._ln(x, p + "norm2"), p + "ffn.0")), p + "ffn.3")
         short_cut = x

@@ -70,6 +70,7 @@ EXPORTS = {
     "macvo_small_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
     "macvo_query_prep": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "macvo_small_attention_ex": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 10 + [C.c_void_p] * 2 + [C.c_int, C.c_void_p]),
+    "macvo_latent_pool": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_void_p]),
     "macvo_gru_input": (C.c_int, [C.c_void_p] * 7 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_gates": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_blend": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
@@ -627,5 +628,22 @@ def attention_with_terms(q: Tensor, k: Tensor, v: Tensor, heads: int, q_add: Ten
                                                  c // heads, 0, int(allow_tf32), 0, 0, 0,
                                                  None if q_add is None else q_add.data_ptr(), None, period, _stream())
     _check(rc, "macvo_small_attention_ex")
+    LAUNCHES[0] += 1
+    return out
+
+
+def latent_pool(tokens: Tensor, q: Tensor, wk: Tensor, wv: Tensor, bv: Tensor) -> Tensor:
+    """Perceiver input-layer attention without K / V: tokens (M, nk, 128), q (8, 128) shared latent queries (already
+    projected), wk / wv (128, 128), bv (128) -> (M, 8, 128). TF32 tensor cores (see macvo_latent_pool)."""
+    tokens = _dense(tokens, 128, "latent_pool tokens")
+    m, nk, c = tokens.shape
+    if c != 128 or tuple(q.shape[-2:]) != (8, 128):
+        raise MacvoB200Error("latent_pool: expects tokens (M, nk, 128) and q (8, 128)")
+    # U^T[h*8 + i, :] = Wk[h*16:(h+1)*16, :]^T q[i, h*16:(h+1)*16] / sqrt(16)
+    ut = torch.einsum("ihd,hdc->hic", q.reshape(8, 8, 16), wk.reshape(8, 16, 128)).reshape(64, 128).mul_(0.25).contiguous()
+    out = torch.empty(m, 8, 128, dtype=torch.float32, device=tokens.device)
+    rc = load_library().macvo_latent_pool(tokens.data_ptr(), ut.data_ptr(), _dense(wv, 128, "wv").data_ptr(),
+                                          _bias_ptr(bv, 128, "bv"), out.data_ptr(), m, nk, _stream())
+    _check(rc, "macvo_latent_pool")
     LAUNCHES[0] += 1
     return out

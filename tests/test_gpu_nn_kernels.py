@@ -161,3 +161,20 @@ def test_fused_qkv_attention_with_additive_terms(ops, tf32):
     ref = _ref_attention(q + qa2[torch.arange(6, device=DEV) % 2], k, v, heads)
     got = ops.attention_with_terms(q, k, v, heads, qa2, allow_tf32=tf32)
     assert (got.double() - ref).abs().max().item() <= (4e-3 if tf32 else 2e-5) * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("m,nk", [(5, 80), (3, 35), (2, 96), (7, 1)])
+def test_latent_pool_equals_cross_attention(ops, m, nk):
+    """fused perceiver input layer (no K / V tensors) vs the explicit MultiHeadAttention of core/attention.py:32-68,
+    including the key bias that the fused form drops (softmax-invariant). TF32 tolerance."""
+    g = torch.Generator().manual_seed(m * 100 + nk)
+    tokens = torch.randn(m, nk, 128, generator=g).to(DEV)
+    q = torch.randn(1, 8, 128, generator=g).to(DEV)
+    wk, wv = (torch.randn(128, 128, generator=g) * 0.15).to(DEV), (torch.randn(128, 128, generator=g) * 0.15).to(DEV)
+    bk, bv = torch.randn(128, generator=g).to(DEV), torch.randn(128, generator=g).to(DEV)
+    k = F.linear(tokens.double(), wk.double(), bk.double())
+    v = F.linear(tokens.double(), wv.double(), bv.double())
+    ref = _ref_attention(q.double(), k, v, 8)
+    got = ops.latent_pool(tokens, q[0], wk, wv, bv)
+    assert got.shape == (m, 8, 128)
+    assert (got.double() - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
