@@ -210,12 +210,14 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
         ops.LAUNCHES[0] = 0
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
+        torch.cuda.nvtx.range_push("macvo_timed")     # lets `ncu --nvtx --nvtx-include macvo_timed/` list exactly these launches
         last = None
         for f in seq[warmup:]:
             odo.run_pair(f)
             if read_pose and odo.optimizer.get_result() is not None:
                 last = odo.optimizer.get_result().motion.cpu()            # D2H of the step's result (synchronises)
         odo.finish()
+        torch.cuda.nvtx.range_pop()
         e.record()
         barrier()
         ms = s.elapsed_time(e)

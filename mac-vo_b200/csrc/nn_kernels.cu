@@ -269,19 +269,30 @@ attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
     uint32_t* sv = sk + nkp * ST;
     const int b = blockIdx.z, hd = blockIdx.y;
     const float* kadd = ex.k_add ? ex.k_add + ((long long)(b % ex.period) * nk * heads + hd) * D : nullptr;
-    for (int e = threadIdx.x; e < nkp * (D / 4); e += blockDim.x) {
-        const int j = e / (D / 4), c = (e % (D / 4)) * 4;
-        float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
-        if (j < nk) {
-            kk = *reinterpret_cast<const float4*>(k + ((long long)b * nk + j) * ex.ldk + hd * D + c);
-            vv = *reinterpret_cast<const float4*>(v + ((long long)b * nk + j) * ex.ldv + hd * D + c);
-            if (kadd) {
-                const float4 u = *reinterpret_cast<const float4*>(kadd + (long long)j * heads * D + c);
-                kk.x += u.x; kk.y += u.y; kk.z += u.z; kk.w += u.w;
+    constexpr int FILL_U = 4;                                        // row loads in flight per thread
+    for (int e0 = threadIdx.x; e0 < nkp * (D / 4); e0 += blockDim.x * FILL_U) {
+        float4 kb_[FILL_U], vb_[FILL_U];
+#pragma unroll
+        for (int u = 0; u < FILL_U; ++u) {
+            const int e = e0 + u * blockDim.x, j = e / (D / 4), c = (e % (D / 4)) * 4;
+            kb_[u] = vb_[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < nk) {
+                kb_[u] = *reinterpret_cast<const float4*>(k + ((long long)b * nk + j) * ex.ldk + hd * D + c);
+                vb_[u] = *reinterpret_cast<const float4*>(v + ((long long)b * nk + j) * ex.ldv + hd * D + c);
+                if (kadd) {
+                    const float4 w = *reinterpret_cast<const float4*>(kadd + (long long)j * heads * D + c);
+                    kb_[u].x += w.x; kb_[u].y += w.y; kb_[u].z += w.z; kb_[u].w += w.w;
+                }
             }
         }
-        *reinterpret_cast<uint4*>(sk + j * ST + c) = make_uint4(to_tf32(kk.x), to_tf32(kk.y), to_tf32(kk.z), to_tf32(kk.w));
-        *reinterpret_cast<uint4*>(sv + j * ST + c) = make_uint4(to_tf32(vv.x), to_tf32(vv.y), to_tf32(vv.z), to_tf32(vv.w));
+#pragma unroll
+        for (int u = 0; u < FILL_U; ++u) {
+            const int e = e0 + u * blockDim.x, j = e / (D / 4), c = (e % (D / 4)) * 4;
+            if (j < nkp) {
+                *reinterpret_cast<uint4*>(sk + j * ST + c) = make_uint4(to_tf32(kb_[u].x), to_tf32(kb_[u].y), to_tf32(kb_[u].z), to_tf32(kb_[u].w));
+                *reinterpret_cast<uint4*>(sv + j * ST + c) = make_uint4(to_tf32(vb_[u].x), to_tf32(vb_[u].y), to_tf32(vb_[u].z), to_tf32(vb_[u].w));
+            }
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -371,7 +382,7 @@ attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
 // so neither K nor V (2 x 393 MB at 640x480, plus their two GEMMs) is ever materialised: one CTA per cost map runs a
 // 64-"query" (row = h*8+i of U^T = Wk^T q, pre-scaled), 128-dim attention whose keys AND values are the token rows,
 // then projects the pooled tokens with Wv. TF32 mma.sync, fp32 softmax/accumulate; tokens are read exactly once.
-constexpr int LP_D = 128, LP_ROWS = 64, LP_HEADS = 8, LP_HD = 16;
+constexpr int LP_D = 128, LP_HEADS = 8, LP_HD = 16;   // 64 score rows = 8 heads x 8 latents
 __global__ void __launch_bounds__(128)
 latent_pool_kernel(const float* __restrict__ tokens, const float* __restrict__ ut, const float* __restrict__ wv,
                    const float* __restrict__ bv, float* __restrict__ out, int nk) {
@@ -381,11 +392,20 @@ latent_pool_kernel(const float* __restrict__ tokens, const float* __restrict__ u
     uint32_t* st = reinterpret_cast<uint32_t*>(sm);                  // [nkp][ST] tf32 tokens, rows >= nk zero
     const long long b = blockIdx.x;
     const float* tb = tokens + b * nk * LP_D;
-    for (int e = threadIdx.x; e < nkp * (LP_D / 4); e += blockDim.x) {
-        const int j = e / (LP_D / 4), c = (e % (LP_D / 4)) * 4;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < nk) t = __ldg(reinterpret_cast<const float4*>(tb + (long long)j * LP_D + c));
-        *reinterpret_cast<uint4*>(st + j * ST + c) = make_uint4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
+    constexpr int FILL_U = 8;                                        // loads in flight per thread (the fill is latency bound)
+    for (int e0 = threadIdx.x; e0 < nkp * (LP_D / 4); e0 += blockDim.x * FILL_U) {
+        float4 buf[FILL_U];
+#pragma unroll
+        for (int u = 0; u < FILL_U; ++u) {
+            const int e = e0 + u * blockDim.x, j = e / (LP_D / 4), c = (e % (LP_D / 4)) * 4;
+            buf[u] = (j < nk) ? __ldg(reinterpret_cast<const float4*>(tb + (long long)j * LP_D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < FILL_U; ++u) {
+            const int e = e0 + u * blockDim.x, j = e / (LP_D / 4), c = (e % (LP_D / 4)) * 4;
+            if (j < nkp)
+                *reinterpret_cast<uint4*>(st + j * ST + c) = make_uint4(to_tf32(buf[u].x), to_tf32(buf[u].y), to_tf32(buf[u].z), to_tf32(buf[u].w));
+        }
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int r0 = warp * 16 + g, r1 = r0 + 8;                        // rows of U^T: head 2*warp (i = g) and head 2*warp+1
@@ -545,6 +565,52 @@ attn_few_queries_kernel(const float* __restrict__ q, const float* __restrict__ k
     }
 }
 
+// one query per batch element (decoder cross-attention: each pixel's query vs its 8 cost-memory tokens,
+// decoder.py:56-76): one thread per (batch element, head); the 8 heads of a key row are one coalesced segment.
+template <int D>
+__global__ void __launch_bounds__(256)
+attn_single_query_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                         float* __restrict__ out, long long batch, int nk, int heads, float scale) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= batch * heads) return;
+    const long long b = e / heads;
+    const int hd = (int)(e % heads), C = heads * D;
+    float qr[D], acc[D];
+#pragma unroll
+    for (int c = 0; c < D; c += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(q + b * C + hd * D + c);
+        qr[c] = t.x * scale; qr[c + 1] = t.y * scale; qr[c + 2] = t.z * scale; qr[c + 3] = t.w * scale;
+        acc[c] = acc[c + 1] = acc[c + 2] = acc[c + 3] = 0.f;
+    }
+    float m = -CUDART_INF_F, l = 0.f;
+    const float* kp = k + b * nk * C + hd * D;
+    const float* vp = v + b * nk * C + hd * D;
+#pragma unroll 4
+    for (int j = 0; j < nk; ++j) {
+        float kk[D], vv[D];
+#pragma unroll
+        for (int c = 0; c < D; c += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(kp + (long long)j * C + c));
+            const float4 u = __ldg(reinterpret_cast<const float4*>(vp + (long long)j * C + c));
+            kk[c] = t.x; kk[c + 1] = t.y; kk[c + 2] = t.z; kk[c + 3] = t.w;
+            vv[c] = u.x; vv[c + 1] = u.y; vv[c + 2] = u.z; vv[c + 3] = u.w;
+        }
+        float sc = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) sc = fmaf(qr[c], kk[c], sc);
+        const float mn = fmaxf(m, sc);
+        const float corr = __expf(m - mn), p = __expf(sc - mn);
+        m = mn;
+        l = l * corr + p;
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] = fmaf(p, vv[c], acc[c] * corr);
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int c = 0; c < D; c += 4)
+        *reinterpret_cast<float4*>(out + b * C + hd * D + c) = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
+}
+
 }  // namespace
 
 extern "C" int macvo_layer_norm(const float* x, const float* weight, const float* bias, float* y, long long rows,
@@ -599,7 +665,11 @@ extern "C" int macvo_small_attention_ex(const float* q, const float* k, const fl
     cudaStream_t st = as_stream(stream);
     const float scale = 1.f / sqrtf((float)head_dim);
     const long long qbs = q_broadcast ? 0 : (long long)nq * ex.ldq;
-    if (plain && nq <= FQ_SLOTS * FQ_QPT && heads == FQ_HEADS && head_dim <= 16) {
+    if (plain && nq == 1 && !q_broadcast && head_dim <= 16) {
+        const unsigned grid = (unsigned)(((long long)batch * heads + 255) / 256);
+        if (head_dim == 16) attn_single_query_kernel<16><<<grid, 256, 0, st>>>(q, k, v, out, batch, nk, heads, scale);
+        else attn_single_query_kernel<8><<<grid, 256, 0, st>>>(q, k, v, out, batch, nk, heads, scale);
+    } else if (plain && nq <= FQ_SLOTS * FQ_QPT && heads == FQ_HEADS && head_dim <= 16) {
         const unsigned grid = (unsigned)((batch + 3) / 4);
         if (head_dim == 16) attn_few_queries_kernel<16><<<grid, 128, 0, st>>>(q, k, v, out, batch, nq, nk, qbs, scale);
         else attn_few_queries_kernel<8><<<grid, 128, 0, st>>>(q, k, v, out, batch, nq, nk, qbs, scale);

@@ -311,7 +311,7 @@ class FlowFormerCovNet:
         """softmax(q k^T / sqrt(d)) v on (B|1, Nq, C), (B, Nk, C), (B, Nk, C) token matrices -> (B, Nq, C)."""
         B, J, C = k.shape
         d = C // heads
-        if self._native(k) and (d in (16, 32) or (d == 8 and heads == 8 and q.shape[1] <= 8)) and 2 * J * d * 4 <= 200 * 1024:
+        if self._native(k) and (d in (16, 32) or (d == 8 and q.shape[1] <= 8 and (heads == 8 or q.shape[1] == 1))) and 2 * J * d * 4 <= 200 * 1024:
             return self._ops.small_attention(q, k, v, heads)
         I = q.shape[1]
         qh = q.reshape(q.shape[0], I, heads, d).permute(0, 2, 1, 3).expand(B, -1, -1, -1)
@@ -558,6 +558,7 @@ class FlowFormerCovNet:
         x = x + self._lin(F.gelu(self._lin(self._ln(x, p + "norm2"), p + "ffn.0")), p + "ffn.3")
         short_cut = x
         N = H1 * W1
+        self._join_context()                                      # first use of the context map
         for i in range(ENCODER_DEPTH):
             x = self._latent_layer(x, c + f"encoder_layers.{i}.")
             x = x.view(B, N, LATENT_TOKENS, -1).permute(0, 2, 1, 3).reshape(B * LATENT_TOKENS, N, -1)
@@ -665,8 +666,20 @@ class FlowFormerCovNet:
             corr = torch.cat([cost_global, cost_forward], dim=1)
             # motion encoder (gru.py:45-64)
             e = ub + "encoder."
-            cor = self._conv_relu(self._conv_relu(corr, e + "convc1"), e + "convc2", padding=1)
-            flo = self._conv_relu(self._conv_relu(flow, e + "convf1", padding=3), e + "convf2", padding=1)
+            if native:                                               # flow branch of the motion encoder on the side stream
+                main = torch.cuda.current_stream()
+                fork = torch.cuda.Event()
+                fork.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(fork)
+                    flo = self._conv_relu(self._conv_relu(flow, e + "convf1", padding=3), e + "convf2", padding=1)
+                    joinf = torch.cuda.Event()
+                    joinf.record(side)
+                cor = self._conv_relu(self._conv_relu(corr, e + "convc1"), e + "convc2", padding=1)
+                main.wait_event(joinf)
+            else:
+                cor = self._conv_relu(self._conv_relu(corr, e + "convc1"), e + "convc2", padding=1)
+                flo = self._conv_relu(self._conv_relu(flow, e + "convf1", padding=3), e + "convf2", padding=1)
             mf = torch.cat([self._conv_relu(torch.cat([cor, flo], dim=1), e + "conv", padding=1), flow], dim=1)
             # GMA aggregation (gma.py:84-130)
             mf = mf.contiguous(memory_format=torch.channels_last)
@@ -714,9 +727,31 @@ class FlowFormerCovNet:
     def forward(self, image1: Tensor, image2: Tensor) -> tuple[Tensor, Tensor]:
         image1 = ((2 * image1) - 1.0).to(self.enc_dtype)
         image2 = ((2 * image2) - 1.0).to(self.enc_dtype)
-        context = self.svt(image1, "context_encoder")
+        self._ctx_join = None
+        if self._ops is not None and image1.is_cuda:
+            # the context encoder (a chain of small kernels on 2 images) is independent of the feature encoder, the
+            # correlation volume and PatchEmbed: it runs on a forked stream and is joined where the cost perceiver first
+            # needs the context (its vertical layers)
+            main = torch.cuda.current_stream()
+            side = self._memo(("side_stream", image1.device), lambda: torch.cuda.Stream(image1.device))
+            fork = torch.cuda.Event()
+            fork.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(fork)
+                context = self.svt(image1, "context_encoder")
+                self._ctx_join = torch.cuda.Event()
+                self._ctx_join.record(side)
+            context.record_stream(main)
+        else:
+            context = self.svt(image1, "context_encoder")
         cost_memory, cost_maps = self.memory_encoder(image1, image2, context)
+        self._join_context()
         return self.memory_decoder(cost_memory, context.float(), cost_maps.float())
+
+    def _join_context(self) -> None:
+        if getattr(self, "_ctx_join", None) is not None:
+            torch.cuda.current_stream().wait_event(self._ctx_join)
+            self._ctx_join = None
 
     @torch.inference_mode()
     def inference(self, image1: Tensor, image2: Tensor) -> tuple[Tensor, Tensor]:

@@ -58,7 +58,7 @@ ATTN_CASES = [(37, 8, 80, 8, 16, True), (50, 8, 8, 8, 16, False), (33, 1, 8, 8, 
               (12, 49, 49, 8, 16, False), (9, 49, 49, 4, 32, False), (3, 1000, 300, 8, 16, False),
               (2, 700, 300, 4, 32, False), (2, 130, 75, 8, 32, False), (1, 5, 513, 8, 16, False),
               (5, 6, 21, 4, 32, False), (7, 3, 10, 8, 16, False), (2, 9, 30, 8, 16, False),
-              (41, 1, 8, 8, 8, False), (6, 8, 20, 8, 8, True)]
+              (41, 1, 8, 8, 8, False), (6, 8, 20, 8, 8, True), (77, 1, 8, 4, 16, False), (300, 1, 5, 8, 8, False)]
 
 
 @pytest.mark.parametrize("case", ATTN_CASES)

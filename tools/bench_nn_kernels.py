@@ -28,10 +28,13 @@ def sd(q, k, v, heads):
     kh, vh = (z.reshape(B, J, heads, d).permute(0, 2, 1, 3) for z in (k, v))
     return F.scaled_dot_product_attention(qh, kh, vh).permute(0, 2, 1, 3).reshape(B, -1, C)
 for name, (B, nq, nk, heads, d, bc) in {"input_layer": (9600, 8, 80, 8, 16, True), "latent": (9600, 8, 8, 8, 16, False),
-        "decoder_cross": (4800, 1, 8, 8, 16, False), "vert_local": (1728, 49, 49, 8, 16, False),
+        "decoder_cross": (9600, 1, 8, 8, 8, False), "vert_local": (1728, 49, 49, 8, 16, False),
         "vert_global": (16, 4800, 300, 8, 16, False), "svt_s0_local": (4 * 18 * 23, 49, 49, 4, 32, False),
         "svt_s0_global": (4, 19200, 300, 4, 32, False), "svt_s1_global": (4, 4800, 300, 8, 32, False)}.items():
     q = torch.randn(1 if bc else B, nq, heads * d, device=dev); k = torch.randn(B, nk, heads * d, device=dev); v = torch.randn_like(k)
     print("attn %-14s torch-sdpa %.1f us  native fp32 %.1f us  native tf32 %.1f us" % (
         name, t(lambda: sd(q, k, v, heads)), t(lambda: ops.small_attention(q, k, v, heads, False)),
         t(lambda: ops.small_attention(q, k, v, heads, True))))
+
+tok = torch.randn(9600, 80, 128, device=dev); q8 = torch.randn(8, 128, device=dev); wk = torch.randn(128, 128, device=dev) * 0.1; wv = torch.randn(128, 128, device=dev) * 0.1; bv = torch.randn(128, device=dev)
+print("latent_pool 9600x80x128: %.1f us" % t(lambda: ops.latent_pool(tok, q8, wk, wv, bv)))
