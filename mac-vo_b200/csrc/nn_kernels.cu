@@ -258,15 +258,26 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Shared-memory fragment layouts (both conflict-free for 128-bit loads, one LDS.128 feeds two mma B operands):
+//   K row j (stride STK = 16 mod 32 words):  word (ks/2)*16 + t*4 + (ks%2)*2 + h  holds K[j][ks*8 + t + 4h]
+//     -> lane (g,t) reads uint4 at row (key g), word (ks/2)*16 + t*4 = {b0,b1 of k-step ks, b0,b1 of k-step ks+1}
+//   V block of 8 keys kb8, column pair-tile ndp: word (((ndp*nkb8 + kb8)*8 + g)*4 + t)*4 + (key&1)*2 + (nd&1)
+//     holds V[kb8*8 + 2t + (key&1)][(2 ndp + (nd&1))*8 + g]  -> uint4 = {b0(nd even), b0(nd odd), b1(nd even), b1(nd odd)}
 template <int D>
 __global__ void __launch_bounds__(256)
 attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                float* __restrict__ out, int nq, int nk, int heads, long long q_bstride, float scale, AttnExtra ex) {
     extern __shared__ float sm[];
-    constexpr int ST = D + 4, KS = D / 8;
-    const int nkp = (nk + 31) / 32 * 32;
-    uint32_t* sk = reinterpret_cast<uint32_t*>(sm);      // [nkp][ST] tf32 bit patterns, rows >= nk zero
-    uint32_t* sv = sk + nkp * ST;
+    constexpr int KS = D / 8, STK = (D / 32) * 32 + 16, NVH = D / 16;
+    const int nkp = (nk + 31) / 32 * 32, nkb8 = nkp / 8;
+    uint32_t* sk = reinterpret_cast<uint32_t*>(sm);      // [nkp][STK]
+    uint32_t* sv = sk + nkp * STK;                       // [NVH][nkb8][8][4][4]
     const int b = blockIdx.z, hd = blockIdx.y;
     const float* kadd = ex.k_add ? ex.k_add + ((long long)(b % ex.period) * nk * heads + hd) * D : nullptr;
     constexpr int FILL_U = 4;                                        // row loads in flight per thread
@@ -289,8 +300,12 @@ attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
         for (int u = 0; u < FILL_U; ++u) {
             const int e = e0 + u * blockDim.x, j = e / (D / 4), c = (e % (D / 4)) * 4;
             if (j < nkp) {
-                *reinterpret_cast<uint4*>(sk + j * ST + c) = make_uint4(to_tf32(kb_[u].x), to_tf32(kb_[u].y), to_tf32(kb_[u].z), to_tf32(kb_[u].w));
-                *reinterpret_cast<uint4*>(sv + j * ST + c) = make_uint4(to_tf32(vb_[u].x), to_tf32(vb_[u].y), to_tf32(vb_[u].z), to_tf32(vb_[u].w));
+                const int ks = c >> 3, h = (c >> 2) & 1;                       // c..c+3 -> t = 0..3 of (k-step ks, half h)
+                uint32_t* kd = sk + j * STK + (ks >> 1) * 16 + (ks & 1) * 2 + h;
+                kd[0] = to_tf32(kb_[u].x); kd[4] = to_tf32(kb_[u].y); kd[8] = to_tf32(kb_[u].z); kd[12] = to_tf32(kb_[u].w);
+                const int nd = c >> 3, g0 = c & 7;                             // c..c+3 -> g = g0..g0+3 of column tile nd
+                uint32_t* vd = sv + ((((nd >> 1) * nkb8 + (j >> 3)) * 8 + g0) * 4 + ((j & 7) >> 1)) * 4 + (j & 1) * 2 + (nd & 1);
+                vd[0] = to_tf32(vb_[u].x); vd[16] = to_tf32(vb_[u].y); vd[32] = to_tf32(vb_[u].z); vd[48] = to_tf32(vb_[u].w);
             }
         }
     }
@@ -304,6 +319,7 @@ attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
     const float* q0p = qb + (long long)c0r * ex.ldq;
     const float* q1p = qb + (long long)c1r * ex.ldq;
     const float* qa = ex.q_add ? ex.q_add + ((long long)(b % ex.period) * nq * heads + hd) * D : nullptr;
+    const float sl2 = scale * 1.4426950408889634f;                  // scores in log2 units: p = 2^(s - m)
     uint32_t a[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -313,23 +329,29 @@ attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
             const float* a1p = qa + (long long)c1r * heads * D + ks * 8 + t;
             x0 += a0p[0]; x1 += a1p[0]; x2 += a0p[4]; x3 += a1p[4];
         }
-        a[ks][0] = to_tf32(x0 * scale);
-        a[ks][1] = to_tf32(x1 * scale);
-        a[ks][2] = to_tf32(x2 * scale);
-        a[ks][3] = to_tf32(x3 * scale);
+        a[ks][0] = to_tf32(x0 * sl2);
+        a[ks][1] = to_tf32(x1 * sl2);
+        a[ks][2] = to_tf32(x2 * sl2);
+        a[ks][3] = to_tf32(x3 * sl2);
     }
     float acc[KS][4];
 #pragma unroll
     for (int nd = 0; nd < KS; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
     float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+    const uint32_t* kbase = sk + g * STK + t * 4;
+    const uint32_t* vbase = sv + (g * 4 + t) * 4;
     for (int kb = 0; kb < nkp; kb += 32) {
         float s[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-            const uint32_t* kr = sk + (kb + nt * 8 + g) * ST + t;
+            const uint32_t* kr = kbase + (kb + nt * 8) * STK;
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) mma_tf32(s[nt], a[ks], kr[ks * 8], kr[ks * 8 + 4]);
+            for (int kp = 0; kp < KS / 2; ++kp) {
+                const uint4 kq = *reinterpret_cast<const uint4*>(kr + kp * 16);
+                mma_tf32(s[nt], a[2 * kp], kq.x, kq.y);
+                mma_tf32(s[nt], a[2 * kp + 1], kq.z, kq.w);
+            }
         }
         if (kb + 32 > nk) {                                  // ragged tail: keys >= nk do not take part
 #pragma unroll
@@ -348,20 +370,24 @@ attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
         x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
         x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
         const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
-        const float c0 = __expf(m0 - n0), c1 = __expf(m1 - n1);
+        const float c0 = ex2f(m0 - n0), c1 = ex2f(m1 - n1);
         m0 = n0; m1 = n1;
         l0 *= c0; l1 *= c1;
 #pragma unroll
         for (int nd = 0; nd < KS; ++nd) { acc[nd][0] *= c0; acc[nd][1] *= c0; acc[nd][2] *= c1; acc[nd][3] *= c1; }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-            const float p00 = __expf(s[nt][0] - n0), p01 = __expf(s[nt][1] - n0);
-            const float p10 = __expf(s[nt][2] - n1), p11 = __expf(s[nt][3] - n1);
+            const float p00 = ex2f(s[nt][0] - n0), p01 = ex2f(s[nt][1] - n0);
+            const float p10 = ex2f(s[nt][2] - n1), p11 = ex2f(s[nt][3] - n1);
             l0 += p00 + p01; l1 += p10 + p11;
             const uint32_t pa[4] = {to_tf32(p00), to_tf32(p10), to_tf32(p01), to_tf32(p11)};   // A cols t <-> key 2t, t+4 <-> 2t+1
-            const uint32_t* vr = sv + (kb + nt * 8 + 2 * t) * ST + g;
+            const uint32_t* vr = vbase + ((kb >> 3) + nt) * 128;
 #pragma unroll
-            for (int nd = 0; nd < KS; ++nd) mma_tf32(acc[nd], pa, vr[nd * 8], vr[ST + nd * 8]);
+            for (int ndp = 0; ndp < NVH; ++ndp) {
+                const uint4 vq = *reinterpret_cast<const uint4*>(vr + ndp * nkb8 * 128);
+                mma_tf32(acc[2 * ndp], pa, vq.x, vq.z);
+                mma_tf32(acc[2 * ndp + 1], pa, vq.y, vq.w);
+            }
         }
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -676,7 +702,7 @@ extern "C" int macvo_small_attention_ex(const float* q, const float* k, const fl
     } else if (head_dim == 8) {
         return MACVO_E_UNSUPPORTED;
     } else if (allow_tf32 && nq >= 16) {
-        const size_t smem = (size_t)2 * ((nk + 31) / 32 * 32) * (head_dim + 4) * sizeof(float);
+        const size_t smem = (size_t)((nk + 31) / 32 * 32) * ((head_dim / 32) * 32 + 16 + head_dim) * sizeof(float);
         if (smem > 200 * 1024) return MACVO_E_UNSUPPORTED;
         const int warps = nq > 64 ? 8 : 4;
         dim3 grid(ceil_div(nq, 16 * warps), heads, batch);

@@ -311,7 +311,7 @@ class FlowFormerCovNet:
         """softmax(q k^T / sqrt(d)) v on (B|1, Nq, C), (B, Nk, C), (B, Nk, C) token matrices -> (B, Nq, C)."""
         B, J, C = k.shape
         d = C // heads
-        if self._native(k) and (d in (16, 32) or (d == 8 and q.shape[1] <= 8 and (heads == 8 or q.shape[1] == 1))) and 2 * J * d * 4 <= 200 * 1024:
+        if self._native(k) and (d in (16, 32) or (d == 8 and q.shape[1] <= 8 and (heads == 8 or q.shape[1] == 1))) and (J + 31) // 32 * 32 * (2 * d + 16) * 4 <= 200 * 1024:
             return self._ops.small_attention(q, k, v, heads)
         I = q.shape[1]
         qh = q.reshape(q.shape[0], I, heads, d).permute(0, 2, 1, 3).expand(B, -1, -1, -1)
@@ -638,6 +638,9 @@ class FlowFormerCovNet:
             side = self._memo(("side_stream", ctx.device), lambda: torch.cuda.Stream(ctx.device))
             net_d, cnet_d = torch.empty(P, 128, dtype=dd, device=ctx.device), torch.empty(P, 128, dtype=dd, device=ctx.device)
             as_map = lambda t: t.view(B, H1, W1, -1).permute(0, 3, 1, 2)                   # channels_last logical map
+        # the N x N GMA attention matrix (184 MB at 640x480) is re-read by every iteration's aggregation GEMM, which is
+        # bound by that read: when TF32 matmuls are allowed it is kept in fp16 (values in [0, 1]; no precision below TF32's)
+        attention_h = attention.to(torch.float16) if native and torch.backends.cuda.matmul.allow_tf32 else None
         fast_tokens = native and QUERY_DIM == 64 and self.lookup_fn is self._ops.corr_lookup
         if fast_tokens:
             fte0_w, fte0_b = self.W[m + "flow_token_encoder.0.weight"].flatten(1), self.W[m + "flow_token_encoder.0.bias"]
@@ -684,7 +687,10 @@ class FlowFormerCovNet:
             # GMA aggregation (gma.py:84-130)
             mf = mf.contiguous(memory_format=torch.channels_last)
             v = self._conv(mf, ub + "aggregator.to_v").flatten(2).transpose(1, 2)   # (B, N, 128)
-            agg = torch.matmul(attention, v)                                        # (B, N, 128) = pixels-major
+            if attention_h is not None:     # fp16 operands (11-bit mantissa >= TF32's 10), fp32 accumulate AND fp32 output
+                agg = torch.bmm(attention_h, v.to(torch.float16), out_dtype=torch.float32)
+            else:
+                agg = torch.matmul(attention, v)                                    # (B, N, 128) = pixels-major
             if native:
                 # the flow branch (GRU + flow head) and the covariance branch (GRU + cov head) only share their input:
                 # at 60x80 each conv fills about half of the 148 SMs, so the two run on forked streams (fork/join is

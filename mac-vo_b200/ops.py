@@ -303,6 +303,7 @@ class CandidateList:
         self.thresh = torch.zeros((1,), dtype=torch.float32, device=device)
         self.status = torch.zeros((1,), dtype=torch.int32, device=device)
         self.host = torch.zeros((2,), dtype=torch.int32).pin_memory()      # [n, status]
+        self.perm_host = torch.empty((4096,), dtype=torch.int64).pin_memory()   # staging for the sampled permutation
         self.w = w
 
 
@@ -352,7 +353,10 @@ def sample_candidates(cand: CandidateList, num_point: int) -> Tensor:
     k = perm.numel()
     out = torch.empty((k, 2), dtype=torch.int64, device=dev)
     if k:
-        perm_d = perm.pin_memory().to(dev, non_blocking=True)
+        if k > cand.perm_host.numel():                               # (pinning per call costs ~0.1 ms: keep a buffer)
+            cand.perm_host = torch.empty((k,), dtype=torch.int64).pin_memory()
+        cand.perm_host[:k].copy_(perm)
+        perm_d = cand.perm_host[:k].to(dev, non_blocking=True)
         _check(lib.macvo_gather_pixels(cand.idx.data_ptr(), perm_d.data_ptr(), k, cand.w, out.data_ptr(), _stream()),
                "macvo_gather_pixels")
         LAUNCHES[0] += 1

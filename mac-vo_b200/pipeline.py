@@ -106,9 +106,9 @@ class TwoFrameOdometry:
         # CovarianceSanityFilter (Module/OutlierFilter.py:91-100)
         bad = (pos0_cov.isnan().any(dim=(-1, -2)) | pos0_cov.isinf().any(dim=(-1, -2))
                | pos1_cov.isnan().any(dim=(-1, -2)) | pos1_cov.isinf().any(dim=(-1, -2)))
+        num_obs = int((~bad).sum())                                    # `bad` lives on the host like the covariances: no sync
         keep = (~bad).to(dev)
         pos_Tw = se3_act(prev_pose.to(dev), pos0_Tc.float())[keep]
-        num_obs = int(keep.sum().item())
 
         self.poses.append(est_pose)
         out = None

@@ -317,6 +317,7 @@ class B200_MatchCovariance(ICovariance2to3):
         super().__init__(config)
         self.device = _require_cuda(config.device, "B200_MatchCovariance")
         self.last_status: torch.Tensor | None = None
+        self._status_host: torch.Tensor | None = None
 
     def estimate_device(self, frame, kp, depth_est, depth_cov, flow_cov, want_point: bool = False):
         """Device-resident variant: (cov (K,3,3) fp64 CUDA, point (K,3) fp32 CUDA or None)."""
@@ -334,8 +335,11 @@ class B200_MatchCovariance(ICovariance2to3):
     @torch.inference_mode()
     def estimate(self, frame, kp, depth_est, depth_cov, flow_cov) -> torch.Tensor:
         cov, _ = self.estimate_device(frame, kp, depth_est, depth_cov, flow_cov)
-        out = cov.cpu()
-        if int(self.last_status.item()) != 0:
+        if self._status_host is None:
+            self._status_host = torch.zeros((1,), dtype=self.last_status.dtype).pin_memory()
+        self._status_host.copy_(self.last_status, non_blocking=True)      # rides in front of the blocking copy below
+        out = cov.cpu()                                                     # ONE synchronising device->host copy
+        if int(self._status_host[0]) != 0:
             raise IndexError("MatchCovariance: a keypoint's depth patch leaves the image")
         return out
 
