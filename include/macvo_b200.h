@@ -216,9 +216,10 @@ int macvo_pgo_accumulate(const double* pos_Tw, const double* kp2_uv, const doubl
 int macvo_layer_norm(const float* x, const float* weight, const float* bias, float* y, long long rows,
                      int channels, float eps, void* stream);
 /* maps (n_maps, 1, h, w) -> out (n_maps, ho, wo, 16) [NHWC], ho = ceil8(h)/2, wo = ceil8(w)/2:
- * ReLU(conv2d(zero-pad to multiples of 8, weight (16,1,6,6), stride 2, padding 2) + bias). */
+ * ReLU(conv2d(zero-pad to multiples of 8, weight (16,1,6,6), stride 2, padding 2) + bias).
+ * allow_tf32 != 0: TF32 tensor-core implicit GEMM (what cuDNN does for the reference under cudnn.allow_tf32), else fp32 FMA. */
 int macvo_patch_embed_conv1(const float* maps, const float* weight, const float* bias, float* out,
-                            long long n_maps, int h, int w, void* stream);
+                            long long n_maps, int h, int w, int allow_tf32, void* stream);
 /* in place x[r, :] = relu(x[r, :] + term[r % period, :]); x (rows, channels), term (period, channels), channels % 4 == 0
  * (PatchEmbed.ffn_with_coord.0 with its position input folded into a per-position bias, encoder.py:40-52) */
 int macvo_add_rows_relu(float* x, const float* term, long long rows, int period, int channels, void* stream);

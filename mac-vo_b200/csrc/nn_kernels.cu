@@ -401,6 +401,61 @@ attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
     }
 }
 
+// ---- PatchEmbed conv1 on the tensor cores (TF32 mma.sync implicit GEMM), used when the caller allows TF32 convolutions
+// like cuDNN does for the reference (torch.backends.cudnn.allow_tf32): per cost map M = ho*wo output positions,
+// N = 16 channels, K = 36 taps (padded to 40). The A fragment is gathered straight from the map in shared memory
+// (neighbouring lanes read overlapping pixels -> broadcasts, no conflicts); the 16 x 40 filter lives in 20 registers.
+__global__ void __launch_bounds__(256)
+patch_conv1_tc_kernel(const float* __restrict__ maps, const float* __restrict__ wgt, const float* __restrict__ bias,
+                      float* __restrict__ out, int h, int w, int ho, int wo) {
+    extern __shared__ float sm[];
+    uint32_t* s_map = reinterpret_cast<uint32_t*>(sm);   // tf32 map with a 2-pixel zero frame on the top / left, (2ho+4) x (2wo+4)
+    const int hp = 2 * ho + 4, wp = 2 * wo + 4;
+    const float* src = maps + (long long)blockIdx.x * h * w;
+    for (int e = threadIdx.x; e < hp * wp; e += blockDim.x) {
+        const int y = e / wp - 2, x = e % wp - 2;
+        s_map[e] = (y >= 0 && y < h && x >= 0 && x < w) ? to_tf32(__ldg(src + y * w + x)) : 0u;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    // B fragments: b0 = W[tap = 8 ks + t][c = 8 nt + g], b1 = W[tap + 4][c]; wgt is (16, 1, 6, 6) = [c][tap]
+    uint32_t bw[5][2][2];
+    int toff[5][2];                                      // smem offset of tap (ky, kx) relative to the window origin
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int tap = ks * 8 + t + 4 * hh;
+            toff[ks][hh] = tap < 36 ? (tap / 6) * wp + tap % 6 : 0;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) bw[ks][nt][hh] = tap < 36 ? to_tf32(__ldg(wgt + (nt * 8 + g) * 36 + tap)) : 0u;
+        }
+    const float2 bia0 = make_float2(__ldg(bias + 2 * t), __ldg(bias + 2 * t + 1));
+    const float2 bia1 = make_float2(__ldg(bias + 8 + 2 * t), __ldg(bias + 8 + 2 * t + 1));
+    __syncthreads();
+    float* dst = out + (long long)blockIdx.x * ho * wo * PE_C;
+    const int npos = ho * wo;
+    for (int p0 = warp * 16; p0 < npos; p0 += (blockDim.x >> 5) * 16) {
+        const int pa = min(p0 + g, npos - 1), pb = min(p0 + g + 8, npos - 1);
+        const uint32_t* wa = s_map + (2 * (pa / wo)) * wp + 2 * (pa % wo);      // window origin of position pa
+        const uint32_t* wb = s_map + (2 * (pb / wo)) * wp + 2 * (pb % wo);
+        float c0[4] = {bia0.x, bia0.y, bia0.x, bia0.y}, c1[4] = {bia1.x, bia1.y, bia1.x, bia1.y};
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) {
+            const uint32_t a[4] = {wa[toff[ks][0]], wb[toff[ks][0]], wa[toff[ks][1]], wb[toff[ks][1]]};
+            mma_tf32(c0, a, bw[ks][0][0], bw[ks][0][1]);
+            mma_tf32(c1, a, bw[ks][1][0], bw[ks][1][1]);
+        }
+        if (p0 + g < npos) {
+            *reinterpret_cast<float2*>(dst + (long long)(p0 + g) * PE_C + 2 * t) = make_float2(fmaxf(c0[0], 0.f), fmaxf(c0[1], 0.f));
+            *reinterpret_cast<float2*>(dst + (long long)(p0 + g) * PE_C + 8 + 2 * t) = make_float2(fmaxf(c1[0], 0.f), fmaxf(c1[1], 0.f));
+        }
+        if (p0 + g + 8 < npos) {
+            *reinterpret_cast<float2*>(dst + (long long)(p0 + g + 8) * PE_C + 2 * t) = make_float2(fmaxf(c0[2], 0.f), fmaxf(c0[3], 0.f));
+            *reinterpret_cast<float2*>(dst + (long long)(p0 + g + 8) * PE_C + 8 + 2 * t) = make_float2(fmaxf(c1[2], 0.f), fmaxf(c1[3], 0.f));
+        }
+    }
+}
+
 // ---- perceiver input layer, fused (core/encoder.py:150-191, attention.py:32-68) ---------------------------------------
 // 8 learned latents cross-attend to the 80 patch tokens of every cost map. With q shared by all maps, linearity gives
 //     score[i,h,j] = q[i,h] . (Wk[h] t_j + bk[h]) = (Wk[h]^T q[i,h]) . t_j + const     (const drops out of the softmax)
@@ -657,7 +712,7 @@ extern "C" int macvo_layer_norm(const float* x, const float* weight, const float
 }
 
 extern "C" int macvo_patch_embed_conv1(const float* maps, const float* weight, const float* bias, float* out,
-                                       long long n_maps, int h, int w, void* stream) {
+                                       long long n_maps, int h, int w, int allow_tf32, void* stream) {
     if (!maps || !weight || !bias || !out || n_maps < 0 || h <= 0 || w <= 0) return MACVO_E_ARG;
     if (n_maps == 0) return MACVO_OK;
     const int hp8 = (h + 7) / 8 * 8, wp8 = (w + 7) / 8 * 8;
@@ -665,6 +720,12 @@ extern "C" int macvo_patch_embed_conv1(const float* maps, const float* weight, c
     const size_t smem = (size_t)(2 * ho + 4) * (2 * wo + 4) * sizeof(float);
     if (smem > 200 * 1024) return MACVO_E_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
+    if (allow_tf32) {
+        MACVO_CUDA_TRY(cudaFuncSetAttribute(patch_conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        patch_conv1_tc_kernel<<<(unsigned)n_maps, 256, smem, st>>>(maps, weight, bias, out, h, w, ho, wo);
+        MACVO_LAUNCH_CHECK();
+        return MACVO_OK;
+    }
     // weights -> constant bank (a 2.4 KB device-to-device copy node; stays valid under CUDA-graph replay)
     float* packed = nullptr;
     MACVO_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&packed), g_pe_pack));

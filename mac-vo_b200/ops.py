@@ -65,7 +65,7 @@ EXPORTS = {
     "macvo_pgo_accumulate": (C.c_int, [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2 + [C.c_double]
                              + [C.c_void_p] * 2),
     "macvo_layer_norm": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
-    "macvo_patch_embed_conv1": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "macvo_patch_embed_conv1": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "macvo_add_rows_relu": (C.c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "macvo_small_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
     "macvo_query_prep": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
@@ -116,7 +116,8 @@ def _dev(t: Tensor, dtype, what: str) -> Tensor:
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of torch's current stream; the public torch.cuda.current_stream() costs ~20 us of Python per call
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 _ws: dict = {}
@@ -471,7 +472,7 @@ def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5) -> Te
     return y
 
 
-def patch_embed_conv1(maps: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+def patch_embed_conv1(maps: Tensor, weight: Tensor, bias: Tensor, allow_tf32: bool | None = None) -> Tensor:
     """(M,1,H,W) cost maps -> ReLU(conv 6x6/2 (+ pad to x8)) as a logical (M,16,Ho,Wo) channels_last tensor."""
     maps = _dev(maps, torch.float32, "patch_embed maps")
     m, one, h, w = maps.shape
@@ -481,7 +482,8 @@ def patch_embed_conv1(maps: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     out = torch.empty(m, ho, wo, 16, dtype=torch.float32, device=maps.device)
     rc = load_library().macvo_patch_embed_conv1(maps.data_ptr(), _dev(weight, torch.float32, "w").data_ptr(),
                                                 _dev(bias, torch.float32, "b").data_ptr(), out.data_ptr(),
-                                                m, h, w, _stream())
+                                                m, h, w, int(torch.backends.cudnn.allow_tf32 if allow_tf32 is None else allow_tf32),
+                                                _stream())
     _check(rc, "macvo_patch_embed_conv1")
     LAUNCHES[0] += 1
     return out.permute(0, 3, 1, 2)

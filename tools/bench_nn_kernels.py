@@ -21,7 +21,7 @@ print("LN 76800x128   torch %.1f us  native %.1f us" % (t(lambda: F.layer_norm(x
 maps = torch.randn(9600, 1, 60, 80, device=dev); wt = torch.randn(16, 1, 6, 6, device=dev); bb = torch.randn(16, device=dev)
 def torch_conv():
     return F.relu(F.conv2d(F.pad(maps, (0, 0, 0, 4)), wt, bb, stride=2, padding=2))
-print("conv1 9600x60x80  torch %.1f us  native %.1f us" % (t(torch_conv), t(lambda: ops.patch_embed_conv1(maps, wt, bb))))
+print("conv1 9600x60x80  torch %.1f us  native fp32 %.1f us  native tf32 %.1f us" % (t(torch_conv), t(lambda: ops.patch_embed_conv1(maps, wt, bb, False)), t(lambda: ops.patch_embed_conv1(maps, wt, bb, True))))
 def sd(q, k, v, heads):
     B, J, C = k.shape; d = C // heads
     qh = q.reshape(q.shape[0], -1, heads, d).permute(0, 2, 1, 3).expand(B, -1, -1, -1)
