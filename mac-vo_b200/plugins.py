@@ -86,6 +86,8 @@ class B200_FlowFormerCovFrontend(IFrontend):
         # the reference frontend enables TF32 tensor cores for the dense layers (Frontend.py:275-277)
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
+        if os.environ.get("MACVO_B200_CUDNN_BENCHMARK") == "1":      # experiment switch: cuDNN autotuning of the conv algorithms
+            torch.backends.cudnn.benchmark = True
         torch.set_float32_matmul_precision("medium")
         self._graph = None
         self._static: dict = {}
