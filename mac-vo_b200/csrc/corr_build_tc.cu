@@ -126,6 +126,16 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
         "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(bar), "r"(rank) : "memory");
 }
+// explicit shared-space vector accesses for the epilogue transpose: through the generic `uint8_t*` the compiler emitted
+// LD.E / ST.E (generic address path, long-scoreboard latency) — ncu showed the epilogue warps waiting on exactly those
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -387,7 +397,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int quarter = warp & 3;
         const int group = (warp - 2) >> 2;
         const float unscale = PASSES == 3 ? SPLIT_UNSCALE : 1.f;
-        uint8_t* tbuf = smem_epi + (warp - 2) * EPI_WARP_BYTES;
+        const uint32_t tb = smem_u32(smem_epi + (warp - 2) * EPI_WARP_BYTES);
         const int acc = group;
         uint32_t acc_phase = 0;
         int row = row_begin, col = col_begin + group;
@@ -419,7 +429,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     v.y = __uint_as_float(r[c >> 3][4 * (c & 7) + 1]) * unscale;
                     v.z = __uint_as_float(r[c >> 3][4 * (c & 7) + 2]) * unscale;
                     v.w = __uint_as_float(r[c >> 3][4 * (c & 7) + 3]) * unscale;
-                    *reinterpret_cast<float4*>(tbuf + lane * 256 + ((c ^ (lane & 7)) << 4)) = v;
+                    sts128(tb + lane * 256 + ((c ^ (lane & 7)) << 4), v);
                 }
                 __syncwarp();
                 // read back transposed: instruction i covers rows 2i, 2i+1; 16 lanes x 16 B = one 256-byte row segment
@@ -429,7 +439,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int rr = 2 * i + (lane >> 4);
-                        const float4 v = *reinterpret_cast<const float4*>(tbuf + rr * 256 + (((lane & 15) ^ (rr & 7)) << 4));
+                        const float4 v = lds128(tb + rr * 256 + (((lane & 15) ^ (rr & 7)) << 4));
                         if (orow0 + rr < n && ocol < n) *reinterpret_cast<float4*>(dst0 + (long long)rr * n) = v;   // n % 8 == 0
                     }
                 }
