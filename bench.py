@@ -152,8 +152,9 @@ def time_corr_kernel(device: str, iters: int = 10) -> dict:
     """achieved HBM GB/s of the correlation-volume build at the workload's shape (B=2, D=256, N=4800)."""
     from macvo_b200 import ops
     g = torch.Generator().manual_seed(2)
-    f1 = (torch.randn(2, 256, H // 8, W // 8, generator=g) * 0.5).to(device)
-    f2 = (torch.randn(2, 256, H // 8, W // 8, generator=g) * 0.5).to(device)
+    # channels_last like the network's `channel_convertor` output (cuDNN NHWC): the operand pre-pass is then elementwise
+    f1 = (torch.randn(2, 256, H // 8, W // 8, generator=g) * 0.5).to(device).contiguous(memory_format=torch.channels_last)
+    f2 = (torch.randn(2, 256, H // 8, W // 8, generator=g) * 0.5).to(device).contiguous(memory_format=torch.channels_last)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     for _ in range(3):
         ops.corr_build(f1, f2)
@@ -258,7 +259,7 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
                 "h2d_bytes_per_step": 4 * 3 * H * W * 4, "d2h_bytes_per_step": 7 * 8 + 2 * 8 + 3 * 4},
         "gpu_launches": launches,
         "clocks": clk.summary(),
-        "roofline": {"kernel": "macvo_corr_build (split pre-pass + corr_tc_kernel<3>), B=2 D=256 N=4800", "bound": "hbm",
+        "roofline": {"kernel": "macvo_corr_build (fp16 hi/lo operand split + corr_tc_kernel<3>), B=2 D=256 N=4800, channels_last features", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": corr["bytes"],
                      "launch_seconds": corr["seconds"]},

@@ -51,6 +51,10 @@ const char* macvo_b200_version(void);
 #define MACVO_CORR_SIMT 0
 #define MACVO_CORR_TC_3XF16 1
 #define MACVO_CORR_TC_1XF16 2
+/* OR-ed into `mode` (tensor-core modes only): fmap1 / fmap2 are given K-major, (batch, n, dim) row-major — the memory of
+ * a channels_last (B, D, H1, W1) tensor, which is what cuDNN's NHWC `channel_convertor` produces — so the operand
+ * pre-pass is an elementwise fp16 split instead of a transpose. */
+#define MACVO_CORR_KMAJOR_INPUT 16
 size_t macvo_corr_workspace_bytes(int batch, int dim, int n, int mode);
 int macvo_corr_build(const float* fmap1, const float* fmap2, float* corr, int batch, int dim, int n, int mode,
                      void* workspace, size_t workspace_bytes, void* stream);

@@ -229,6 +229,30 @@ split_transpose_kernel(const float* __restrict__ f1, const float* __restrict__ f
     }
 }
 
+// K-major input (channels_last features, (B, N, D) rows): the pre-pass is a pure elementwise split, no transpose.
+// One thread per 4 consecutive d of one token; blockIdx.y selects the map (f1 -> A operands, f2 -> B operands).
+__global__ void __launch_bounds__(256)
+split_kmajor_kernel(const float* __restrict__ f1, const float* __restrict__ f2, __half* __restrict__ a_hi,
+                    __half* __restrict__ a_lo, __half* __restrict__ b_hi, __half* __restrict__ b_lo, long long quads,
+                    float scale) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= quads) return;
+    const bool second = blockIdx.y != 0;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(second ? f2 : f1) + e);
+    __half* hi = second ? b_hi : a_hi;
+    __half* lo = second ? b_lo : a_lo;
+    const float v[4] = {x.x * scale, x.y * scale, x.z * scale, x.w * scale};
+    __half h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h[i] = __float2half_rn(v[i]); l[i] = __float2half_rn(v[i] - __half2float(h[i])); }
+    __half2 hh[2] = {__halves2half2(h[0], h[1]), __halves2half2(h[2], h[3])};
+    *reinterpret_cast<uint2*>(hi + 4 * e) = *reinterpret_cast<uint2*>(hh);
+    if (lo) {
+        __half2 ll[2] = {__halves2half2(l[0], l[1]), __halves2half2(l[2], l[3])};
+        *reinterpret_cast<uint2*>(lo + 4 * e) = *reinterpret_cast<uint2*>(ll);
+    }
+}
+
 // ---- kernel 2 -----------------------------------------------------------------------------------------------
 template <int PASSES>   // 3: hi*hi + hi*lo + lo*hi     1: hi*hi
 __global__ void __launch_bounds__(THREADS, 1)
@@ -408,27 +432,32 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             if (warp == 2 && lane == 0) TR(2, 500 + acc);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t r[2][32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + h * EPI_COLS;
+            // drain the warp's whole 32 x 128 accumulator slice into registers first and hand the accumulator back at once
+            // (an event trace showed it being held 1.5 us — the smem transpose + stores of the first half — while the
+            // MMAs of the tile after next were waiting for it); the transposes / stores then overlap the next MMAs.
+            uint32_t r[4][32];
+            {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
                 tmem_ld_32x32b_x32(taddr, r[0]);
                 tmem_ld_32x32b_x32(taddr + 32, r[1]);
+                tmem_ld_32x32b_x32(taddr + 64, r[2]);
+                tmem_ld_32x32b_x32(taddr + 96, r[3]);
                 tmem_ld_wait();
-                if (h == 1) {                                             // whole accumulator is in registers: hand it back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * acc, 0);
-                    if (warp == 2 && lane == 0) TR(2, 600 + acc);
-                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * acc, 0);
+                if (warp == 2 && lane == 0) TR(2, 600 + acc);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
                 // write: row = lane (256 B), 16-byte chunk c stored at c ^ (row & 7)  -> conflict free
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     float4 v;
-                    v.x = __uint_as_float(r[c >> 3][4 * (c & 7) + 0]) * unscale;
-                    v.y = __uint_as_float(r[c >> 3][4 * (c & 7) + 1]) * unscale;
-                    v.z = __uint_as_float(r[c >> 3][4 * (c & 7) + 2]) * unscale;
-                    v.w = __uint_as_float(r[c >> 3][4 * (c & 7) + 3]) * unscale;
+                    v.x = __uint_as_float(r[2 * h + (c >> 3)][4 * (c & 7) + 0]) * unscale;
+                    v.y = __uint_as_float(r[2 * h + (c >> 3)][4 * (c & 7) + 1]) * unscale;
+                    v.z = __uint_as_float(r[2 * h + (c >> 3)][4 * (c & 7) + 2]) * unscale;
+                    v.w = __uint_as_float(r[2 * h + (c >> 3)][4 * (c & 7) + 3]) * unscale;
                     sts128(tb + lane * 256 + ((c ^ (lane & 7)) << 4), v);
                 }
                 __syncwarp();
@@ -531,7 +560,7 @@ size_t macvo_corr_tc_workspace_bytes(int batch, int dim, int n, int passes) {
     return operand_bytes(batch, dim, n) * (passes == 3 ? 4 : 2);
 }
 
-int macvo_corr_build_tc(const float* f1, const float* f2, float* corr, int batch, int dim, int n, int passes,
+int macvo_corr_build_tc(const float* f1, const float* f2, float* corr, int batch, int dim, int n, int passes, int kmajor,
                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (dim % BLOCK_K != 0 || dim > KMAX || n % 8 != 0) return MACVO_E_UNSUPPORTED;
     if (!workspace || workspace_bytes < macvo_corr_tc_workspace_bytes(batch, dim, n, passes)) return MACVO_E_WORKSPACE;
@@ -545,9 +574,18 @@ int macvo_corr_build_tc(const float* f1, const float* f2, float* corr, int batch
 
     // one launch splits both feature maps: blockIdx.z in [0, batch) -> f1, [batch, 2 batch) -> f2
     dim3 pgrid(ceil_div(n, 32), ceil_div(dim, 64), 2 * batch);
-    split_transpose_kernel<<<pgrid, 256, 0, st>>>(f1, f2, a_hi, a_lo, b_hi, b_lo, batch, dim, n,
-                                                  passes == 3 ? SPLIT_SCALE : 1.f);
-    MACVO_LAUNCH_CHECK();
+    static const int s_dbg_host = [] { const char* e = getenv("MACVO_B200_CORR_DEBUG"); return e ? atoi(e) : 0; }();
+    if (!(s_dbg_host & 16)) {                       // profiling aid (bit 16): reuse the operands of the previous call
+        if (kmajor) {
+            const long long quads = (long long)batch * n * dim / 4;
+            dim3 kgrid((unsigned)((quads + 255) / 256), 2);
+            split_kmajor_kernel<<<kgrid, 256, 0, st>>>(f1, f2, a_hi, a_lo, b_hi, b_lo, quads, passes == 3 ? SPLIT_SCALE : 1.f);
+        } else {
+            split_transpose_kernel<<<pgrid, 256, 0, st>>>(f1, f2, a_hi, a_lo, b_hi, b_lo, batch, dim, n,
+                                                          passes == 3 ? SPLIT_SCALE : 1.f);
+        }
+        MACVO_LAUNCH_CHECK();
+    }
 
     CUtensorMap m_a_hi, m_a_lo, m_b_hi, m_b_lo;
     float* m_out = corr;

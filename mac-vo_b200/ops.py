@@ -17,6 +17,7 @@ from .build import LIB_PATH
 Tensor = torch.Tensor
 
 CORR_SIMT, CORR_TC_3XF16, CORR_TC_1XF16 = 0, 1, 2
+CORR_KMAJOR_INPUT = 16      # OR-ed into the mode: operands given K-major (channels_last features)
 PGO_ACC = 55
 
 _lib = None
@@ -155,12 +156,19 @@ def corr_build(fmap1: Tensor, fmap2: Tensor, mode: int | None = None) -> Tensor:
         mode = default_corr_mode(D, n)
         if fmap1.dtype == torch.float16 and mode == CORR_TC_3XF16:
             mode = CORR_TC_1XF16
-    f1 = _dev(fmap1.float() if fmap1.dtype != torch.float32 else fmap1, torch.float32, "corr_build fmap1")
-    f2 = _dev(fmap2.float() if fmap2.dtype != torch.float32 else fmap2, torch.float32, "corr_build fmap2")
+    f1 = fmap1.float() if fmap1.dtype != torch.float32 else fmap1
+    f2 = fmap2.float() if fmap2.dtype != torch.float32 else fmap2
+    cl = torch.channels_last
+    kmajor = (mode != CORR_SIMT and f1.is_cuda and f2.is_cuda and not f1.is_contiguous() and not f2.is_contiguous()
+              and f1.is_contiguous(memory_format=cl) and f2.is_contiguous(memory_format=cl))
+    if kmajor:      # channels_last features are already K-major (B, N, D) rows: elementwise operand split, no transpose
+        f1, f2 = f1.permute(0, 2, 3, 1), f2.permute(0, 2, 3, 1)
+    f1 = _dev(f1, torch.float32, "corr_build fmap1")
+    f2 = _dev(f2, torch.float32, "corr_build fmap2")
     out = torch.empty((B, 1, H, W, H, W), dtype=torch.float32, device=f1.device)
     nbytes = lib.macvo_corr_workspace_bytes(B, D, n, mode)
     ws = _workspace("corr", nbytes, f1.device) if nbytes else None
-    rc = lib.macvo_corr_build(f1.data_ptr(), f2.data_ptr(), out.data_ptr(), B, D, n, mode,
+    rc = lib.macvo_corr_build(f1.data_ptr(), f2.data_ptr(), out.data_ptr(), B, D, n, mode | (CORR_KMAJOR_INPUT if kmajor else 0),
                               ws.data_ptr() if ws is not None else None, nbytes, _stream())
     _check(rc, "macvo_corr_build")
     LAUNCHES[0] += (1 if mode == CORR_SIMT else 2)

@@ -134,9 +134,23 @@ class B200_FlowFormerCovFrontend(IFrontend):
     def estimate_pair(self, frame_t1: StereoData, frame_t2: StereoData):
         """-> (IStereoDepth.Output of t2, IMatcher.Output t1 -> t2); batches [t2.L, t1.L] vs [t2.R, t2.L]
         exactly like the reference (Frontend.py:284-285)."""
+        bl_fx = frame_t2.frame_baseline * frame_t2.fx
+        if self._graph is not None:
+            # steady state: the four images go straight into the graph's static input buffers (no host-side concatenation;
+            # from pinned host memory these are asynchronous copies that overlap the previous frame's tail)
+            st = self._static
+            shape = (2,) + tuple(frame_t2.imageL.shape[1:])
+            assert shape == st["shape"], f"Input shape mismatch for CUDAGraph replay: {shape} != {st['shape']}"
+            assert bl_fx == st["bl_fx"], "camera baseline * fx changed since the CUDA graph was captured"
+            st["A"][0:1].copy_(frame_t2.imageL, non_blocking=True)
+            st["A"][1:2].copy_(frame_t1.imageL, non_blocking=True)
+            st["B"][0:1].copy_(frame_t2.imageR, non_blocking=True)
+            st["B"][1:2].copy_(frame_t2.imageL, non_blocking=True)
+            self._graph.replay()
+            ops.LAUNCHES[0] += st["launches"]
+            return self._outputs(st["out"], clone=True)
         input_A = torch.cat([frame_t2.imageL, frame_t1.imageL], dim=0)
         input_B = torch.cat([frame_t2.imageR, frame_t2.imageL], dim=0)
-        bl_fx = frame_t2.frame_baseline * frame_t2.fx
         if not getattr(self.config, "cuda_graph", True):
             out = self._run(input_A.to(self.device, non_blocking=True), input_B.to(self.device, non_blocking=True), bl_fx)
             return self._outputs(out, clone=False)
@@ -160,14 +174,7 @@ class B200_FlowFormerCovFrontend(IFrontend):
                             "launches": ops.LAUNCHES[0] - n0}     # macvo_b200 kernels inside one replay
             graph.replay()                             # (the reference returns its warm-up result here)
             return self._outputs(out, clone=True)
-        st = self._static
-        assert tuple(input_A.shape) == st["shape"], f"Input shape mismatch for CUDAGraph replay: {input_A.shape} != {st['shape']}"
-        assert bl_fx == st["bl_fx"], "camera baseline * fx changed since the CUDA graph was captured"
-        st["A"].copy_(input_A, non_blocking=True)
-        st["B"].copy_(input_B, non_blocking=True)
-        self._graph.replay()
-        ops.LAUNCHES[0] += st["launches"]
-        return self._outputs(st["out"], clone=True)
+        raise AssertionError("unreachable: the replay path returns above")
 
     @staticmethod
     def retrieve_pixels(pixel_uv: torch.Tensor, scalar_map: torch.Tensor | None, interpolate: bool = False):

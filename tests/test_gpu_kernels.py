@@ -311,3 +311,15 @@ def test_pgo_accumulate_packed(ops):
     np.testing.assert_allclose(acc[27:48], G[:6, :6][iu], rtol=1e-10, atol=1e-9)
     np.testing.assert_allclose(acc[48:54], np.einsum("kai,ka->i", Js, Rs)[:6], rtol=1e-10, atol=1e-9)
     np.testing.assert_allclose(acc[54], opgo.robust_loss(g, pose, 0.1), rtol=1e-12)
+
+
+def test_corr_build_channels_last_inputs_bit_identical(ops):
+    """K-major (channels_last) features take the elementwise operand split; same operands -> same bits as the NCHW path"""
+    f1, f2 = cases.corr_inputs(2, 12, 16)
+    a = ops.corr_build(f1.to(DEV), f2.to(DEV))
+    b = ops.corr_build(f1.to(DEV).contiguous(memory_format=torch.channels_last),
+                       f2.to(DEV).contiguous(memory_format=torch.channels_last))
+    assert torch.equal(a, b)
+    c = ops.corr_build(f1.to(DEV).contiguous(memory_format=torch.channels_last),
+                       f2.to(DEV).contiguous(memory_format=torch.channels_last), mode=ops.CORR_TC_1XF16)
+    assert torch.equal(c, ops.corr_build(f1.to(DEV), f2.to(DEV), mode=ops.CORR_TC_1XF16))
