@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ f1, const float* __restrict__ f2, __half* __restrict__ a_hi,
                        __half* __restrict__ a_lo, __half* __restrict__ b_hi, __half* __restrict__ b_lo, int batch,
                        int dim, int n, float scale) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the main kernel's prologue start early (PDL)
     __shared__ float tile[64][33];                                   // [d][token]
     const bool second = (int)blockIdx.z >= batch;
     const int b = second ? blockIdx.z - batch : blockIdx.z;
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(256)
 split_kmajor_kernel(const float* __restrict__ f1, const float* __restrict__ f2, __half* __restrict__ a_hi,
                     __half* __restrict__ a_lo, __half* __restrict__ b_hi, __half* __restrict__ b_lo, long long quads,
                     float scale) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the main kernel's prologue start early (PDL)
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= quads) return;
     const bool second = blockIdx.y != 0;
@@ -309,6 +311,9 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (warp == 0) {
         // ===================== TMA producer (both CTAs; completion is signalled on the leader's barriers) ==========
         if (elect_one()) {
+            // programmatic dependent launch: everything above (barrier init, TMEM allocation, cluster sync) overlapped the
+            // tail of the operand pre-pass; its fp16 operands are only touched from here on
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             int slot = 0; uint32_t phase = 0;
             int row = row_begin, col = col_begin;
             bool new_row = true;
@@ -534,14 +539,17 @@ int launch_main(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensor
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = SMEM_TOTAL;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    static const int dbg = getenv("MACVO_B200_CORR_DEBUG") ? atoi(getenv("MACVO_B200_CORR_DEBUG")) : 0;
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    // programmatic dependent launch on the operand pre-pass (bit 32 of MACVO_B200_CORR_DEBUG switches it off)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    static const int dbg = getenv("MACVO_B200_CORR_DEBUG") ? atoi(getenv("MACVO_B200_CORR_DEBUG")) : 0;
+    cfg.numAttrs = (dbg & 32) ? 1 : 2;
     unsigned long long* trace = nullptr;
     if (dbg & 8) {   // profiling aid: leave the event trace of cluster 0 in a managed buffer and dump it at exit
         static unsigned long long* tbuf = nullptr;
