@@ -174,7 +174,6 @@ class B200_FlowFormerCovFrontend(IFrontend):
                             "launches": ops.LAUNCHES[0] - n0}     # macvo_b200 kernels inside one replay
             graph.replay()                             # (the reference returns its warm-up result here)
             return self._outputs(out, clone=True)
-        raise AssertionError("unreachable: the replay path returns above")
 
     @staticmethod
     def retrieve_pixels(pixel_uv: torch.Tensor, scalar_map: torch.Tensor | None, interpolate: bool = False):

@@ -63,3 +63,38 @@ def test_ops_refuse_cpu_tensors(lib):
         ops.corr_build(torch.zeros(1, 64, 4, 4), torch.zeros(1, 64, 4, 4))
     with pytest.raises(ops.MacvoB200Error):
         ops.corr_lookup(torch.zeros(16, 1, 4, 4), torch.zeros(1, 2, 4, 4))
+
+
+def test_layer_ops_refuse_cpu_tensors(lib):
+    """the perceiver / decoder layer kernels have no CPU fallback either (the network class keeps the torch ops for
+    CPU tensors itself; the wrappers must fail loudly)"""
+    import torch
+    from macvo_b200 import ops
+    z = torch.zeros
+    calls = [
+        lambda: ops.layer_norm(z(4, 128), z(128), z(128)),
+        lambda: ops.patch_embed_conv1(z(2, 1, 8, 8), z(16, 1, 6, 6), z(16)),
+        lambda: ops.small_attention(z(2, 4, 128), z(2, 4, 128), z(2, 4, 128), 8),
+        lambda: ops.fused_qkv_attention(z(2, 49, 384), 8),
+        lambda: ops.latent_pool(z(2, 80, 128), z(8, 128), z(128, 128), z(128, 128), z(128)),
+        lambda: ops.add_rows_relu_(z(2, 80, 128), z(80, 128)),
+        lambda: ops.query_prep(z(8, 64), z(64), z(64), z(1, 2, 2, 4), z(16)),
+        lambda: ops.gru_gates(z(8, 256), z(8, 512), z(8, 128), z(8, 512)),
+        lambda: ops.gru_blend(z(8, 128), z(8, 128), z(8, 512), None),
+        lambda: ops.gru_input(z(8, 128), z(8, 128), z(1), [z(8, 512)]),
+    ]
+    for call in calls:
+        with pytest.raises(ops.MacvoB200Error):
+            call()
+
+
+def test_network_on_cpu_keeps_torch_layers():
+    """FlowFormerCovNet on a CPU device never touches the CUDA library (golden-parity runs of the oracle use it)"""
+    import torch
+    from macvo_b200.flowformer_cov import FlowFormerCovNet, synthetic_state_dict
+    from oracle import frontend as ofe
+    net = FlowFormerCovNet(synthetic_state_dict(0), "cpu", corr_fn=ofe.corr_volume, lookup_fn=ofe.window_lookup, decoder_depth=1)
+    assert net._ops is None
+    g = torch.Generator().manual_seed(0)
+    flow, cov = net.inference(torch.rand(1, 3, 64, 96, generator=g), torch.rand(1, 3, 64, 96, generator=g))
+    assert flow.shape == (1, 2, 64, 96) and cov.shape == (1, 2, 64, 96) and torch.isfinite(flow).all() and (cov > 0).all()

@@ -138,7 +138,12 @@ def test_dense_postproc_bit_exact(ops, golden, epd):
     for k in ("depth", "disparity", "depth_cov", "disparity_uncertainty", "flow", "flow_cov"):
         a, b = out[k].cpu(), g[k]
         assert a.shape == b.shape and a.dtype == torch.float32, k
-        assert torch.equal(a.nan_to_num(123.0), b.nan_to_num(123.0)), f"{k}: {(a - b).abs().nan_to_num(0).max()}"
+        if not torch.equal(a.nan_to_num(123.0), b.nan_to_num(123.0)):
+            bad = a.nan_to_num(123.0) != b.nan_to_num(123.0)
+            idx = bad.nonzero()[:4].tolist()
+            raise AssertionError(f"{k}: {int(bad.sum())} mismatches at {idx}: got {a[bad][:4].tolist()} want {b[bad][:4].tolist()}; "
+                                 f"inputs flow {flow[0, 0].flatten()[:2].tolist()} cov sum {float(cov.double().sum())!r} "
+                                 f"threads {torch.get_num_threads()}")
     if epd:
         assert out["depth_mask"].dtype == torch.bool and torch.equal(out["depth_mask"].cpu(), g["depth_mask"])
     else:
