@@ -41,6 +41,12 @@ CONFIGS = {
 SEQ_LEN = 8     # distinct synthetic frames, cycled (forwards / backwards) by the timed loop
 
 
+def workload_name(cfg: dict) -> str:
+    """one name for the workload, shared by both arms' `config`"""
+    return (f"640x480 synthetic stereo sequence, MACVO_{'Performant' if cfg['enc_dtype'] == 'fp32' else 'Fast'} settings "
+            f"({cfg['num_point']} keypoints, mapping on, decoder_depth 12), BASELINE configs[1]")
+
+
 def _dist():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -248,8 +254,7 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
         "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if cfg["enc_dtype"] == "fp32" else "f16/bf16 mixed",
         "data": "synthetic (seeded smoothed-noise TartanAir-shape stereo sequence, synthetic:0 network weights)",
-        "config": {"workload": f"640x480 synthetic stereo sequence, MACVO_{'Performant' if cfg['enc_dtype'] == 'fp32' else 'Fast'}"
-                               f" settings ({cfg['num_point']} keypoints, mapping on, decoder_depth 12), BASELINE configs[1]",
+        "config": {"workload": workload_name(cfg),
                    "streams": world, "parallelism": "replicas only (one independent stream per GPU, no collective)",
                    "l2": "per-frame working set (184 MB correlation volume + >1 GB activations) exceeds the 126 MB L2; "
                          "the corr roofline loop flushes L2 with a 256 MB write between launches",
@@ -291,8 +296,9 @@ def main() -> None:
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": a.gpus,
                 "steps": steps, "warmup": warm, "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "640x480 synthetic stereo sequence, MACVO_Performant settings, CPU arithmetic of the "
-                                       "reference (oracle port; the reference tree cannot travel to the GPU box)"},
+                "config": {"workload": workload_name(cfg),
+                           "arm": "CPU arithmetic of the reference (oracle port; the reference tree cannot travel to the GPU box), "
+                                  "bounded sample of the same workload"},
                 "cpu_baseline": r, "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
