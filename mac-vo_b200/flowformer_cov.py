@@ -10,7 +10,11 @@ re-implementation of the reference network
     Module/Network/FlowFormerCov/covhead.py:60-140      (12-iteration flow + covariance decoder)
     Module/Network/FlowFormer/core/gma.py, gru.py, attention.py
 
-The dense layers go through torch (cuDNN / cuBLAS) exactly as in the reference; the two operators
+Plain GEMMs and convolutions go through torch (cuBLAS / cuDNN — library GEMMs); everything memory-bound on a CUDA
+fp32 run goes through our own kernels (`csrc/nn_kernels.cu`, `csrc/decoder_fused.cu`: LayerNorm, PatchEmbed conv1,
+the attention family incl. the K/V-free perceiver input layer, the SepConvGRU glue on NHWC `[h|x]` state buffers, the
+decoder's query preparation); CPU tensors and half-precision runs keep the torch ops (`_native()`), which is also how
+the class is checked against the reference network's golden outputs on the CPU. The two operators
 `BASELINE.json: north_star` names are NOT torch ops here:
 
 * `corr_fn(f1, f2) -> (B, 1, H1, W1, H1, W1)`   all-pairs correlation volume (encoder.py:256-275)
@@ -24,7 +28,11 @@ Restructuring relative to the reference (same arithmetic per output, fewer launc
 * eval mode only returns the last prediction, so the convex upsampling and both 576-channel mask
   heads run once (after the last refinement) instead of 12 times;
 * z and r gates of each separable GRU share their input -> one conv with concatenated filters;
-* sine position encodings that do not depend on the input are built once per resolution.
+* sine position encodings that do not depend on the input are built once per resolution;
+* projections whose input is `cat([x, context]) + position` are split by linearity: the context / position half is a
+  per-(image % 2, position) term computed once per layer on 2 x N tokens and added inside the attention kernel;
+* independent branches (context encoder vs feature path, flow GRU vs covariance GRU, the two motion-encoder
+  branches) run on forked streams, which the frontend's CUDA graph captures as parallel branches.
 """
 from __future__ import annotations
 
