@@ -615,7 +615,7 @@ def fused_qkv_attention(qkv: Tensor, heads: int, q_add: Tensor | None = None, k_
                 raise MacvoB200Error("fused_qkv_attention: additive terms must be (period, N, C)")
             period = t.numel() // (n * c)
     out = torch.empty(b, n, c, dtype=torch.float32, device=qkv.device)
-    base = qkv.data_ptr()
+    base = qkv.data_ptr()                       # q | k | v start c floats (4 c bytes) apart inside every 3c-float row
     rc = load_library().macvo_small_attention_ex(base, base + 4 * c, base + 8 * c, out.data_ptr(), b, n, n, heads, c // heads,
                                                  0, int(allow_tf32), c3, c3, c3,
                                                  None if q_add is None else q_add.data_ptr(),
