@@ -6,8 +6,8 @@ HBM GB/s vs roofline).
 
 One "step" = one stereo frame through the whole hot path: FlowFormerCov frontend (correlation volume +
 12 x window lookup on the sm_100a kernels, dense layers through cuDNN/cuBLAS, CUDA graph) -> fused dense
-post-processing + keypoint scoring -> candidate selection -> per-keypoint gathers -> 2 x observation
-covariance -> two-frame pose-graph LM solve, on a seeded synthetic TartanAir-shape 640x480 sequence with the
+post-processing + keypoint scoring -> candidate selection -> device-side observation building (gathers, 2 x observation
+covariance, sanity filter, MatchObs packing) -> two-frame pose-graph LM solve -> mapping points, on a seeded synthetic TartanAir-shape 640x480 sequence with the
 MACVO_Performant settings (fp32 network, 200 keypoints, mapping on). `value` keeps the images resident in
 HBM; `e2e` goes through the plugin API with pinned HOST images (H2D inside the timed region) and reads the
 optimised pose back every frame. N > 1 = N independent streams, one per GPU (BASELINE config 5:
@@ -139,10 +139,10 @@ def run_cpu(cfg: dict, frames_to_time: int, warm: int) -> dict:
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-def build_gpu_pipeline(cfg: dict, device: str):
+def build_gpu_pipeline(cfg: dict, device: str, fused: bool = True):
     from types import SimpleNamespace as NS
     from macvo_b200 import plugins
-    from macvo_b200.pipeline import TwoFrameOdometry
+    from macvo_b200.pipeline import FusedTwoFrameOdometry, TwoFrameOdometry
     fe = plugins.B200_FlowFormerCovFrontend(NS(weight="synthetic:0", device=device, enc_dtype=cfg["enc_dtype"],
                                                dec_dtype=cfg["dec_dtype"], decoder_depth=12,
                                                enforce_positive_disparity=False, cuda_graph=True))
@@ -151,7 +151,10 @@ def build_gpu_pipeline(cfg: dict, device: str):
     cov = plugins.B200_MatchCovariance(NS(device=device, kernel_size=31, match_cov_default=0.25, min_depth_cov=0.05,
                                           min_flow_cov=0.25))
     pgo = plugins.B200_TwoFrame_PGO(NS(graph_type="disp", device=device, vectorize=True, parallel=False, autodiff=False))
-    return TwoFrameOdometry(fe, sel, cov, pgo, num_point=cfg["num_point"], map_selector=msel)
+    # fused: observation building / sanity filter / MatchObs packing / counted LM solve on the device, one host sync per
+    # frame (pipeline.FusedTwoFrameOdometry); plugin-API: the call sequence Odometry/MACVO.py:173-337 makes
+    cls = FusedTwoFrameOdometry if fused else TwoFrameOdometry
+    return cls(fe, sel, cov, pgo, num_point=cfg["num_point"], map_selector=msel)
 
 
 def time_corr_kernel(device: str, iters: int = 10) -> dict:
@@ -204,9 +207,9 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(frames, read_pose: bool):
+    def timed(frames, read_pose: bool, fused: bool = True):
         torch.manual_seed(5)
-        odo = build_gpu_pipeline(cfg, device)
+        odo = build_gpu_pipeline(cfg, device, fused)
         odo.initialize(frames[0])
         period = 2 * SEQ_LEN - 2                                          # ping-pong 0,1,..,7,6,..,1,0,1,...
         pp = lambda i: (i % period) if (i % period) < SEQ_LEN else period - (i % period)
@@ -221,7 +224,9 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
         last = None
         for f in seq[warmup:]:
             odo.run_pair(f)
-            if read_pose and odo.optimizer.get_result() is not None:
+            if read_pose and fused:
+                last = odo.latest_pose()                                  # D2H of the step's result (waits for this frame)
+            elif read_pose and odo.optimizer.get_result() is not None:
                 last = odo.optimizer.get_result().motion.cpu()            # D2H of the step's result (synchronises)
         odo.finish()
         torch.cuda.nvtx.range_pop()
@@ -237,6 +242,7 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
     with ClockSampler(local) as clk:
         ms_dev, launches, _ = timed(frames_dev, read_pose=False)
         ms_e2e, _, _ = timed(frames_host, read_pose=True)
+        ms_api, _, _ = timed(frames_host, read_pose=True, fused=False)
     corr = time_corr_kernel(device)
 
     peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
@@ -260,8 +266,14 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
                          "the corr roofline loop flushes L2 with a 256 MB write between launches",
                    "matmul_precision": "TF32 for the cuDNN/cuBLAS layers like the reference frontend (Frontend.py:275-277); "
                                        "correlation volume fp32-class (3 x fp16 split, fp32 accumulate)"},
+        # e2e: pinned HOST images in, optimised pose + the frame's packed observations / mapping points out, through the
+        # package's public driver (FusedTwoFrameOdometry over the C ABI); each image crosses PCIe once (2 per frame)
         "e2e": {"value": world * steps / (ms_e2e * 1e-3), "unit": "frames/s",
-                "h2d_bytes_per_step": 4 * 3 * H * W * 4, "d2h_bytes_per_step": 7 * 8 + 2 * 8 + 3 * 4},
+                "h2d_bytes_per_step": 2 * 3 * H * W * 4 + 2 * 8 * 2200,
+                "d2h_bytes_per_step": 7 * 8 + (31 * cfg["num_point"] + 4) * 8 + 2000 * (72 + 12) + 3 * 8},
+        # the same frames through the plugin-API call sequence of Odometry/MACVO.py:173-337 (CPU fp64 covariances,
+        # boolean indexing on the host's behalf: >= 7 host syncs per frame that the reference's API shape forces)
+        "e2e_plugin_api": {"value": world * steps / (ms_api * 1e-3), "unit": "frames/s"},
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "roofline": {"kernel": "macvo_corr_build (fp16 hi/lo operand split + corr_tc_kernel<3>), B=2 D=256 N=4800, channels_last features", "bound": "hbm",

@@ -165,10 +165,13 @@ int macvo_retrieve_pixels(const void* kp, int kp_is_int64, int k, const float* m
  *
  * kp (k,2) [u,v] int64 or fp32; depth (h,w) fp32; flow_cov (k,3) fp32 [uu, vv, uv], CLAMPED IN
  * PLACE to >= min_flow_cov^2 on its first two columns (reference side effect), or NULL = use
- * match_cov_default. out_cov (k,3,3) float64 (NED order z,x,y); out_point (k,3) fp32 NED point of
+ * match_cov_default; element (i, c) is read / written at flow_cov[i * row_stride + c * col_stride] (in elements), so the
+ * transposed view Odometry/MACVO.py:231-232 passes is clamped in the caller's own storage. depth_var (k) fp32 or NULL:
+ * with flow_cov == NULL it replaces the Gaussian-weighted patch variance (Project2to3.py:163-171). out_cov (k,3,3) float64 (NED order z,x,y); out_point (k,3) fp32 NED point of
  * the CENTRE pixel depth (may be NULL); *status != 0 if a patch leaves the image (reference raises).
  */
 int macvo_match_covariance(const void* kp, int kp_is_int64, int k, const float* depth, int h, int w, float* flow_cov,
+                           long long flow_cov_row_stride, long long flow_cov_col_stride, const float* depth_var,
                            float fx, float fy, float cx, float cy, int kernel_size, float min_flow_cov,
                            float min_depth_cov, float match_cov_default, double* out_cov, float* out_point,
                            int* status, void* stream);
@@ -201,6 +204,14 @@ typedef struct {
 int macvo_pgo_solve(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp, const double* uv_cov,
                     const double* disp_cov, int k, const double* intr, double* pose_io,
                     const macvo_pgo_params_t* params, double* stats, void* stream);
+
+/* Same solve with the residual-block count read on the DEVICE (k = min(*k_dev, k_capacity)), so that the
+ * observation kernel's survivor count never visits the host; fewer than min_k blocks ("lost track",
+ * Odometry/MACVO.py:300-305: the optimiser is not started) leaves pose_io untouched and sets stats[6] = 1.
+ * stats[7] = 1 when a rank-deficient covariance block received its pseudo-inverse weight. */
+int macvo_pgo_solve_counted(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp, const double* uv_cov,
+                            const double* disp_cov, int k_capacity, const int* k_dev, int min_k, const double* intr,
+                            double* pose_io, const macvo_pgo_params_t* params, double* stats, void* stream);
 
 /* One evaluation of the packed normal-equation accumulator for a SHARD of residual blocks
  * (multi-GPU: each rank reduces its blocks, ranks all-reduce the 55 doubles):
@@ -269,6 +280,30 @@ int macvo_gru_blend(const float* q, const float* bias, const float* z, float* hx
  * coords (batch, 2, n1) [x, y]; freq: the 16 fp32 frequencies k*pi/200. */
 int macvo_query_prep(const float* query, const float* ln_weight, const float* ln_bias, const float* coords,
                      const float* freq, float* out, int batch, int n1, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (f3) observation building + sanity filter + MatchObs packing on the device — replaces the host code of
+ *      Odometry/MACVO.py:198-270 (flow lookup, filterPointsInRange, retrieve_pixels x9, ObsCovModel.estimate x2,
+ *      pixel2point_NED, MatchObs.init), CovarianceSanityFilter.filter (Module/OutlierFilter.py:91-100) and the
+ *      point registration SE3.Act(prev_pose, pos0_Tc) (MACVO.py:279-283) for the two-frame pose graph.
+ *
+ * kp0_uv (k,2) int64 selected keypoints; flow (2,h,w), match_cov (3,h,w) of the frame0->frame1 match; depth0 of
+ * frame 0; depth1 / disparity1 / disp_unc1 of frame 1 (all (h,w) fp32 device). intr0 / intr1: HOST {fx,fy,cx,cy}.
+ * prev_pose (7) float64 device [t, q_xyzw]; next_pose (7) receives the static-motion-model prediction (prev pose
+ * rounded to fp32, what the map stores). packed: macvo_observe_packed_doubles(capacity) float64, layout with c = capacity:
+ *   [0,3c) pos_Tw | [3c,5c) pixel2_uv | [5c,6c) pixel2_disp | [6c,9c) pixel2_uv_cov | [9c,10c) pixel2_disp_cov
+ *   [10c,19c) obs1_covTc | [19c,28c) obs2_covTc | [28c,30c) pixel1_uv | [30c,31c) pixel1_d | [31c,31c+4) n_obs, n_inbound, k, status
+ * (the first five sections are exactly the arrays macvo_pgo_solve_counted reads). *n_obs = survivors (device int).
+ * *status (zeroed by the caller): 1 = a covariance patch left the image (the reference raises IndexError).
+ */
+size_t macvo_observe_workspace_bytes(int capacity);
+size_t macvo_observe_packed_doubles(int capacity);
+int macvo_observe_pack(const int64_t* kp0_uv, int k, int capacity, const float* flow, const float* match_cov,
+                       const float* depth0, const float* depth1, const float* disparity1, const float* disp_unc1,
+                       int h, int w, int edge_width, const float* intr0, const float* intr1, int kernel_size,
+                       float min_flow_cov, float min_depth_cov, float match_cov_default, const double* prev_pose,
+                       double* next_pose, double* packed, int* n_obs, int* status, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,6 +106,9 @@ __device__ void reduce_all(Shared& S, cg::cluster_group& cluster, double acc0, d
 struct Problem {
     const double *pos, *uv, *disp, *uvcov, *dcov;
     int k;
+    const int* k_dev;          // optional device-side block count (<= k): the observation kernel's survivor count
+    int min_k;                 // fewer blocks than this: leave the pose untouched (Odometry/MACVO.py:300-305)
+    double* singular_flag;     // stats + 7 or nullptr
     Intr K;
     double delta;
 };
@@ -163,8 +166,22 @@ __device__ void accumulate_full(const Problem& P, const double* posevec, Shared&
         const double s = sn < P.delta ? 1.0 : sqrt(P.delta / sn);              // FastTriggs: sqrt(rho'(|r|^2))
         // information matrix of the block: inverse of [[a, c, 0], [c, b, 0], [0, 0, e]]
         const double ca = P.uvcov[3 * k], cb = P.uvcov[3 * k + 1], cc = P.uvcov[3 * k + 2], ce = P.dcov[k];
-        const double idet = 1.0 / (ca * cb - cc * cc);
-        const double w00 = cb * idet, w11 = ca * idet, w01 = -cc * idet, w22 = 1.0 / ce;
+        // the reference takes torch.pinverse of every 3x3 covariance block (Graphs.py:139-148): identical to the inverse
+        // for the positive-definite blocks of this path; a rank-deficient block gets its Moore-Penrose weight (rank-1
+        // symmetric M: M / trace(M)^2; zero block: zero weight) instead of inf / NaN, and is reported in stats[7]
+        const double det = ca * cb - cc * cc, scale2 = ca * cb + cc * cc;
+        double w00, w11, w01, w22;
+        bool singular = false;
+        if (fabs(det) > 1e-14 * scale2 && isfinite(det)) {
+            const double idet = 1.0 / det;
+            w00 = cb * idet; w11 = ca * idet; w01 = -cc * idet;
+        } else {
+            const double tr = ca + cb, itr2 = (tr * tr > 0.0 && isfinite(tr)) ? 1.0 / (tr * tr) : 0.0;
+            w00 = ca * itr2; w11 = cb * itr2; w01 = cc * itr2;
+            singular = true;
+        }
+        if (fabs(ce) > 0.0 && isfinite(ce)) w22 = 1.0 / ce; else { w22 = 0.0; singular = true; }
+        if (singular && lane == 0 && P.singular_flag) *P.singular_flag = 1.0;
         if (lane < 18) {
             const int a = ja;
             const double j0v = h00 * jp0 + h01 * jp1;
@@ -306,6 +323,14 @@ pgo_lm_kernel(Problem P, double* __restrict__ pose_io, macvo_pgo_params_t prm, d
     const int gthread = rank * THREADS + threadIdx.x, nthreads = nblk * THREADS;
 
     if (threadIdx.x < 7) S.pose[threadIdx.x] = pose_io[threadIdx.x];
+    if (P.k_dev != nullptr) P.k = min(P.k, max(*P.k_dev, 0));
+    if (P.k < P.min_k) {        // lost track: every CTA of the cluster takes this branch together
+        if (rank == 0 && threadIdx.x == 0 && stats) {
+            for (int i = 0; i < 6; ++i) stats[i] = 0.0;
+            stats[6] = 1.0;                                       // skipped
+        }
+        return;
+    }
     __syncthreads();
 
     // optimiser / scheduler state, replicated identically in thread 0 of every CTA
@@ -396,7 +421,7 @@ pgo_lm_kernel(Problem P, double* __restrict__ pose_io, macvo_pgo_params_t prm, d
         for (int i = 0; i < 7; ++i) pose_io[i] = S.pose[i];
         if (stats) {
             stats[0] = steps; stats[1] = evals; stats[2] = loss; stats[3] = first_loss;
-            stats[4] = reject_count; stats[5] = damping; stats[6] = 0; stats[7] = 0;
+            stats[4] = reject_count; stats[5] = damping; stats[6] = 0;      // stats[7]: singular-block flag (set above)
         }
     }
     cluster.sync();     // no CTA may exit while a peer can still read its shared memory
@@ -432,9 +457,10 @@ int launch_cluster(const void* fn, int cluster, void** args, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int macvo_pgo_solve(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
-                               const double* uv_cov, const double* disp_cov, int k, const double* intr,
-                               double* pose_io, const macvo_pgo_params_t* params, double* stats, void* stream) {
+static int pgo_solve_impl(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
+                          const double* uv_cov, const double* disp_cov, int k, const int* k_dev, int min_k,
+                          const double* intr, double* pose_io, const macvo_pgo_params_t* params, double* stats,
+                          void* stream) {
     if (k < 0 || !intr || !pose_io || !params) return MACVO_E_ARG;
     if (k > 0 && (!pos_Tw || !kp2_uv || !kp2_disp || !uv_cov || !disp_cov)) return MACVO_E_ARG;
     macvo_pgo_params_t prm = *params;
@@ -444,11 +470,27 @@ extern "C" int macvo_pgo_solve(const double* pos_Tw, const double* kp2_uv, const
     if (cluster > 8) cluster = 8;
     Problem P;
     P.pos = pos_Tw; P.uv = kp2_uv; P.disp = kp2_disp; P.uvcov = uv_cov; P.dcov = disp_cov; P.k = k;
+    P.k_dev = k_dev; P.min_k = min_k; P.singular_flag = stats ? stats + 7 : nullptr;
     // intr is HOST memory: {fx, fy, cx, cy, baseline}
     P.K.fx = intr[0]; P.K.fy = intr[1]; P.K.cx = intr[2]; P.K.cy = intr[3]; P.K.bl = intr[4];
     P.delta = prm.huber_delta;
     void* args[] = {&P, &pose_io, &prm, &stats};
     return launch_cluster(reinterpret_cast<const void*>(&pgo_lm_kernel), cluster, args, as_stream(stream));
+}
+
+extern "C" int macvo_pgo_solve(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
+                               const double* uv_cov, const double* disp_cov, int k, const double* intr,
+                               double* pose_io, const macvo_pgo_params_t* params, double* stats, void* stream) {
+    return pgo_solve_impl(pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov, k, nullptr, 0, intr, pose_io, params, stats, stream);
+}
+
+extern "C" int macvo_pgo_solve_counted(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
+                                       const double* uv_cov, const double* disp_cov, int k_capacity, const int* k_dev,
+                                       int min_k, const double* intr, double* pose_io,
+                                       const macvo_pgo_params_t* params, double* stats, void* stream) {
+    if (!k_dev || min_k < 0) return MACVO_E_ARG;
+    return pgo_solve_impl(pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov, k_capacity, k_dev, min_k, intr, pose_io, params,
+                          stats, stream);
 }
 
 extern "C" int macvo_pgo_accumulate(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
@@ -458,6 +500,7 @@ extern "C" int macvo_pgo_accumulate(const double* pos_Tw, const double* kp2_uv, 
     if (k > 0 && (!pos_Tw || !kp2_uv || !kp2_disp || !uv_cov || !disp_cov)) return MACVO_E_ARG;
     Problem P;
     P.pos = pos_Tw; P.uv = kp2_uv; P.disp = kp2_disp; P.uvcov = uv_cov; P.dcov = disp_cov; P.k = k;
+    P.k_dev = nullptr; P.min_k = 0; P.singular_flag = nullptr;
     P.K.fx = intr[0]; P.K.fy = intr[1]; P.K.cx = intr[2]; P.K.cy = intr[3]; P.K.bl = intr[4];
     P.delta = huber_delta;
     void* args[] = {&P, &pose, &acc};

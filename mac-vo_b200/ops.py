@@ -59,10 +59,17 @@ EXPORTS = {
                                         + [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p]),
     "macvo_gather_pixels": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p] * 2),
     "macvo_retrieve_pixels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p] * 2),
-    "macvo_match_covariance": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    "macvo_match_covariance": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_longlong, C.c_longlong, C.c_void_p]
                                + [C.c_float] * 4 + [C.c_int] + [C.c_float] * 3 + [C.c_void_p] * 4),
     "macvo_pgo_solve": (C.c_int, [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2 + [C.POINTER(_PgoParams)]
                         + [C.c_void_p] * 2),
+    "macvo_pgo_solve_counted": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 2
+                                + [C.POINTER(_PgoParams)] + [C.c_void_p] * 2),
+    "macvo_observe_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "macvo_observe_packed_doubles": (C.c_size_t, [C.c_int]),
+    "macvo_observe_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p] * 2
+                           + [C.c_int] + [C.c_float] * 3 + [C.c_void_p] * 6 + [C.c_size_t, C.c_void_p]),
     "macvo_pgo_accumulate": (C.c_int, [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2 + [C.c_double]
                              + [C.c_void_p] * 2),
     "macvo_layer_norm": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
@@ -121,16 +128,12 @@ def _stream() -> int:
     return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
-_ws: dict = {}
-
-
 def _workspace(key, nbytes: int, device) -> Tensor:
-    """Grow-only scratch buffers (allocated outside CUDA-graph capture by the warm-up runs)."""
-    k = (key, str(device))
-    buf = _ws.get(k)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1024) + 1024, dtype=torch.uint8, device=device)
-        _ws[k] = buf
+    """Per-call scratch from torch's caching allocator (1024-B aligned view). Never a process-global buffer: inside a
+    CUDA-graph capture the allocation comes from the graph's private pool and lives as long as the graph does, so a
+    replay can never touch memory that a later, larger call re-allocated (kernel arguments and TMA tensor maps bake
+    the address in); outside a capture, stream-ordered reuse by the allocator is safe for these same-stream kernels."""
+    buf = torch.empty(max(nbytes, 1024) + 1024, dtype=torch.uint8, device=device)
     off = (-buf.data_ptr()) % 1024
     return buf[off:off + max(nbytes, 1)]
 
@@ -352,24 +355,35 @@ def select_mapping_candidates(depth: Tensor, depth_cov: Tensor, mask_width: int,
 def sample_candidates(cand: CandidateList, num_point: int) -> Tensor:
     """`perm = torch.randperm(n)[:numPoint]` on the CPU default generator (KeypointSelector.py:404) — the one
     host round trip of the selector (the reference has two: `.item()` and `nonzero`)."""
+    return sample_candidates_many([(cand, num_point)])[0]
+
+
+def sample_candidates_many(requests: list[tuple[CandidateList, int]]) -> list[Tensor]:
+    """Sampling for several candidate lists behind ONE host synchronisation: the counts of all lists are fetched
+    together, then `torch.randperm(n)[:numPoint]` is drawn per list IN THE GIVEN ORDER from the CPU default generator
+    (the order MAC-VO consumes it: keypoints, then mapping points — Odometry/MACVO.py:197,315)."""
     lib = load_library()
-    dev = cand.idx.device
-    cand.host[0:1].copy_(cand.n, non_blocking=True)
-    cand.host[1:2].copy_(cand.status, non_blocking=True)
+    for cand, _ in requests:
+        cand.host[0:1].copy_(cand.n, non_blocking=True)
+        cand.host[1:2].copy_(cand.status, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    n = int(cand.host[0])       # host[1] = 1 flags "no NMS survivor" (then n == 0, like the reference: median([]) = nan)
-    perm = torch.randperm(n)[:num_point]
-    k = perm.numel()
-    out = torch.empty((k, 2), dtype=torch.int64, device=dev)
-    if k:
-        if k > cand.perm_host.numel():                               # (pinning per call costs ~0.1 ms: keep a buffer)
-            cand.perm_host = torch.empty((k,), dtype=torch.int64).pin_memory()
-        cand.perm_host[:k].copy_(perm)
-        perm_d = cand.perm_host[:k].to(dev, non_blocking=True)
-        _check(lib.macvo_gather_pixels(cand.idx.data_ptr(), perm_d.data_ptr(), k, cand.w, out.data_ptr(), _stream()),
-               "macvo_gather_pixels")
-        LAUNCHES[0] += 1
-    return out
+    outs = []
+    for cand, num_point in requests:
+        dev = cand.idx.device
+        n = int(cand.host[0])   # host[1] = 1 flags "no NMS survivor" (then n == 0, like the reference: median([]) = nan)
+        perm = torch.randperm(n)[:num_point]
+        k = perm.numel()
+        out = torch.empty((k, 2), dtype=torch.int64, device=dev)
+        if k:
+            if k > cand.perm_host.numel():                           # (pinning per call costs ~0.1 ms: keep a buffer)
+                cand.perm_host = torch.empty((k,), dtype=torch.int64).pin_memory()
+            cand.perm_host[:k].copy_(perm)
+            perm_d = cand.perm_host[:k].to(dev, non_blocking=True)
+            _check(lib.macvo_gather_pixels(cand.idx.data_ptr(), perm_d.data_ptr(), k, cand.w, out.data_ptr(), _stream()),
+                   "macvo_gather_pixels")
+            LAUNCHES[0] += 1
+        outs.append(out)
+    return outs
 
 
 # ------------------------------------------------------------------------------------------------
@@ -395,8 +409,14 @@ def retrieve_pixels(pixel_uv: Tensor, scalar_map: Tensor) -> Tensor:
 # ------------------------------------------------------------------------------------------------
 def match_covariance(kp: Tensor, depth_map: Tensor, flow_cov: Tensor | None, fx: float, fy: float, cx: float,
                      cy: float, kernel_size: int = 31, min_flow_cov: float = 0.25, min_depth_cov: float = 0.05,
-                     match_cov_default: float = 0.25, want_point: bool = False):
-    """-> (cov (K,3,3) float64 on the device, point (K,3) fp32 or None, status int32 tensor)."""
+                     match_cov_default: float = 0.25, want_point: bool = False, depth_cov: Tensor | None = None,
+                     out_cov: Tensor | None = None):
+    """-> (cov (K,3,3) float64 on the device, point (K,3) fp32 or None, status int32 tensor).
+
+    flow_cov: (K,3) fp32 CUDA tensor with ANY strides (MAC-VO passes the transposed view of a (3,K) gather,
+    Odometry/MACVO.py:231-232); its first two columns are clamped in place in the caller's storage like the reference.
+    depth_cov: (K,) per-keypoint depth variance, only used when flow_cov is None (Project2to3.py:163-171).
+    out_cov: optional preallocated (K,3,3) float64 CUDA view to fill (e.g. a slice of a packed buffer)."""
     lib = load_library()
     dm = _dev(depth_map, torch.float32, "match_covariance depth")
     if kp.dtype not in (torch.int64, torch.float32):
@@ -404,16 +424,30 @@ def match_covariance(kp: Tensor, depth_map: Tensor, flow_cov: Tensor | None, fx:
     kpd = _dev(kp, kp.dtype, "match_covariance kp")
     K = kpd.shape[0]
     H, W = dm.shape[-2:]
-    fc = None
+    fc, rs, cs = None, 0, 0
     if flow_cov is not None:
-        if not (flow_cov.is_cuda and flow_cov.dtype == torch.float32 and flow_cov.is_contiguous()):
-            raise MacvoB200Error("match_covariance: flow_cov must be a contiguous fp32 CUDA tensor (clamped in place)")
+        if not (flow_cov.is_cuda and flow_cov.dtype == torch.float32 and flow_cov.dim() == 2 and flow_cov.shape == (K, 3)):
+            raise MacvoB200Error("match_covariance: flow_cov must be a (K,3) fp32 CUDA tensor (clamped in place)")
         fc = flow_cov
-    cov = torch.empty((K, 3, 3), dtype=torch.float64, device=dm.device)
+        rs, cs = (fc.stride(0), fc.stride(1)) if K > 0 else (3, 1)
+        if K > 0 and (rs == 0 or cs == 0):
+            raise MacvoB200Error("match_covariance: flow_cov is an expanded (stride-0) view; the in-place clamp needs real storage")
+    dv = None
+    if fc is None and depth_cov is not None:
+        dv = _dev(depth_cov.reshape(-1), torch.float32, "match_covariance depth_cov")
+        if dv.numel() != K:
+            raise MacvoB200Error("match_covariance: depth_cov must have one value per keypoint")
+    if out_cov is None:
+        cov = torch.empty((K, 3, 3), dtype=torch.float64, device=dm.device)
+    else:
+        cov = out_cov
+        if not (cov.is_cuda and cov.dtype == torch.float64 and cov.is_contiguous() and cov.shape == (K, 3, 3)):
+            raise MacvoB200Error("match_covariance: out_cov must be a contiguous (K,3,3) float64 CUDA tensor")
     pt = torch.empty((K, 3), dtype=torch.float32, device=dm.device) if want_point else None
     status = torch.zeros((1,), dtype=torch.int32, device=dm.device)
     rc = lib.macvo_match_covariance(kpd.data_ptr(), int(kpd.dtype == torch.int64), K, dm.data_ptr(), H, W,
-                                    fc.data_ptr() if fc is not None else None, fx, fy, cx, cy, kernel_size,
+                                    fc.data_ptr() if fc is not None else None, rs, cs,
+                                    dv.data_ptr() if dv is not None else None, fx, fy, cx, cy, kernel_size,
                                     min_flow_cov, min_depth_cov, match_cov_default, cov.data_ptr(),
                                     pt.data_ptr() if pt is not None else None, status.data_ptr(), _stream())
     _check(rc, "macvo_match_covariance")
@@ -459,6 +493,86 @@ def pgo_accumulate(pos_Tw: Tensor, kp2_uv: Tensor, kp2_disp: Tensor, uv_cov: Ten
     _check(rc, "macvo_pgo_accumulate")
     LAUNCHES[0] += 1
     return acc
+
+
+# ------------------------------------------------------------------------------------------------
+# (f3) device-side observation building / sanity filter / MatchObs packing + counted PGO solve
+# ------------------------------------------------------------------------------------------------
+class ObservationBuffers:
+    """Device + pinned-host buffers of one frame's observations (layout: include/macvo_b200.h, macvo_observe_pack)."""
+
+    def __init__(self, capacity: int, device):
+        lib = load_library()
+        self.capacity = int(capacity)
+        self.n_doubles = int(lib.macvo_observe_packed_doubles(self.capacity))
+        self.packed = torch.zeros((self.n_doubles,), dtype=torch.float64, device=device)
+        self.n_obs = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.ws_bytes = int(lib.macvo_observe_workspace_bytes(self.capacity))
+        self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=device)
+        self.host = torch.zeros((self.n_doubles,), dtype=torch.float64).pin_memory()
+        self.ready = torch.cuda.Event()
+
+    def section(self, name: str, host: bool = False) -> Tensor:
+        c = self.capacity
+        lo, hi, shape = {"pos_Tw": (0, 3 * c, (c, 3)), "pixel2_uv": (3 * c, 5 * c, (c, 2)), "pixel2_disp": (5 * c, 6 * c, (c,)),
+                         "pixel2_uv_cov": (6 * c, 9 * c, (c, 3)), "pixel2_disp_cov": (9 * c, 10 * c, (c,)),
+                         "obs1_covTc": (10 * c, 19 * c, (c, 3, 3)), "obs2_covTc": (19 * c, 28 * c, (c, 3, 3)),
+                         "pixel1_uv": (28 * c, 30 * c, (c, 2)), "pixel1_d": (30 * c, 31 * c, (c,)),
+                         "header": (31 * c, 31 * c + 4, (4,))}[name]
+        return (self.host if host else self.packed)[lo:hi].view(shape)
+
+    def download_async(self) -> None:
+        """ONE asynchronous device->host copy of the whole frame's observations; `self.ready` fires when it landed."""
+        self.host.copy_(self.packed, non_blocking=True)
+        self.ready.record()
+
+
+def observe_pack(buf: ObservationBuffers, kp0_uv: Tensor, flow: Tensor, match_cov: Tensor, depth0: Tensor, depth1: Tensor,
+                 disparity1: Tensor, disp_unc1: Tensor, edge_width: int, intr0, intr1, prev_pose: Tensor, next_pose: Tensor,
+                 kernel_size: int = 31, min_flow_cov: float = 0.25, min_depth_cov: float = 0.05,
+                 match_cov_default: float = 0.25) -> None:
+    """Odometry/MACVO.py:198-283 for the two-frame graph as two launches (csrc/observe.cu); everything stays on the device."""
+    lib = load_library()
+    kp = _dev(kp0_uv, torch.int64, "observe_pack kp0_uv")
+    k = kp.shape[0]
+    fl = _dev(flow, torch.float32, "observe_pack flow")
+    mc = _dev(match_cov, torch.float32, "observe_pack match_cov")
+    maps = [_dev(t, torch.float32, "observe_pack map") for t in (depth0, depth1, disparity1, disp_unc1)]
+    H, W = fl.shape[-2:]
+    if fl.numel() != 2 * H * W or mc.numel() != 3 * H * W or any(m.numel() != H * W for m in maps):
+        raise MacvoB200Error("observe_pack: expects flow (1,2,H,W), match_cov (1,3,H,W) and (1,1,H,W) maps")
+    if k > buf.capacity:
+        raise MacvoB200Error(f"observe_pack: {k} keypoints exceed the buffer capacity {buf.capacity}")
+    pp = _dev(prev_pose, torch.float64, "observe_pack prev_pose")
+    if not (next_pose.is_cuda and next_pose.dtype == torch.float64 and next_pose.is_contiguous() and next_pose.numel() == 7):
+        raise MacvoB200Error("observe_pack: next_pose must be a contiguous (7,) float64 CUDA tensor")
+    i0 = (C.c_float * 4)(*[float(v) for v in intr0])
+    i1 = (C.c_float * 4)(*[float(v) for v in intr1])
+    buf.status.zero_()
+    rc = lib.macvo_observe_pack(kp.data_ptr() if k else None, k, buf.capacity, fl.data_ptr(), mc.data_ptr(),
+                                *(m.data_ptr() for m in maps), H, W, int(edge_width), C.cast(i0, C.c_void_p),
+                                C.cast(i1, C.c_void_p), int(kernel_size), float(min_flow_cov), float(min_depth_cov),
+                                float(match_cov_default), pp.data_ptr(), next_pose.data_ptr(), buf.packed.data_ptr(),
+                                buf.n_obs.data_ptr(), buf.status.data_ptr(), buf.ws.data_ptr(), buf.ws_bytes, _stream())
+    _check(rc, "macvo_observe_pack")
+    LAUNCHES[0] += 2
+
+
+def pgo_solve_counted(buf: ObservationBuffers, intr: tuple[float, float, float, float, float], pose_io: Tensor,
+                      stats: Tensor, min_k: int = 10, cluster: int = 0, **kw) -> None:
+    """LM solve on the packed observation arrays, block count read from buf.n_obs on the device; pose_io (7,) float64
+    CUDA holds the initial pose and receives the result (untouched when fewer than min_k observations survive)."""
+    lib = load_library()
+    c = buf.capacity
+    base = buf.packed.data_ptr()
+    intr_c = (C.c_double * 5)(*[float(v) for v in intr])
+    prm = _pgo_params(cluster=cluster, **kw)       # 0: cluster size chosen from the capacity
+    rc = lib.macvo_pgo_solve_counted(base, base + 8 * 3 * c, base + 8 * 5 * c, base + 8 * 6 * c, base + 8 * 9 * c, c,
+                                     buf.n_obs.data_ptr(), int(min_k), C.cast(intr_c, C.c_void_p), pose_io.data_ptr(),
+                                     C.byref(prm), stats.data_ptr(), _stream())
+    _check(rc, "macvo_pgo_solve_counted")
+    LAUNCHES[0] += 1
 
 
 # ---- frontend "next" rows: memory-bound perceiver layers (csrc/nn_kernels.cu) ------------------------------

@@ -142,3 +142,133 @@ class TwoFrameOdometry:
         """Synchronise on the last optimisation and return all poses (F, 7)."""
         self._write_back()
         return torch.stack(self.poses)
+
+
+class FusedTwoFrameOdometry:
+    """Same per-frame data flow as `TwoFrameOdometry`, with everything between the frontend and the optimiser result kept
+    on the device: observation building, CovarianceSanityFilter and MatchObs packing are two launches
+    (`ops.observe_pack`, csrc/observe.cu), the LM kernel reads the survivor count on the device
+    (`ops.pgo_solve_counted`), the optimised pose of frame t is consumed by frame t+1 without visiting the host, and a
+    frame's observations / mapping points / pose travel to pinned host memory in asynchronous copies.
+
+    Host synchronisations per frame: ONE — the two candidate counts that `torch.randperm` needs on the CPU default
+    generator (kept for bit-exact keypoints; drawn in MAC-VO's order: keypoints, then mapping points). `TwoFrameOdometry`
+    with the plugin-API calls has >= 7 (candidate counts x2, boolean indexing x2, covariance `.cpu()` x3).
+
+    Requires the B200 plugins (uses their device buffers); keypoints and poses equal `TwoFrameOdometry`'s
+    (tests/test_gpu_pipeline.py::test_fused_tail_matches_plugin_path)."""
+
+    def __init__(self, frontend, kp_selector, cov_model, optimizer, num_point: int = 200, edgewidth: int = 32,
+                 match_cov_default: float = 0.25, mapping: bool = True, map_selector=None, min_num_point: int = 10,
+                 num_map_point: int = 2000, keep_debug: bool = False):
+        from . import ops
+        self.ops = ops
+        self.frontend, self.kp_selector, self.cov_model, self.optimizer = frontend, kp_selector, cov_model, optimizer
+        self.map_selector = map_selector
+        self.num_point, self.edgewidth, self.match_cov_default = num_point, edgewidth, match_cov_default
+        self.mapping, self.min_num_point, self.num_map_point = mapping and map_selector is not None, min_num_point, num_map_point
+        self.keep_debug = keep_debug
+        self.device = kp_selector.device
+        cc = cov_model.config
+        self.cov_args = dict(kernel_size=cc.kernel_size, min_flow_cov=cc.min_flow_cov, min_depth_cov=cc.min_depth_cov)
+        self.cluster = int(getattr(optimizer, "context", {}).get("cluster", 0)) if hasattr(optimizer, "context") else 0
+        self.obs = [ops.ObservationBuffers(num_point, self.device) for _ in range(2)]      # double buffered
+        self.stats = [torch.zeros((8,), dtype=torch.float64, device=self.device) for _ in range(2)]
+        if self.mapping:
+            self.map_cov = [torch.empty((num_map_point, 3, 3), dtype=torch.float64, device=self.device) for _ in range(2)]
+            self.map_cov_host = [torch.empty((num_map_point, 3, 3), dtype=torch.float64).pin_memory() for _ in range(2)]
+            self.map_pt_host = [torch.empty((num_map_point, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.pose_dev: list[torch.Tensor] = []          # (7,) float64 per frame, on the device
+        self.pose_host = torch.zeros((2, 7), dtype=torch.float64).pin_memory()
+        self.pose_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.n_map = [0, 0]
+        self.frame_no = 0
+        self.prev = None
+        self.last: FrameResult | None = None
+
+    def initialize(self, frame0) -> None:
+        depth0 = self.frontend.estimate_depth(frame0)
+        self.prev = (frame0, depth0)
+        self.pose_dev = [torch.tensor([0., 0., 0., 0., 0., 0., 1.], dtype=torch.float64, device=self.device)]
+
+    @staticmethod
+    def _intr(frame) -> tuple[float, float, float, float]:
+        K = frame.frame_K if hasattr(frame, "frame_K") else frame.K[0]
+        return float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+
+    @torch.inference_mode()
+    def run_pair(self, frame1) -> FrameResult:
+        ops = self.ops
+        frame0, depth0 = self.prev
+        slot = self.frame_no & 1
+        depth1, match01 = self.frontend.estimate_pair(frame0, frame1)
+        # selection kernels for keypoints AND mapping points first, then a single synchronisation for both counts
+        reqs = [(self.kp_selector.enqueue_candidates(match01), self.num_point)]
+        if self.mapping:
+            reqs.append((self.map_selector.enqueue_candidates(depth0), self.num_map_point))
+        picks = ops.sample_candidates_many(reqs)
+        kp0_uv = picks[0]
+        obs, stats = self.obs[slot], self.stats[slot]
+        next_pose = torch.empty((7,), dtype=torch.float64, device=self.device)
+        i0, i1 = self._intr(frame0), self._intr(frame1)
+        ops.observe_pack(obs, kp0_uv, match01.flow, match01.cov, depth0.depth, depth1.depth, depth1.disparity,
+                         depth1.disparity_uncertainty, self.edgewidth, i0, i1, self.pose_dev[-1], next_pose,
+                         match_cov_default=self.match_cov_default, **self.cov_args)
+        bl = float(torch.as_tensor(frame1.frame_baseline, dtype=torch.float32).double().reshape(-1)[0])
+        stats.zero_()
+        ops.pgo_solve_counted(obs, (*i1, bl), next_pose, stats, min_k=self.min_num_point, cluster=self.cluster)
+        self.pose_dev.append(next_pose)
+        n_map = 0
+        if self.mapping:
+            map0_uv = picks[1]
+            n_map = map0_uv.size(0)
+            if n_map:   # constant quantisation covariance for manually selected pixels, clamped like any flow_cov
+                sig = max(float(torch.tensor(self.match_cov_default, dtype=torch.float32)),
+                          float(torch.tensor(self.cov_args["min_flow_cov"], dtype=torch.float32) ** 2))
+                _, pt, _ = ops.match_covariance(map0_uv, depth0.depth, None, *i0, kernel_size=self.cov_args["kernel_size"],
+                                                min_flow_cov=self.cov_args["min_flow_cov"],
+                                                min_depth_cov=self.cov_args["min_depth_cov"], match_cov_default=sig,
+                                                want_point=True, out_cov=self.map_cov[slot][:n_map])
+                self.map_cov_host[slot][:n_map].copy_(self.map_cov[slot][:n_map], non_blocking=True)
+                self.map_pt_host[slot][:n_map].copy_(pt, non_blocking=True)
+        self.n_map[slot] = n_map
+        # one asynchronous copy ships the frame's MatchObs columns; the pose follows; nothing waits here
+        obs.download_async()
+        self.pose_host[slot].copy_(next_pose, non_blocking=True)
+        self.pose_ready[slot].record()
+        self.prev = (frame1, depth1)
+        self.frame_no += 1
+        res = FrameResult(num_kp=-1, num_obs=-1, pose_init=None, optimizer_output=None, map_points=n_map)
+        if self.keep_debug:
+            res.kp0_uv = kp0_uv
+            res.extras = {"depth1": depth1, "match01": match01, "slot": slot}
+        self.last = res
+        return res
+
+    def latest_pose(self) -> torch.Tensor:
+        """Optimised pose of the newest frame on the HOST (float64 (7,)); waits for that frame's pose copy only."""
+        slot = (self.frame_no - 1) & 1
+        self.pose_ready[slot].synchronize()
+        return self.pose_host[slot].clone()
+
+    def observations(self) -> dict:
+        """The newest frame's packed observations from pinned host memory (waits for its copy)."""
+        slot = (self.frame_no - 1) & 1
+        obs = self.obs[slot]
+        obs.ready.synchronize()
+        hdr = obs.section("header", host=True)
+        n = int(hdr[0])
+        out = {k: obs.section(k, host=True)[:n].clone() for k in
+               ("pos_Tw", "pixel2_uv", "pixel2_disp", "pixel2_uv_cov", "pixel2_disp_cov", "obs1_covTc", "obs2_covTc",
+                "pixel1_uv", "pixel1_d")}
+        out.update(num_obs=n, num_kp=int(hdr[1]), num_selected=int(hdr[2]), status=int(hdr[3]))
+        if self.mapping:
+            self.pose_ready[slot].synchronize()
+            m = self.n_map[slot]
+            out.update(map_cov=self.map_cov_host[slot][:m].clone(), map_pos_Tc=self.map_pt_host[slot][:m].clone())
+        return out
+
+    def finish(self) -> torch.Tensor:
+        """All poses (F, 7) float32 like `TwoFrameOdometry.finish` (the map stores fp32 poses)."""
+        torch.cuda.current_stream().synchronize()
+        return torch.stack([p.cpu().float() for p in self.pose_dev])

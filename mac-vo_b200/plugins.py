@@ -46,13 +46,6 @@ else:
 _DTYPES = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
 
 
-def _version(t: torch.Tensor) -> int:
-    try:
-        return t._version
-    except RuntimeError:          # inference tensors do not track a version counter
-        return -1
-
-
 def _require_cuda(device: str, who: str) -> torch.device:
     if "cuda" not in str(device):
         raise ValueError(f"{who}: the B200 plugins only run on a CUDA device (got device={device!r}); "
@@ -115,7 +108,9 @@ class B200_FlowFormerCovFrontend(IFrontend):
         match = IMatcher.Output(flow=c(d["flow"]), cov=c(d["flow_cov"]), mask=None)
         # let the selector plugin reuse the fused scores instead of re-reading the covariance map
         self._score.generation += 1
-        match._b200_score = (self._score, self._score.generation, match.cov.data_ptr(), _version(match.cov))  # type: ignore[attr-defined]
+        # (the token is keyed by buffer generation + map address; the covariance map must not be edited in place between
+        # estimate_pair and select_point — inference tensors carry no version counter that could detect it)
+        match._b200_score = (self._score, self._score.generation, match.cov.data_ptr())  # type: ignore[attr-defined]
         return depth, match
 
     @torch.inference_mode()
@@ -142,10 +137,16 @@ class B200_FlowFormerCovFrontend(IFrontend):
             shape = (2,) + tuple(frame_t2.imageL.shape[1:])
             assert shape == st["shape"], f"Input shape mismatch for CUDAGraph replay: {shape} != {st['shape']}"
             assert bl_fx == st["bl_fx"], "camera baseline * fx changed since the CUDA graph was captured"
+            # each image crosses PCIe once: t1.L is last call's t2.L and already sits in A[0] (device->device move), and
+            # B[1] = t2.L is copied from A[0] after the upload
+            if st.get("last_t2L") is frame_t1.imageL:
+                st["A"][1:2].copy_(st["A"][0:1])
+            else:
+                st["A"][1:2].copy_(frame_t1.imageL, non_blocking=True)
             st["A"][0:1].copy_(frame_t2.imageL, non_blocking=True)
-            st["A"][1:2].copy_(frame_t1.imageL, non_blocking=True)
             st["B"][0:1].copy_(frame_t2.imageR, non_blocking=True)
-            st["B"][1:2].copy_(frame_t2.imageL, non_blocking=True)
+            st["B"][1:2].copy_(st["A"][0:1])
+            st["last_t2L"] = frame_t2.imageL
             self._graph.replay()
             ops.LAUNCHES[0] += st["launches"]
             return self._outputs(st["out"], clone=True)
@@ -171,7 +172,8 @@ class B200_FlowFormerCovFrontend(IFrontend):
             out = self._run(sA, sB, bl_fx)
         self._graph = graph
         self._static = {"A": sA, "B": sB, "out": out, "shape": tuple(input_A.shape), "bl_fx": bl_fx,
-                        "launches": ops.LAUNCHES[0] - n0}     # macvo_b200 kernels inside one replay
+                        "launches": ops.LAUNCHES[0] - n0,     # macvo_b200 kernels inside one replay
+                        "last_t2L": frame_t2.imageL}
         graph.replay()                             # (the reference returns its warm-up result here)
         return self._outputs(out, clone=True)
 
@@ -188,15 +190,20 @@ class B200_FlowFormerCovFrontend(IFrontend):
 
     @classmethod
     def is_valid_config(cls, config: SimpleNamespace | None) -> None:
-        cls._enforce_config_spec(config, {
+        spec = {
             "weight": lambda s: isinstance(s, str),
             "device": lambda s: isinstance(s, str) and "cuda" in s,
             "dec_dtype": lambda b: b in ("fp32", "fp16", "bf16"),
             "enc_dtype": lambda b: b in ("fp32", "fp16", "bf16"),
             "enforce_positive_disparity": lambda b: isinstance(b, bool),
             "decoder_depth": lambda v: isinstance(v, int),
-            "cuda_graph": lambda b: isinstance(b, bool),
-        })
+        }
+        # optional keys (the reference class has neither): cuda_graph defaults to True, score_kernel_size to 7
+        optional = {"cuda_graph": lambda b: isinstance(b, bool),
+                    "score_kernel_size": lambda k: isinstance(k, int) and k % 2 == 1 and 1 <= k <= 15}
+        if config is not None:
+            spec.update({k: v for k, v in optional.items() if hasattr(config, k)})
+        cls._enforce_config_spec(config, spec)
 
 
 # ================================================================================================
@@ -213,7 +220,8 @@ class B200_CovAwareSelector_NoDepth(IKeypointSelector):
         self._cand: ops.CandidateList | None = None
 
     @torch.inference_mode()
-    def select_point(self, frame, numPoint: int, depth0_est, depth1_est, match_est) -> torch.Tensor:
+    def enqueue_candidates(self, match_est) -> "ops.CandidateList":
+        """Kernels only (median threshold, flags, ordered compaction) — no host synchronisation."""
         if match_est is None or match_est.cov is None:
             raise ValueError("B200_CovAwareSelector_NoDepth needs match_est.cov (the reference falls back to a grid "
                              "selector here; compose it with GridSelector in the YAML if that is wanted)")
@@ -222,8 +230,8 @@ class B200_CovAwareSelector_NoDepth(IKeypointSelector):
         token = getattr(match_est, "_b200_score", None)
         score = None
         if token is not None:                              # scores fused into the frontend's post-processing pass
-            sc, gen, ptr, ver = token
-            if (sc.generation == gen and ptr == cov.data_ptr() and ver == _version(cov)
+            sc, gen, ptr = token
+            if (sc.generation == gen and ptr == cov.data_ptr()
                     and sc.ksize == self.config.kernel_size and (sc.h, sc.w) == (H, W)):
                 score = sc
         if score is None:                                  # foreign frontend / modified map: score it ourselves
@@ -234,7 +242,11 @@ class B200_CovAwareSelector_NoDepth(IKeypointSelector):
         if self._cand is None or self._cand.idx.numel() != H * W:
             self._cand = ops.CandidateList(H, W, self.device)
         ops.select_candidates(score, self.config.mask_width, self.config.max_match_cov, match_est.mask, self._cand)
-        return ops.sample_candidates(self._cand, numPoint)
+        return self._cand
+
+    @torch.inference_mode()
+    def select_point(self, frame, numPoint: int, depth0_est, depth1_est, match_est) -> torch.Tensor:
+        return ops.sample_candidates(self.enqueue_candidates(match_est), numPoint)
 
     @classmethod
     def is_valid_config(cls, config: SimpleNamespace | None) -> None:
@@ -295,14 +307,18 @@ class B200_MappingPointSelector(IKeypointSelector):
         self._cand: ops.CandidateList | None = None
 
     @torch.inference_mode()
-    def select_point(self, frame, numPoint: int, depth0_est, depth1_est, match_est) -> torch.Tensor:
+    def enqueue_candidates(self, depth0_est) -> "ops.CandidateList":
         assert depth0_est.cov is not None
         H, W = depth0_est.depth.shape[-2:]
         if self._cand is None or self._cand.idx.numel() != H * W or self._cand.idx.device != depth0_est.depth.device:
             self._cand = ops.CandidateList(H, W, depth0_est.depth.device)
         ops.select_mapping_candidates(depth0_est.depth, depth0_est.cov, self.config.mask_width, self.config.max_depth,
                                       self.config.max_depth_cov, self._cand)
-        return ops.sample_candidates(self._cand, numPoint)
+        return self._cand
+
+    @torch.inference_mode()
+    def select_point(self, frame, numPoint: int, depth0_est, depth1_est, match_est) -> torch.Tensor:
+        return ops.sample_candidates(self.enqueue_candidates(depth0_est), numPoint)
 
     @classmethod
     def is_valid_config(cls, config: SimpleNamespace | None) -> None:
@@ -328,15 +344,24 @@ class B200_MatchCovariance(ICovariance2to3):
         self._status_host: torch.Tensor | None = None
 
     def estimate_device(self, frame, kp, depth_est, depth_cov, flow_cov, want_point: bool = False):
-        """Device-resident variant: (cov (K,3,3) fp64 CUDA, point (K,3) fp32 CUDA or None)."""
+        """Device-resident variant: (cov (K,3,3) fp64 CUDA, point (K,3) fp32 CUDA or None).
+
+        flow_cov may be ANY (K,3) view — Odometry/MACVO.py:231-232 passes `retrieve_pixels(kp, match.cov).T`, a
+        transposed view of a (3,K) tensor — the kernel addresses it through its strides, so the reference's in-place
+        clamp (Project2to3.py:130-133) lands in the caller's storage (that tensor later becomes `pixel2_uv_cov`).
+        A tensor on another device / of another dtype is staged and copied back after the clamp."""
         fc = flow_cov
-        if fc is not None and not (fc.is_cuda and fc.dtype == torch.float32 and fc.is_contiguous()):
-            raise ValueError("flow_cov must be a contiguous fp32 CUDA tensor (it is clamped in place, like the reference)")
+        staged = None
+        if fc is not None and not (fc.is_cuda and fc.device == self.device and fc.dtype == torch.float32):
+            staged = fc.to(device=self.device, dtype=torch.float32).contiguous()
+            fc = staged
         cov, pt, status = ops.match_covariance(
             kp.to(self.device), depth_est.depth, fc, frame.fx, frame.fy, frame.cx, frame.cy,
             kernel_size=self.config.kernel_size, min_flow_cov=self.config.min_flow_cov,
             min_depth_cov=self.config.min_depth_cov, match_cov_default=self.config.match_cov_default,
-            want_point=want_point)
+            want_point=want_point, depth_cov=depth_cov.to(self.device) if (fc is None and depth_cov is not None) else None)
+        if staged is not None:
+            flow_cov.copy_(staged)
         self.last_status = status
         return cov, pt
 

@@ -139,11 +139,21 @@ def test_dense_postproc_bit_exact(ops, golden, epd):
         a, b = out[k].cpu(), g[k]
         assert a.shape == b.shape and a.dtype == torch.float32, k
         if not torch.equal(a.nan_to_num(123.0), b.nan_to_num(123.0)):
+            # round-1 flake (2 of ~60 fresh-process runs): classify the next occurrence — is it the read-back, the kernel
+            # run, the uploaded inputs, or the host-side input generation that differs?
             bad = a.nan_to_num(123.0) != b.nan_to_num(123.0)
             idx = bad.nonzero()[:4].tolist()
-            raise AssertionError(f"{k}: {int(bad.sum())} mismatches at {idx}: got {a[bad][:4].tolist()} want {b[bad][:4].tolist()}; "
-                                 f"inputs flow {flow[0, 0].flatten()[:2].tolist()} cov sum {float(cov.double().sum())!r} "
-                                 f"threads {torch.get_num_threads()}")
+            again = out[k].cpu()
+            rerun = ops.dense_postproc(flow.to(DEV), cov.to(DEV), 0.25 * 320.0, bool(epd))[k].cpu()
+            import hashlib
+            sha = lambda t: hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()[:12]
+            raise AssertionError(
+                f"{k}: {int(bad.sum())} mismatches at {idx}: got {a[bad][:4].tolist()} want {b[bad][:4].tolist()}; "
+                f"second read-back equal to first: {torch.equal(again.nan_to_num(123.0), a.nan_to_num(123.0))}; "
+                f"re-run equals golden: {torch.equal(rerun.nan_to_num(123.0), b.nan_to_num(123.0))}; "
+                f"inputs sha flow {sha(flow)} cov {sha(cov)} (build container: b00239533f11 / c7c1072af39e); "
+                f"upload round trip exact: {torch.equal(flow.to(DEV).cpu(), flow) and torch.equal(cov.to(DEV).cpu(), cov)}; "
+                f"cpu capability {torch.backends.cpu.get_cpu_capability()} threads {torch.get_num_threads()}")
     if epd:
         assert out["depth_mask"].dtype == torch.bool and torch.equal(out["depth_mask"].cpu(), g["depth_mask"])
     else:
@@ -328,3 +338,41 @@ def test_corr_build_channels_last_inputs_bit_identical(ops):
     c = ops.corr_build(f1.to(DEV).contiguous(memory_format=torch.channels_last),
                        f2.to(DEV).contiguous(memory_format=torch.channels_last), mode=ops.CORR_TC_1XF16)
     assert torch.equal(c, ops.corr_build(f1.to(DEV), f2.to(DEV), mode=ops.CORR_TC_1XF16))
+
+
+def test_pgo_rank_deficient_blocks_take_pseudo_inverse_weight(ops):
+    """The reference weights every block with torch.pinverse(cov) (Graphs.py:139-148): a zero disparity variance or a
+    singular 2x2 pixel covariance must get its Moore-Penrose weight (finite pose), not inf / NaN, and be flagged."""
+    c = cases.pgo_inputs(64, 6)
+    c["disp_cov"][3] = 0.0
+    c["uv_cov"][5] = torch.tensor([1.0, 1.0, 1.0])          # det = 0, rank 1
+    c["uv_cov"][9] = torch.tensor([0.0, 0.0, 0.0])          # zero block
+    pose, stats = ops.pgo_solve(*_pgo_device_args(c))
+    ref = opgo.lm_solve(cases.pgo_graph(c))                  # oracle: np.linalg.pinv per block
+    assert np.isfinite(pose.cpu().numpy()).all()
+    np.testing.assert_allclose(pose.cpu().numpy(), ref, rtol=1e-8, atol=1e-9)
+    assert stats[7].item() == 1.0
+    c2 = cases.pgo_inputs(64, 6)
+    _, stats2 = ops.pgo_solve(*_pgo_device_args(c2))
+    assert stats2[7].item() == 0.0
+
+
+def test_pgo_solve_counted_reads_block_count_on_device(ops):
+    """macvo_pgo_solve_counted: k = min(*k_dev, capacity) read on the device; fewer than min_k blocks leave the pose alone."""
+    c = cases.pgo_inputs(64, 6)
+    a = _pgo_device_args(c)
+    cap = 96
+    buf = ops.ObservationBuffers(cap, DEV)
+    for name, t in (("pos_Tw", a[0]), ("pixel2_uv", a[1]), ("pixel2_disp", a[2]), ("pixel2_uv_cov", a[3]), ("pixel2_disp_cov", a[4])):
+        buf.section(name)[:64] = t
+    buf.n_obs.fill_(64)
+    pose = a[6].clone()
+    stats = torch.zeros(8, dtype=torch.float64, device=DEV)
+    ops.pgo_solve_counted(buf, a[5], pose, stats, min_k=10)
+    ref, _ = ops.pgo_solve(*a, cluster=1)
+    np.testing.assert_allclose(pose.cpu().numpy(), ref.cpu().numpy(), rtol=1e-12, atol=1e-13)
+    buf.n_obs.fill_(7)
+    pose2 = a[6].clone()
+    stats.zero_()
+    ops.pgo_solve_counted(buf, a[5], pose2, stats, min_k=10)
+    assert torch.equal(pose2, a[6]) and stats[6].item() == 1.0

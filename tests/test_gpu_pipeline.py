@@ -164,3 +164,139 @@ def test_pipeline_on_identical_dense_maps_is_exact(plugins):
                                          (a.extras["depth1"].depth.cpu() - b.extras["depth1"].depth).abs().max().item())
         assert a.num_obs == b.num_obs and a.map_points == b.map_points
     np.testing.assert_allclose(pg.numpy(), pcpu.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def _upload_frontend_cls(P):
+    from oracle import pipeline_cpu as pc
+
+    class UploadFrontend(pc.CpuFrontend):           # CPU network, outputs moved to the GPU as-is
+        def _post(self, flow, cov, frame):
+            d, m = super()._post(flow, cov, frame)
+            up = lambda t: None if t is None else t.to(DEV).contiguous()
+            return (NS(depth=up(d.depth), cov=up(d.cov), disparity=up(d.disparity),
+                       disparity_uncertainty=up(d.disparity_uncertainty), mask=up(d.mask)),
+                    NS(flow=up(m.flow), cov=up(m.cov), mask=None))
+        retrieve_pixels = staticmethod(P.B200_FlowFormerCovFrontend.retrieve_pixels)
+    return UploadFrontend
+
+
+def test_fused_tail_matches_cpu_oracle_chain(plugins):
+    """(f3) device-side observation building + sanity filter + MatchObs packing + counted LM solve
+    (`FusedTwoFrameOdometry`: one host sync per frame) against the CPU oracle chain on IDENTICAL dense maps:
+    keypoints bit-exact, pixel2_uv bit-exact, observation covariances 1e-5 relative, survivor counts equal,
+    poses 1e-6 (north_star: 1e-4)."""
+    from macvo_b200 import synthetic
+    from macvo_b200.flowformer_cov import synthetic_state_dict
+    from macvo_b200.pipeline import FusedTwoFrameOdometry, TwoFrameOdometry
+    from oracle import pipeline_cpu as pc
+    P = plugins
+    _strict_fp32()
+    H, W = 192, 256
+    frames = synthetic.make_sequence(4, H, W)
+    sd = synthetic_state_dict(0)
+    gpu = FusedTwoFrameOdometry(
+        _upload_frontend_cls(P)(sd, decoder_depth=4),
+        P.B200_CovAwareSelector_NoDepth(NS(device=DEV, kernel_size=7, mask_width=32, max_match_cov=100.0)),
+        P.B200_MatchCovariance(NS(device=DEV, kernel_size=31, match_cov_default=0.25, min_depth_cov=0.05, min_flow_cov=0.25)),
+        P.B200_TwoFrame_PGO(NS(graph_type="disp", device=DEV, vectorize=True, parallel=False, autodiff=False)),
+        num_point=64, map_selector=P.B200_MappingPointSelector(NS(max_depth=5.0, max_depth_cov=0.005, mask_width=32)),
+        keep_debug=True)
+    cpu = TwoFrameOdometry(pc.CpuFrontend(sd, decoder_depth=4), pc.CpuSelector(), pc.CpuCovariance(), pc.CpuPGO(),
+                           num_point=64, map_selector=pc.CpuMapSelector(), keep_debug=True)
+    torch.manual_seed(5)
+    gpu.initialize(frames[0])
+    got = []
+    for f in frames[1:]:
+        r = gpu.run_pair(f)
+        got.append((r, gpu.observations(), gpu.latest_pose()))
+    pg = gpu.finish()
+    torch.manual_seed(5)
+    cpu.initialize(frames[0])
+    rc = [cpu.run_pair(f) for f in frames[1:]]
+    pcpu = cpu.finish()
+    for (r, o, pose), b in zip(got, rc):
+        assert o["status"] == 0
+        keep = b.extras["keep"]
+        assert o["num_kp"] == b.num_kp and o["num_obs"] == b.num_obs and r.map_points == b.map_points
+        assert torch.equal(o["pixel1_uv"].long(), b.kp0_uv[keep]), "keypoint indices must be bit-exact"
+        assert torch.equal(o["pixel2_uv"].float(), b.kp1_uv[keep]), "kp1 = kp0 + flow must be bit-exact"
+        for name, ref in (("obs1_covTc", b.extras["pos0_cov"][keep]), ("obs2_covTc", b.extras["pos1_cov"][keep])):
+            rel = ((o[name] - ref).abs() / ref.abs().amax(dim=(1, 2), keepdim=True)).amax()
+            assert rel.item() < 1e-5, (name, rel.item())
+        torch.testing.assert_close(o["pos_Tw"].float(), b.extras["pos_Tw"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(pg.numpy(), pcpu.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_fused_tail_equals_plugin_api_path(plugins):
+    """Same frames through the plugin-API driver (`TwoFrameOdometry`, the calls MACVO.run_pair makes) and the fused
+    device tail, both on the real B200 frontend: identical keypoints, poses within 1e-6."""
+    from macvo_b200 import synthetic
+    from macvo_b200.pipeline import FusedTwoFrameOdometry, TwoFrameOdometry
+    P = plugins
+    _strict_fp32()
+    frames = synthetic.make_sequence(4, 192, 256)
+
+    def build(cls):
+        return cls(_frontend(P, False, 4),
+                   P.B200_CovAwareSelector_NoDepth(NS(device=DEV, kernel_size=7, mask_width=32, max_match_cov=100.0)),
+                   P.B200_MatchCovariance(NS(device=DEV, kernel_size=31, match_cov_default=0.25, min_depth_cov=0.05, min_flow_cov=0.25)),
+                   P.B200_TwoFrame_PGO(NS(graph_type="disp", device=DEV, vectorize=True, parallel=False, autodiff=False)),
+                   num_point=64, map_selector=P.B200_MappingPointSelector(NS(max_depth=5.0, max_depth_cov=0.005, mask_width=32)),
+                   keep_debug=True)
+    a, b = build(TwoFrameOdometry), build(FusedTwoFrameOdometry)
+    _strict_fp32()
+    torch.manual_seed(5)
+    a.initialize(frames[0])
+    ra = [a.run_pair(f) for f in frames[1:]]
+    pa = a.finish()
+    torch.manual_seed(5)
+    b.initialize(frames[0])
+    for f, x in zip(frames[1:], ra):
+        b.run_pair(f)
+        o = b.observations()
+        assert torch.equal(o["pixel1_uv"].long(), x.kp0_uv.cpu()[x.extras["keep"].cpu()])
+        assert o["num_obs"] == x.num_obs
+    pb = b.finish()
+    np.testing.assert_allclose(pb.numpy(), pa.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_match_covariance_accepts_macvo_transposed_view(plugins):
+    """Odometry/MACVO.py:231-243 passes `retrieve_pixels(kp0_uv, match01.cov).T` — a NON-contiguous (K,3) view — and
+    relies on the in-place clamp reaching that storage (it later becomes pixel2_uv_cov)."""
+    from oracle import covariance as ocov
+    P = plugins
+    H, W, K = 160, 224, 96
+    kp, depth, flow_cov = cases.cov_inputs(H, W, K, "float_cov")
+    frame = NS(fx=320.0, fy=320.0, cx=112.0, cy=80.0)
+    model = P.B200_MatchCovariance(NS(device=DEV, kernel_size=31, match_cov_default=0.25, min_depth_cov=0.05, min_flow_cov=0.25))
+    base = flow_cov.T.contiguous().to(DEV)                 # (3,K) like retrieve_pixels returns
+    view = base.T                                          # what MACVO.py hands to estimate()
+    assert not view.is_contiguous()
+    out = model.estimate(frame, kp.to(DEV), NS(depth=depth.to(DEV)), None, view)
+    ref_fc = flow_cov.clone()
+    ref = ocov.match_covariance(kp, depth, ref_fc, 320.0, 320.0, 112.0, 80.0)
+    assert out.device.type == "cpu" and out.dtype == torch.float64
+    rel = ((out - ref).abs() / ref.abs().amax(dim=(1, 2), keepdim=True)).amax().item()
+    assert rel < 1e-5, rel
+    assert torch.equal(base.T.cpu(), ref_fc), "the clamp must land in the caller's (3,K) storage"
+    # a CPU flow_cov (foreign frontend) is staged and written back
+    cpu_fc = flow_cov.clone()
+    out2 = model.estimate(frame, kp.to(DEV), NS(depth=depth.to(DEV)), None, cpu_fc)
+    assert torch.equal(cpu_fc, ref_fc) and torch.equal(out2, out)
+
+
+def test_match_covariance_depth_cov_branch(plugins):
+    """flow_cov None + depth_cov given: `wvar_depth = depth_cov` (Project2to3.py:163-171)."""
+    from oracle import covariance as ocov
+    P = plugins
+    H, W, K = 160, 224, 32
+    kp, depth, _ = cases.cov_inputs(H, W, K, "none")
+    dcov = torch.rand(K, generator=torch.Generator().manual_seed(3)) * 0.5 + 0.01
+    frame = NS(fx=320.0, fy=320.0, cx=112.0, cy=80.0)
+    model = P.B200_MatchCovariance(NS(device=DEV, kernel_size=31, match_cov_default=0.25, min_depth_cov=0.05, min_flow_cov=0.25))
+    out = model.estimate(frame, kp.to(DEV), NS(depth=depth.to(DEV)), dcov.to(DEV), None)
+    ref = ocov.match_covariance(kp, depth, None, 320.0, 320.0, 112.0, 80.0, depth_cov=dcov)
+    rel = ((out - ref).abs() / ref.abs().amax(dim=(1, 2), keepdim=True)).amax().item()
+    assert rel < 1e-5, rel
+    ref_patch = ocov.match_covariance(kp, depth, None, 320.0, 320.0, 112.0, 80.0)
+    assert not torch.allclose(ref, ref_patch), "the branch must actually change the result"
