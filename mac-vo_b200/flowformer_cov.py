@@ -227,6 +227,12 @@ def sine_embed(xy: Tensor, dim: int) -> Tensor:
     return torch.cat([torch.sin(ax), torch.cos(ax), torch.sin(ay), torch.cos(ay)], dim=-1)
 
 
+def _f32(x: Tensor) -> Tensor:
+    """The reference's `.float()` interface casts (flownet.py:28-29, covhead.py:121-131). A float64 run of this class — the
+    ground truth of the parity ladder, tests/golden/make_golden.py — stays float64 end to end."""
+    return x if x.dtype == torch.float64 else x.float()
+
+
 def _sdpa(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
     return F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False)
 
@@ -250,6 +256,11 @@ class FlowFormerCovNet:
         self.corr_fn, self.lookup_fn = corr_fn, lookup_fn
         self.load_state_dict(state_dict)
         self._cache: dict = {}
+        self.taps: dict | None = None      # set to {} to record per-stage intermediates (parity ladder; eager runs only)
+
+    def _tap(self, name: str, t: Tensor) -> None:
+        if self.taps is not None:
+            self.taps.setdefault(name, []).append(t.detach().clone())
 
     # ---- weights -------------------------------------------------------------------------------
     def load_state_dict(self, ckpt: dict[str, Tensor]) -> None:
@@ -265,7 +276,7 @@ class FlowFormerCovNet:
             assert tuple(t.shape) == shape, f"{key}: expected {shape}, got {tuple(t.shape)}"
             if key.startswith("memory_decoder."):
                 dt = self.dec_dtype
-                if key.startswith("memory_decoder.proj."):
+                if key.startswith("memory_decoder.proj.") and dt != torch.float64:
                     dt = torch.float32  # MemoryDecoder.proj is not cast (covhead.py:52-58 omits it)
             else:
                 dt = self.enc_dtype
@@ -580,8 +591,12 @@ class FlowFormerCovNet:
         feats = self.svt(torch.cat([img1, img2], dim=0), "memory_encoder.feat_encoder")
         feats = self._conv(feats, "memory_encoder.channel_convertor")
         B = feats.shape[0] // 2
+        self._tap("feats", feats)
         cost_volume = self.corr_fn(feats[:B], feats[B:]).to(feats.dtype)   # encoder.py:289-290
-        return self.cost_perceiver(cost_volume, context)
+        self._tap("corr_rows", cost_volume.reshape(B, -1, cost_volume.shape[-2] * cost_volume.shape[-1])[:, ::97])
+        out = self.cost_perceiver(cost_volume, context)
+        self._tap("cost_memory", out[0])
+        return out
 
     # ---- decoder (covhead.py:60-140) -----------------------------------------------------------
     def _gru(self, h: Tensor, x: Tensor, p: str) -> Tensor:
@@ -728,12 +743,14 @@ class FlowFormerCovNet:
                 h = cu + "cov_head."
                 t = self._conv(self._conv_relu(cnet, h + "conv1", padding=1), h + "conv2", padding=1)
                 d_cov = self._conv(self._conv_relu(t, h + "conv3", padding=1), h + "conv4", padding=1)
-            coords1 = coords1 + d_flow.float()
-            ccoords1 = ccoords1 + d_cov.float()
+            coords1 = coords1 + _f32(d_flow)
+            ccoords1 = ccoords1 + _f32(d_cov)
+            self._tap("flow_iter", coords1 - coords0)
+            self._tap("cov_iter", ccoords1 - coords0)
         # the reference evaluates both mask heads + upsampling every iteration but (eval mode) returns
         # only the last one (covhead.py:137-140) -> evaluate once
-        up_mask = 0.25 * self._conv(F.relu(self._conv(net, ub + "mask.0", padding=1)), ub + "mask.2").float()
-        cov_mask = (0.25 * self._conv(F.relu(self._conv(cnet, cu + "mask.0", padding=1)), cu + "mask.2")).float()
+        up_mask = _f32(0.25 * self._conv(F.relu(self._conv(net, ub + "mask.0", padding=1)), ub + "mask.2"))
+        cov_mask = _f32(0.25 * self._conv(F.relu(self._conv(cnet, cu + "mask.0", padding=1)), cu + "mask.2"))
         return self.convex_upsample(coords1 - coords0, up_mask), self.convex_upsample(ccoords1 - coords0, cov_mask)
 
     # ---- top level (flownet.py:18-44) -----------------------------------------------------------
@@ -758,9 +775,12 @@ class FlowFormerCovNet:
             context.record_stream(main)
         else:
             context = self.svt(image1, "context_encoder")
+        if self.taps is not None:
+            self._join_context()
+            self._tap("context", context)
         cost_memory, cost_maps = self.memory_encoder(image1, image2, context)
         self._join_context()
-        return self.memory_decoder(cost_memory, context.float(), cost_maps.float())
+        return self.memory_decoder(cost_memory, _f32(context), _f32(cost_maps))
 
     def _join_context(self) -> None:
         if getattr(self, "_ctx_join", None) is not None:

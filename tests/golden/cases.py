@@ -193,3 +193,29 @@ def pgo_graph(c: dict):
         fx=float(K[0, 0]), fy=float(K[1, 1]), cx=float(K[0, 2]), cy=float(K[1, 2]),
         baseline=float(torch.tensor([c["baseline"]]).double().item()),
         init_pose=c["init_pose"].double().numpy())
+
+
+# ---- 640x480 / depth-12 network parity ladder (BASELINE configs[1] shape) -------------------------------------------
+CFGA = (480, 640)
+
+
+def cfgA_inputs() -> tuple[Tensor, Tensor]:
+    """the `estimate_pair` batch of the bench sequence's first step: [t2.L, t1.L] vs [t2.R, t2.L] (Frontend.py:284-285)"""
+    from macvo_b200 import synthetic
+    fr = synthetic.make_sequence(2, *CFGA)
+    return torch.cat([fr[1].imageL, fr[0].imageL]), torch.cat([fr[1].imageR, fr[1].imageL])
+
+
+def cfgA_sample(name: str, t: Tensor) -> Tensor:
+    """fixed strided samples of the per-stage tensors (keeps the fixture < 2 MB; same indices on both sides)"""
+    if name in ("flow", "cov"):                 # (2,2,480,640) full-resolution outputs: stride 5, phase 2 (all 8x8 phases hit)
+        return t[..., 2::5, 2::5]
+    if name in ("feats", "context"):            # (B,256,60,80)
+        return t[:, ::8, ::4, ::5]
+    if name == "corr_rows":                     # (B, N/97, N) rows already strided by the tap
+        return t[:, ::5, ::7]
+    if name == "cost_memory":                   # (B*N, 8, 128)
+        return t[::37, :, ::4]
+    if name in ("flow_iter", "cov_iter"):       # (2,2,60,80) per iteration
+        return t[..., ::2, ::2]
+    raise KeyError(name)
