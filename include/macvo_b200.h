@@ -51,6 +51,10 @@ const char* macvo_b200_version(void);
 #define MACVO_CORR_SIMT 0
 #define MACVO_CORR_TC_3XF16 1
 #define MACVO_CORR_TC_1XF16 2
+#define MACVO_CORR_TC_TF32 3   /* tcgen05 kind::tf32, ONE pass straight over the fp32 K-major (channels_last) features: no
+                                * operand pre-pass, no workspace; operands truncated to TF32 by the tensor core (10-bit
+                                * mantissa) = what the reference's own torch.matmul does for this product once its frontend
+                                * has set allow_tf32 (Frontend.py:275-277). Requires MACVO_CORR_KMAJOR_INPUT. */
 /* OR-ed into `mode` (tensor-core modes only): fmap1 / fmap2 are given K-major, (batch, n, dim) row-major — the memory of
  * a channels_last (B, D, H1, W1) tensor, which is what cuDNN's NHWC `channel_convertor` produces — so the operand
  * pre-pass is an elementwise fp16 split instead of a transpose. */
@@ -304,6 +308,19 @@ int macvo_observe_pack(const int64_t* kp0_uv, int k, int capacity, const float* 
                        float min_flow_cov, float min_depth_cov, float match_cov_default, const double* prev_pose,
                        double* next_pose, double* packed, int* n_obs, int* status, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (f2) decoder token path of one refinement iteration as one kernel — replaces flow_token_encoder (decoder.py:112-116),
+ *      CrossAttentionLayer (decoder.py:20-76: LayerNorm + sine position embedding, q projection, 8-head attention of each
+ *      pixel's query to its 8 cost-memory tokens, output projection, FFN) and the motion encoder's input concat
+ *      (gru.py:53-54).  cost_forward (P,81) pixels-major lookup rows; coords (B,2,n1); key / value (P,8,64) (the k / v
+ *      projections of the cost memory, computed once per frame); weight_blob: macvo_decoder_token_blob_floats() floats =
+ *      [W0^T (81x64) | W2^T (64x64) | Wq^T (64x64) | Wproj^T (128x64) | F0^T (64x64) | F3^T (64x64) | b0 | b2 | ln1.w |
+ *      ln1.b | bq | bproj | ln2.w | ln2.b | bf0 | bf3 | freq(16)].  out (P,160) = [cost_global (64) | cost_forward (81) | 0].
+ */
+size_t macvo_decoder_token_blob_floats(void);
+int macvo_decoder_token(const float* cost_forward, const float* coords, const float* key, const float* value,
+                        const float* weight_blob, float* out, int batch, int n1, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,8 @@ extern "C" int macvo_corr_build(const float* fmap1, const float* fmap2, float* c
         case MACVO_CORR_SIMT: return kmajor ? MACVO_E_UNSUPPORTED : macvo_corr_build_simt(fmap1, fmap2, corr, batch, dim, n, st);
         case MACVO_CORR_TC_3XF16: return macvo_corr_build_tc(fmap1, fmap2, corr, batch, dim, n, 3, kmajor, workspace, workspace_bytes, st);
         case MACVO_CORR_TC_1XF16: return macvo_corr_build_tc(fmap1, fmap2, corr, batch, dim, n, 1, kmajor, workspace, workspace_bytes, st);
+        case MACVO_CORR_TC_TF32: return kmajor ? macvo_corr_build_tc(fmap1, fmap2, corr, batch, dim, n, 2, 1, nullptr, 0, st)
+                                               : MACVO_E_UNSUPPORTED;       // reads the fp32 K-major features in place
         default: return MACVO_E_ARG;
     }
 }

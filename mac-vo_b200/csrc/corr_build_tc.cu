@@ -155,6 +155,15 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, kind::tf32: A (TMEM) and B (smem) hold fp32 bit patterns, the tensor core uses their top 19 bits (sign, 8-bit exponent,
+// 10-bit mantissa: the low 13 mantissa bits are ignored, i.e. operands are TRUNCATED to TF32), K = 8 per instruction
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 // smem (matrix descriptor: 128 rows x 32 B slice) -> TMEM (128 lanes x 8 columns)
 __device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t desc) {
     asm volatile("tcgen05.cp.cta_group::2.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
@@ -191,6 +200,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, both K-major, M x N
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
     return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// kind::tf32 instruction descriptor: D fp32 (c_format 1), A / B TF32 (format 2), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ---- kernel 1: operand pre-pass: fp32 (B, D, N) -> fp16 hi / lo (B, N, D), scaled (both maps, one launch) ----
@@ -267,7 +281,11 @@ split_kmajor_kernel(const float* __restrict__ f1, const float* __restrict__ f2, 
 }
 
 // ---- kernel 2 -----------------------------------------------------------------------------------------------
-template <int PASSES>   // 3: hi*hi + hi*lo + lo*hi     1: hi*hi
+// PASSES 3: fp16 hi*hi + hi*lo + lo*hi (fp32-class)    1: fp16 hi*hi    2: ONE kind::tf32 pass straight over the fp32
+// K-major features (no operand pre-pass, no workspace): map_a_hi / map_b_hi are fp32 maps with 32-element (128 B) boxes,
+// the "lo" half of every 16 KB ring slot carries the NEXT 32 channels instead of the low-order fp16 part, A occupies
+// TMEM columns [256, 512) as 256 fp32 values per lane, and a 64-channel k-block is 8 MMAs of K = 8 (12 in mode 3).
+template <int PASSES>
 __global__ void __launch_bounds__(THREADS, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -303,9 +321,10 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int s_end = (int)((long long)total_steps * (cluster_id + 1) / num_clusters);
     // a step is (row = b * prows + prow, column tile) = one 256 x 128 output block of the CTA pair
     const int row_begin = s_begin / nt, col_begin = s_begin - row_begin * nt;
-    constexpr int A_SLOTS_PER_KB = PASSES == 3 ? 2 : 1;        // A k-block: hi slot (+ lo slot)
+    constexpr bool TF32 = PASSES == 2;
+    constexpr int A_SLOTS_PER_KB = PASSES == 1 ? 1 : 2;        // A k-block: hi slot (+ lo slot)  |  tf32: channels [0,32) + [32,64)
     constexpr uint32_t A_SLOT_TX = 2 * SLOT_BYTES;              // both CTAs deliver 16 KB
-    constexpr uint32_t B_SLOT_TX = 2 * (PASSES == 3 ? 2 : 1) * B_HALF_BYTES;
+    constexpr uint32_t B_SLOT_TX = 2 * (PASSES == 1 ? 1 : 2) * B_HALF_BYTES;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < SLOTS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -337,8 +356,12 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             mbar_wait(bar_empty + 8 * slot, phase ^ 1);
                             const uint32_t full = bar_full + 8 * slot;
                             if (leader) mbar_expect_tx(full, A_SLOT_TX);
-                            tma_load_3d_2cta(smem_u32(smem + slot * SLOT_BYTES), h == 0 ? &map_a_hi : &map_a_lo, full,
-                                             kb * BLOCK_K, m_tile * BLOCK_M, b);
+                            if (TF32)
+                                tma_load_3d_2cta(smem_u32(smem + slot * SLOT_BYTES), &map_a_hi, full,
+                                                 kb * BLOCK_K + h * 32, m_tile * BLOCK_M, b);
+                            else
+                                tma_load_3d_2cta(smem_u32(smem + slot * SLOT_BYTES), h == 0 ? &map_a_hi : &map_a_lo, full,
+                                                 kb * BLOCK_K, m_tile * BLOCK_M, b);
                             if (++slot == SLOTS) { slot = 0; phase ^= 1; }
                         }
                     }
@@ -353,6 +376,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     const int brow = col * BLOCK_N + (int)rank * (BLOCK_N / 2);
                     tma_load_3d_2cta(sb, &map_b_hi, full, kb * BLOCK_K, brow, b);
                     if (PASSES == 3) tma_load_3d_2cta(sb + B_HALF_BYTES, &map_b_lo, full, kb * BLOCK_K, brow, b);
+                    if (TF32) tma_load_3d_2cta(sb + B_HALF_BYTES, &map_b_hi, full, kb * BLOCK_K + 32, brow, b);
                     TR(0, 200 + slot);
                     if (++slot == SLOTS) { slot = 0; phase ^= 1; }
                 }
@@ -363,7 +387,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer: leader CTA only, cta_group::2, TS mode =====================
         if (leader) {
-            constexpr uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BLOCK_N);      // M = 256 across the pair
+            constexpr uint32_t idesc = TF32 ? make_idesc_tf32(2 * BLOCK_M, BLOCK_N)
+                                            : make_idesc_f16(2 * BLOCK_M, BLOCK_N);      // M = 256 across the pair
             int slot = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             int col = col_begin;
@@ -379,9 +404,13 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                 const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem + slot * SLOT_BYTES));
 #pragma unroll
                                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                    const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-                                    const uint32_t acol = (uint32_t)((kb * BLOCK_K + k * UMMA_K) >> 1);
-                                    tmem_cp_128x256b(tmem_base + (h == 0 ? TMEM_A_HI : TMEM_A_LO) + acol, adesc + koff);
+                                    const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);      // 32 B per copy: 16 fp16 | 8 fp32
+                                    if (TF32) {
+                                        tmem_cp_128x256b(tmem_base + TMEM_A_HI + kb * BLOCK_K + h * 32 + k * 8, adesc + koff);
+                                    } else {
+                                        const uint32_t acol = (uint32_t)((kb * BLOCK_K + k * UMMA_K) >> 1);
+                                        tmem_cp_128x256b(tmem_base + (h == 0 ? TMEM_A_HI : TMEM_A_LO) + acol, adesc + koff);
+                                    }
                                 }
                                 umma_commit_mc(bar_empty + 8 * slot, 3);
                             }
@@ -406,7 +435,11 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);          // +32 B per K step in the atom
                             const uint32_t acol = (uint32_t)((kb * BLOCK_K + k * UMMA_K) >> 1);   // 2 fp16 per TMEM column
                             if (dbg & 2) continue;                                   // profiling aid: no MMA
-                            if (PASSES == 3) {   // small cross terms first, the dominant hi*hi product last
+                            if (TF32) {          // channels kb*64 + [8k, 8k+8) from the first half slot, + 32 from the second
+                                const uint32_t a0 = tmem_base + TMEM_A_HI + kb * BLOCK_K + k * 8;
+                                umma_tf32_ts(tmem_d, a0, b_hi + koff, idesc, (kb | k) != 0);
+                                umma_tf32_ts(tmem_d, a0 + 32, b_lo + koff, idesc, 1u);
+                            } else if (PASSES == 3) {   // small cross terms first, the dominant hi*hi product last
                                 umma_f16_ts(tmem_d, tmem_base + TMEM_A_LO + acol, b_hi + koff, idesc, (kb | k) != 0);
                                 umma_f16_ts(tmem_d, tmem_base + TMEM_A_HI + acol, b_lo + koff, idesc, 1u);
                                 umma_f16_ts(tmem_d, tmem_base + TMEM_A_HI + acol, b_hi + koff, idesc, 1u);
@@ -582,8 +615,26 @@ size_t macvo_corr_tc_workspace_bytes(int batch, int dim, int n, int passes) {
 int macvo_corr_build_tc(const float* f1, const float* f2, float* corr, int batch, int dim, int n, int passes, int kmajor,
                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (dim % BLOCK_K != 0 || dim > KMAX || n % 8 != 0) return MACVO_E_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(corr) & 31) return MACVO_E_ARG;
+    int dev = 0, sms = 0;
+    MACVO_CUDA_TRY(cudaGetDevice(&dev));
+    MACVO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int mt = ceil_div(n, BLOCK_M), nt = ceil_div(n, BLOCK_N);
+    const int total_steps = batch * ((mt + 1) / 2) * nt;
+    int clusters = sms / 2;
+    if (clusters > total_steps) clusters = total_steps;
+    if (clusters < 1) clusters = 1;
+    if (passes == 2) {
+        // kind::tf32: TMA reads the fp32 (B, N, D) features themselves, 32 channels (128 B) per swizzled row
+        if (!kmajor || (reinterpret_cast<uintptr_t>(f1) & 15) || (reinterpret_cast<uintptr_t>(f2) & 15)) return MACVO_E_ARG;
+        CUtensorMap m_a, m_b;
+        bool ok = make_map_3d(&m_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(f1), dim, n, batch, 32, BLOCK_M);
+        ok = ok && make_map_3d(&m_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(f2), dim, n, batch, 32, BLOCK_N / 2);
+        if (!ok) return MACVO_E_DRIVER;
+        return launch_main<2>(m_a, m_a, m_b, m_b, corr, batch, n, dim, clusters, st);
+    }
     if (!workspace || workspace_bytes < macvo_corr_tc_workspace_bytes(batch, dim, n, passes)) return MACVO_E_WORKSPACE;
-    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) || (reinterpret_cast<uintptr_t>(corr) & 31)) return MACVO_E_ARG;
+    if (reinterpret_cast<uintptr_t>(workspace) & 1023) return MACVO_E_ARG;
     const size_t ob = operand_bytes(batch, dim, n);
     char* ws = static_cast<char*>(workspace);
     __half* a_hi = reinterpret_cast<__half*>(ws);
@@ -614,14 +665,6 @@ int macvo_corr_build_tc(const float* f1, const float* f2, float* corr, int batch
     ok = ok && make_map_3d(&m_b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, passes == 3 ? b_lo : b_hi, dim, n, batch, BLOCK_K, BLOCK_N / 2);
     if (!ok) return MACVO_E_DRIVER;
 
-    int dev = 0, sms = 0;
-    MACVO_CUDA_TRY(cudaGetDevice(&dev));
-    MACVO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int mt = ceil_div(n, BLOCK_M), nt = ceil_div(n, BLOCK_N);
-    const int total_steps = batch * ((mt + 1) / 2) * nt;
-    int clusters = sms / 2;
-    if (clusters > total_steps) clusters = total_steps;
-    if (clusters < 1) clusters = 1;
     return passes == 3 ? launch_main<3>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, batch, n, dim, clusters, st)
                        : launch_main<1>(m_a_hi, m_a_lo, m_b_hi, m_b_lo, m_out, batch, n, dim, clusters, st);
 }

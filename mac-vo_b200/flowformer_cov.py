@@ -293,6 +293,15 @@ class FlowFormerCovNet:
                 W[p + f"convzr{o}.weight"] = torch.cat([W[p + f"convz{o}.weight"], W[p + f"convr{o}.weight"]], 0).contiguous(
                     memory_format=torch.channels_last)
                 W[p + f"convzr{o}.bias"] = torch.cat([W[p + f"convz{o}.bias"], W[p + f"convr{o}.bias"]], 0).contiguous()
+        # channel-padded motion-encoder filters for the fused token path (csrc/decoder_token.cu): convc1 reads the 160-channel
+        # rows [cost_global 64 | cost_forward 81 | 0 x 15]; `conv` writes 128 channels whose last two (zero filters, zero bias
+        # -> relu(0) = 0) receive the flow afterwards, which removes the 126+2 concat and cuDNN's channel re-padding passes
+        e = "memory_decoder.update_block.encoder."
+        w1 = W[e + "convc1.weight"]
+        W[e + "convc1p.weight"] = F.pad(w1, (0, 0, 0, 0, 0, 160 - w1.shape[1])).contiguous(memory_format=torch.channels_last)
+        W[e + "convc1p.bias"] = W[e + "convc1.bias"]
+        W[e + "convp.weight"] = F.pad(W[e + "conv.weight"], (0, 0, 0, 0, 0, 0, 0, 2)).contiguous(memory_format=torch.channels_last)
+        W[e + "convp.bias"] = F.pad(W[e + "conv.bias"], (0, 2)).contiguous()
 
     def state_dict(self) -> dict[str, Tensor]:
         return {k: self.W[k] for k, _, _ in param_spec()}
@@ -666,17 +675,17 @@ class FlowFormerCovNet:
         attention_h = attention.to(torch.float16) if native and torch.backends.cuda.matmul.allow_tf32 else None
         fast_tokens = native and QUERY_DIM == 64 and self.lookup_fn is self._ops.corr_lookup
         if fast_tokens:
-            fte0_w, fte0_b = self.W[m + "flow_token_encoder.0.weight"].flatten(1), self.W[m + "flow_token_encoder.0.bias"]
-            fte2_w, fte2_b = self.W[m + "flow_token_encoder.2.weight"].flatten(1), self.W[m + "flow_token_encoder.2.bias"]
-            freq16 = torch.arange(QUERY_DIM // 4, device=ctx.device, dtype=dd) * (1 / 200) * torch.pi   # as sine_embed builds it
+            token_blob = self._memo(("token_blob", ctx.device), lambda: self._ops.decoder_token_blob(self.W, m))
+            key, value = key.contiguous(), value.contiguous()
         for _ in range(self.depth):
             flow = (coords1 - coords0).to(dd)
             if native and fast_tokens:
-                # pixels-major rows end to end: lookup -> token MLP (two GEMMs with fused bias) -> fused LN + sine embedding
+                # pixels-major rows end to end: lookup kernel -> ONE token kernel (token MLP, LayerNorm + sine embedding, q
+                # projection, per-pixel 8x8 cross attention, output projection, FFN) writing the motion encoder's input rows
                 cf = self._ops.corr_lookup(cost_maps, coords1, rows=True)                     # (P, 81)
-                query = F.linear(F.gelu(F.linear(cf, fte0_w, fte0_b)), fte2_w, fte2_b)        # (P, 64)
-                qin = self._ops.query_prep(query, self.W[ca + "norm1.weight"], self.W[ca + "norm1.bias"], coords1, freq16)
-                cost_forward = cf.view(B, H1, W1, 81).permute(0, 3, 1, 2)                     # channels_last view
+                corr = self._ops.decoder_token(cf, coords1, key, value, token_blob)           # (P, 160) = [global | forward | 0]
+                corr = corr.view(B, H1, W1, 160).permute(0, 3, 1, 2)                          # channels_last view
+                convc1 = "convc1p"
             else:
                 cost_forward = self.lookup_fn(cost_maps, coords1).to(dd)         # fp32 lookup (covhead.py:91-93)
                 query = self._conv(F.gelu(self._conv(cost_forward, m + "flow_token_encoder.0")), m + "flow_token_encoder.2")
@@ -684,12 +693,13 @@ class FlowFormerCovNet:
                 # cross attention of each pixel's query to its 8 cost-memory tokens (decoder.py:56-76)
                 enc = sine_embed(coords1.to(dd).permute(0, 2, 3, 1).reshape(P, 2), QUERY_DIM)
                 qin = self._ln(query, ca + "norm1") + enc
-            q = self._lin(qin, ca + "q")
-            a = self._attn(q.unsqueeze(1), key, value, 8).squeeze(1)
-            g = query + self._lin(torch.cat([a, query], dim=1), ca + "proj")
-            g = g + self._lin(F.gelu(self._lin(self._ln(g, ca + "norm2"), ca + "ffn.0")), ca + "ffn.3")
-            cost_global = g.view(B, H1, W1, QUERY_DIM).permute(0, 3, 1, 2)
-            corr = torch.cat([cost_global, cost_forward], dim=1)
+                q = self._lin(qin, ca + "q")
+                a = self._attn(q.unsqueeze(1), key, value, 8).squeeze(1)
+                g = query + self._lin(torch.cat([a, query], dim=1), ca + "proj")
+                g = g + self._lin(F.gelu(self._lin(self._ln(g, ca + "norm2"), ca + "ffn.0")), ca + "ffn.3")
+                cost_global = g.view(B, H1, W1, QUERY_DIM).permute(0, 3, 1, 2)
+                corr = torch.cat([cost_global, cost_forward], dim=1)
+                convc1 = "convc1"
             # motion encoder (gru.py:45-64)
             e = ub + "encoder."
             if native:                                               # flow branch of the motion encoder on the side stream
@@ -701,12 +711,16 @@ class FlowFormerCovNet:
                     flo = self._conv_relu(self._conv_relu(flow, e + "convf1", padding=3), e + "convf2", padding=1)
                     joinf = torch.cuda.Event()
                     joinf.record(side)
-                cor = self._conv_relu(self._conv_relu(corr, e + "convc1"), e + "convc2", padding=1)
+                cor = self._conv_relu(self._conv_relu(corr, e + convc1), e + "convc2", padding=1)
                 main.wait_event(joinf)
             else:
-                cor = self._conv_relu(self._conv_relu(corr, e + "convc1"), e + "convc2", padding=1)
+                cor = self._conv_relu(self._conv_relu(corr, e + convc1), e + "convc2", padding=1)
                 flo = self._conv_relu(self._conv_relu(flow, e + "convf1", padding=3), e + "convf2", padding=1)
-            mf = torch.cat([self._conv_relu(torch.cat([cor, flo], dim=1), e + "conv", padding=1), flow], dim=1)
+            if native:      # 128-channel conv output (last two channels zero), flow written into them in place
+                mf = self._conv_relu(torch.cat([cor, flo], dim=1), e + "convp", padding=1)
+                mf.permute(0, 2, 3, 1)[..., 126:] = flow.permute(0, 2, 3, 1)
+            else:
+                mf = torch.cat([self._conv_relu(torch.cat([cor, flo], dim=1), e + "conv", padding=1), flow], dim=1)
             # GMA aggregation (gma.py:84-130)
             mf = mf.contiguous(memory_format=torch.channels_last)
             v = self._conv(mf, ub + "aggregator.to_v").flatten(2).transpose(1, 2)   # (B, N, 128)

@@ -16,7 +16,8 @@ from .build import LIB_PATH
 
 Tensor = torch.Tensor
 
-CORR_SIMT, CORR_TC_3XF16, CORR_TC_1XF16 = 0, 1, 2
+CORR_SIMT, CORR_TC_3XF16, CORR_TC_1XF16, CORR_TC_TF32 = 0, 1, 2, 3
+CORR_MODE_NAMES = {0: "simt", 1: "tc3", 2: "tc1", 3: "tf32"}
 CORR_KMAJOR_INPUT = 16      # OR-ed into the mode: operands given K-major (channels_last features)
 PGO_ACC = 55
 
@@ -79,6 +80,8 @@ EXPORTS = {
     "macvo_query_prep": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "macvo_small_attention_ex": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 10 + [C.c_void_p] * 2 + [C.c_int, C.c_void_p]),
     "macvo_latent_pool": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_void_p]),
+    "macvo_decoder_token_blob_floats": (C.c_size_t, []),
+    "macvo_decoder_token": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "macvo_gru_input": (C.c_int, [C.c_void_p] * 7 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_gates": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_blend": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
@@ -142,28 +145,36 @@ def _workspace(key, nbytes: int, device) -> Tensor:
 # (a3) correlation volume
 # ------------------------------------------------------------------------------------------------
 def default_corr_mode(dim: int, n: int) -> int:
+    """Strict fp32 (allow_tf32 off): the fp32-class 3 x fp16 split. With TF32 matmuls allowed — the reference frontend's
+    own setting (Frontend.py:275-277), under which ITS `torch.matmul` for this product runs on TF32 tensor cores — one
+    kind::tf32 pass straight over the fp32 features (no operand pre-pass)."""
     env = os.environ.get("MACVO_B200_CORR_MODE")
     if env is not None:
-        return {"simt": CORR_SIMT, "tc3": CORR_TC_3XF16, "tc1": CORR_TC_1XF16}[env]
-    return CORR_TC_3XF16 if (dim % 64 == 0 and n % 8 == 0) else CORR_SIMT
+        return {"simt": CORR_SIMT, "tc3": CORR_TC_3XF16, "tc1": CORR_TC_1XF16, "tf32": CORR_TC_TF32}[env]
+    if not (dim % 64 == 0 and dim <= 256 and n % 8 == 0):
+        return CORR_SIMT
+    return CORR_TC_TF32 if torch.backends.cuda.matmul.allow_tf32 else CORR_TC_3XF16
 
 
 def corr_build(fmap1: Tensor, fmap2: Tensor, mode: int | None = None) -> Tensor:
     """(B,D,H,W) x2 -> (B,1,H,W,H,W) fp32, `MemoryEncoder.corr` (encoder.py:256-275).
 
-    fp16 feature maps (MACVO_Fast) use the single-pass tensor-core mode, which is exact for them."""
+    fp16 feature maps (MACVO_Fast) use the single-pass fp16 tensor-core mode, which is exact for them."""
     lib = load_library()
     B, D, H, W = fmap1.shape
     n = H * W
     if mode is None:
         mode = default_corr_mode(D, n)
-        if fmap1.dtype == torch.float16 and mode == CORR_TC_3XF16:
+        if fmap1.dtype == torch.float16 and mode in (CORR_TC_3XF16, CORR_TC_TF32):
             mode = CORR_TC_1XF16
     f1 = fmap1.float() if fmap1.dtype != torch.float32 else fmap1
     f2 = fmap2.float() if fmap2.dtype != torch.float32 else fmap2
     cl = torch.channels_last
     kmajor = (mode != CORR_SIMT and f1.is_cuda and f2.is_cuda and not f1.is_contiguous() and not f2.is_contiguous()
               and f1.is_contiguous(memory_format=cl) and f2.is_contiguous(memory_format=cl))
+    if mode == CORR_TC_TF32 and not kmajor:     # the tf32 kernel reads K-major rows in place: make them (one copy each)
+        f1, f2 = f1.contiguous(memory_format=cl), f2.contiguous(memory_format=cl)
+        kmajor = True
     if kmajor:      # channels_last features are already K-major (B, N, D) rows: elementwise operand split, no transpose
         f1, f2 = f1.permute(0, 2, 3, 1), f2.permute(0, 2, 3, 1)
     f1 = _dev(f1, torch.float32, "corr_build fmap1")
@@ -174,7 +185,7 @@ def corr_build(fmap1: Tensor, fmap2: Tensor, mode: int | None = None) -> Tensor:
     rc = lib.macvo_corr_build(f1.data_ptr(), f2.data_ptr(), out.data_ptr(), B, D, n, mode | (CORR_KMAJOR_INPUT if kmajor else 0),
                               ws.data_ptr() if ws is not None else None, nbytes, _stream())
     _check(rc, "macvo_corr_build")
-    LAUNCHES[0] += (1 if mode == CORR_SIMT else 2)
+    LAUNCHES[0] += {CORR_SIMT: 1, CORR_TC_TF32: 1}.get(mode, 2)
     return out
 
 
@@ -697,6 +708,42 @@ def query_prep(query: Tensor, ln_weight: Tensor, ln_bias: Tensor, coords: Tensor
     rc = load_library().macvo_query_prep(query.data_ptr(), _bias_ptr(ln_weight, 64, "ln weight"), _bias_ptr(ln_bias, 64, "ln bias"),
                                          co.data_ptr(), _bias_ptr(freq, 16, "freq"), out.data_ptr(), B, H * W, float(eps), _stream())
     _check(rc, "macvo_query_prep")
+    LAUNCHES[0] += 1
+    return out
+
+
+def decoder_token_blob(w: dict, prefix: str = "memory_decoder.") -> Tensor:
+    """Pack the token-path weights (checkpoint names) into the blob layout of macvo_decoder_token."""
+    ca = prefix + "decoder_layer.cross_attend."
+    mats = [w[prefix + "flow_token_encoder.0.weight"].flatten(1), w[prefix + "flow_token_encoder.2.weight"].flatten(1),
+            w[ca + "q.weight"], w[ca + "proj.weight"], w[ca + "ffn.0.weight"], w[ca + "ffn.3.weight"]]
+    vecs = [w[prefix + "flow_token_encoder.0.bias"], w[prefix + "flow_token_encoder.2.bias"], w[ca + "norm1.weight"],
+            w[ca + "norm1.bias"], w[ca + "q.bias"], w[ca + "proj.bias"], w[ca + "norm2.weight"], w[ca + "norm2.bias"],
+            w[ca + "ffn.0.bias"], w[ca + "ffn.3.bias"]]
+    dev = mats[0].device
+    freq = torch.arange(16, device=dev, dtype=torch.float32) * (1 / 200) * torch.pi      # as sine_embed builds it
+    blob = torch.cat([m.float().t().contiguous().flatten() for m in mats] + [v.float().flatten() for v in vecs] + [freq])
+    if blob.numel() != load_library().macvo_decoder_token_blob_floats():
+        raise MacvoB200Error(f"decoder_token_blob: {blob.numel()} floats, kernel expects "
+                             f"{load_library().macvo_decoder_token_blob_floats()}")
+    return blob.contiguous()
+
+
+def decoder_token(cost_forward: Tensor, coords: Tensor, key: Tensor, value: Tensor, blob: Tensor, eps: float = 1e-5) -> Tensor:
+    """one refinement iteration's token path: lookup rows (P,81) + coords (B,2,H,W) + per-pixel keys / values (P,8,64)
+    -> (P,160) rows [cost_global | cost_forward | 0] (decoder.py:20-76,112-116; csrc/decoder_token.cu)"""
+    cf = _dense(cost_forward, 81, "decoder_token cost_forward")
+    co = _dev(coords, torch.float32, "decoder_token coords")
+    B, _, H, W = co.shape
+    P = B * H * W
+    k, v = _dense(key, 64, "decoder_token key"), _dense(value, 64, "decoder_token value")
+    if cf.numel() != P * 81 or k.numel() != P * 512 or v.numel() != P * 512:
+        raise MacvoB200Error("decoder_token: expects cost_forward (P,81), key / value (P,8,64) with P = B*H*W")
+    out = torch.empty((P, 160), dtype=torch.float32, device=cf.device)
+    rc = load_library().macvo_decoder_token(cf.data_ptr(), co.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                            _dense(blob, 1, "decoder_token blob").data_ptr(), out.data_ptr(), B, H * W,
+                                            float(eps), _stream())
+    _check(rc, "macvo_decoder_token")
     LAUNCHES[0] += 1
     return out
 

@@ -65,20 +65,20 @@ def main() -> None:
         out = model.memory_encoder.corr(f1, f2)
         # keep fixtures small: store a strided sample of the volume + its full checksum
         rows, cols = cases.corr_sample_index(H1 * W1)
-        save(f"corr_{name}.pt", {"shape": (B, H1, W1), "sample": out.reshape(B, H1 * W1, H1 * W1)[:, rows][:, :, cols].clone(),
+        save(f"corr_{name}.pt", {"shape": (B, H1, W1), "input_sha": cases.sha(f1, f2), "sample": out.reshape(B, H1 * W1, H1 * W1)[:, rows][:, :, cols].clone(),
                                  "sum": out.double().sum(), "abs_sum": out.double().abs().sum()})
 
     # ---- lookup (a5) ----------------------------------------------------------------------
     for name, (B, H1, W1) in cases.LOOKUP_CASES.items():
         cost_maps, coords = cases.lookup_inputs(B, H1, W1)
         out = model.memory_decoder.encode_flow_token(cost_maps, coords.clone())
-        save(f"lookup_{name}.pt", {"shape": (B, H1, W1), "out": out.clone()})
+        save(f"lookup_{name}.pt", {"shape": (B, H1, W1), "out": out.clone(), "input_sha": cases.sha(cost_maps, coords)})
 
     # ---- network end to end (a2), synthetic weights -----------------------------------------
     for name, (B, H, W) in cases.NET_CASES.items():
         img1, img2 = cases.net_inputs(B, H, W)
         flow, cov = model.inference(img1, img2)
-        save(f"net_{name}.pt", {"shape": (B, H, W), "flow": flow.clone(), "cov": cov.clone()})
+        save(f"net_{name}.pt", {"shape": (B, H, W), "flow": flow.clone(), "cov": cov.clone(), "input_sha": cases.sha(img1, img2)})
 
     # ---- dense post-processing (a7) ---------------------------------------------------------
     def stereo(H, W, fx, bl):
@@ -93,7 +93,7 @@ def main() -> None:
             d = FlowFormerCovFrontend.inference_2_depth(est_flow[0:1], est_cov[0:1], frame, epd)
             m = FlowFormerCovFrontend.inference_2_match(est_flow[1:2], est_cov[1:2])
             save(f"dense_{name}_{int(epd)}.pt", {
-                "shape": (H, W), "depth": d.depth, "disparity": d.disparity, "depth_cov": d.cov,
+                "shape": (H, W), "input_sha": cases.sha(est_flow, est_cov), "depth": d.depth, "disparity": d.disparity, "depth_cov": d.cov,
                 "disparity_uncertainty": d.disparity_uncertainty, "depth_mask": d.mask,
                 "flow": m.flow, "flow_cov": m.cov})
 
@@ -110,7 +110,8 @@ def main() -> None:
         torch.manual_seed(cases.SELECTOR_RNG_SEED)
         kp = sel.select_point(frame, num, depth, depth, match)
         mp = mapsel.select_point(frame, 2000, depth, depth, match)      # second randperm of the frame
-        save(f"selector_{name}.pt", {"shape": (H, W), "num": num, "variant": variant, "kp": kp, "map_kp": mp})
+        save(f"selector_{name}.pt", {"shape": (H, W), "num": num, "variant": variant, "kp": kp, "map_kp": mp,
+                                     "input_sha": cases.sha(est_flow, est_cov)})
 
     dsel = CovAwareSelector(SimpleNamespace(device="cpu", kernel_size=7, mask_width=32, max_depth="auto",
                                             max_depth_cov=250.0, max_match_cov=100.0))
@@ -125,7 +126,8 @@ def main() -> None:
             depth0.mask = ~depth0.mask          # reference contract: True = valid (StereoDepth.py:28-30)
         torch.manual_seed(cases.SELECTOR_RNG_SEED)
         kp = dsel.select_point(frame, num, depth0, depth1, match)
-        save(f"selector_{name}.pt", {"shape": (H, W), "num": num, "variant": variant, "kp": kp})
+        save(f"selector_{name}.pt", {"shape": (H, W), "num": num, "variant": variant, "kp": kp,
+                                     "input_sha": cases.sha(f0, c0, f1, c1)})
 
     # ---- covariance model (a10) ---------------------------------------------------------------
     covm = MatchCovariance(SimpleNamespace(device="cpu", kernel_size=31, match_cov_default=0.25,
@@ -137,7 +139,7 @@ def main() -> None:
         fc = None if flow_cov is None else flow_cov.clone()
         out = covm.estimate(frame, kp, dest, None, fc)
         save(f"covariance_{name}.pt", {"shape": (H, W, K), "kind": kind, "out": out,
-                                       "flow_cov_after": fc})
+                                       "flow_cov_after": fc, "input_sha": cases.sha(kp, depth_map, flow_cov)})
 
     # ---- two-frame PGO (a13-a16) --------------------------------------------------------------
     for name, (K, seed) in cases.PGO_CASES.items():
@@ -163,7 +165,7 @@ def main() -> None:
             _, out = TwoFrame_PGO._optimize(ctx, gi)
         finally:
             torch.cuda.current_stream = _cs
-        save(f"pgo_{name}.pt", {"K": K, "seed": seed, "pose": out.motion.detach().as_subclass(torch.Tensor).clone().reshape(7)})
+        save(f"pgo_{name}.pt", {"K": K, "seed": seed, "input_sha": cases.sha(*[c[k] for k in ("pos_Tw", "kp2_uv", "kp2_disp", "uv_cov", "disp_cov")]), "pose": out.motion.detach().as_subclass(torch.Tensor).clone().reshape(7)})
 
 
 if __name__ == "__main__":

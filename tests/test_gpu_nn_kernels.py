@@ -180,3 +180,37 @@ def test_latent_pool_equals_cross_attention(ops, m, nk):
     got = ops.latent_pool(tokens, q[0], wk, wv, bv)
     assert got.shape == (m, 8, 128)
     assert (got.double() - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("b,h,w", [(1, 5, 7), (2, 12, 16), (2, 60, 80), (1, 33, 47)])
+def test_decoder_token_kernel(ops, b, h, w):
+    """csrc/decoder_token.cu vs a float64 torch evaluation of the chain it replaces (decoder.py:20-76,112-116) with the
+    network's own weights: token MLP, LayerNorm + sine embedding, q projection, 8-head attention over the pixel's 8
+    cost-memory tokens, output projection, FFN; out = [cost_global | cost_forward | 0]. fp32 FMA kernel -> 1e-5."""
+    from macvo_b200.flowformer_cov import synthetic_state_dict, sine_embed
+    sd = {k: v.to(DEV) for k, v in synthetic_state_dict(0).items() if k.startswith("memory_decoder.")}
+    P = b * h * w
+    g = torch.Generator().manual_seed(P)
+    cf = torch.randn(P, 81, generator=g).to(DEV) * 2
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    coords = (torch.stack([xs, ys], 0).unsqueeze(0).repeat(b, 1, 1, 1) + torch.randn(b, 2, h, w, generator=g) * 5).to(DEV)
+    key, value = torch.randn(P, 8, 64, generator=g).to(DEV), torch.randn(P, 8, 64, generator=g).to(DEV)
+    blob = ops.decoder_token_blob(sd)
+    got = ops.decoder_token(cf, coords, key, value, blob)
+    assert got.shape == (P, 160) and torch.equal(got[:, 64:145], cf) and not got[:, 145:].any()
+
+    m, ca = "memory_decoder.", "memory_decoder.decoder_layer.cross_attend."
+    W = {k: v.double() for k, v in sd.items()}
+    lin = lambda x, p: F.linear(x, W[p + ".weight"].flatten(1), W[p + ".bias"])
+    x = cf.double()
+    query = lin(F.gelu(lin(x, m + "flow_token_encoder.0")), m + "flow_token_encoder.2")
+    enc = sine_embed(coords.double().permute(0, 2, 3, 1).reshape(P, 2), 64)
+    qin = F.layer_norm(query, (64,), W[ca + "norm1.weight"], W[ca + "norm1.bias"], 1e-5) + enc
+    q = lin(qin, ca + "q").view(P, 8, 1, 8)                                   # (P, heads, 1, d)
+    kh, vh = key.double().view(P, 8, 8, 8).transpose(1, 2), value.double().view(P, 8, 8, 8).transpose(1, 2)   # (P, heads, tokens, d)
+    a = (torch.matmul(q, kh.transpose(-1, -2)) * 8 ** -0.5).softmax(-1) @ vh
+    a = a.reshape(P, 64)
+    gl = query + lin(torch.cat([a, query], 1), ca + "proj")
+    gl = gl + lin(F.gelu(lin(F.layer_norm(gl, (64,), W[ca + "norm2.weight"], W[ca + "norm2.bias"], 1e-5), ca + "ffn.0")), ca + "ffn.3")
+    err = (got[:, :64].double() - gl).abs().max().item()
+    assert err <= 1e-5 * gl.abs().max().item(), err / gl.abs().max().item()

@@ -33,8 +33,9 @@ def _strict_fp32():
 @pytest.mark.parametrize("name", list(cases.NET_CASES))
 def test_network_with_cuda_kernels_matches_reference_golden(plugins, golden, name):
     """FlowFormerCov with the sm_100a corr + lookup kernels vs the REFERENCE network's CPU output (golden).
-    fp32, TF32 off. Tolerance: 2e-3 relative to the output scale after 12 recurrent refinements
-    (cuDNN/cuBLAS fp32 vs MKL summation order; the kernels themselves are checked to 2e-6 elsewhere)."""
+    fp32, TF32 off. The reference's own fp32 result sits ~1e-6 (flow) / ~2e-5 (covariance) from exact arithmetic at these
+    sizes (tests/golden/make_golden_cfgA.py measures the same floor at 640x480); asserted: 2e-5 of the flow scale and 3e-4
+    relative on the covariance. The 640x480 / depth-12 ladder in both precision modes is tests/test_gpu_parity_ladder.py."""
     from macvo_b200.flowformer_cov import FlowFormerCovNet, synthetic_state_dict
     _strict_fp32()
     g = golden(f"net_{name}.pt")
@@ -44,9 +45,9 @@ def test_network_with_cuda_kernels_matches_reference_golden(plugins, golden, nam
     flow, cov = net.inference(img1.to(DEV), img2.to(DEV))
     flow, cov = flow.cpu(), cov.cpu()
     fscale = g["flow"].abs().mean().item()
-    assert (flow - g["flow"]).abs().max().item() <= 2e-3 * max(fscale, 1.0), (flow - g["flow"]).abs().max().item()
+    assert (flow - g["flow"]).abs().max().item() <= 2e-5 * max(fscale, 1.0), (flow - g["flow"]).abs().max().item() / fscale
     rel = ((cov - g["cov"]).abs() / g["cov"].abs().clamp_min(1e-6)).max().item()
-    assert rel <= 5e-3, rel
+    assert rel <= 3e-4, rel
 
 
 def _frontend(P, cuda_graph, depth=12):
