@@ -119,6 +119,37 @@ def _so3_jl(phi: torch.Tensor) -> torch.Tensor:
     return I + c1 * K + c2 * (K @ K)
 
 
+def _so3_log(q: torch.Tensor) -> torch.Tensor:
+    """SO3 Log as pypose computes it: phi = v * 2 atan(|v| / w) / |v| (series 2/w - 2|v|^2 / (3 w^3) near |v| = 0)."""
+    v, w = q[..., :3], q[..., 3:4]
+    n = v.norm(dim=-1, keepdim=True)
+    eps = torch.finfo(q.dtype).eps
+    small = n <= eps
+    safe = torch.where(small, torch.ones_like(n), n)
+    factor = torch.where(small, 2.0 / w - 2.0 * n * n / (3.0 * w * w * w), 2.0 * torch.atan(safe / w) / safe)
+    return v * factor
+
+
+def _so3_jl_inv(phi: torch.Tensor) -> torch.Tensor:
+    """Inverse left Jacobian of SO(3): I - K/2 + (1/t^2 - (1 + cos t) / (2 t sin t)) K^2."""
+    theta = phi.norm(dim=-1, keepdim=True).unsqueeze(-1)
+    t2 = theta * theta
+    eps = torch.finfo(phi.dtype).eps
+    small = theta <= eps
+    safe = torch.where(small, torch.ones_like(theta), theta)
+    coef = torch.where(small, 1.0 / 12 + t2 / 720 + t2 * t2 / 30240,
+                       1.0 / (safe * safe) - (1 + torch.cos(safe)) / (2 * safe * torch.sin(safe)))
+    K = vec2skew(phi)
+    I = torch.eye(3, dtype=phi.dtype, device=phi.device).expand_as(K)
+    return I - 0.5 * K + coef * (K @ K)
+
+
+def _se3_log(x: torch.Tensor) -> torch.Tensor:
+    phi = _so3_log(x[..., 3:7])
+    tau = (_so3_jl_inv(phi) @ x[..., :3].unsqueeze(-1)).squeeze(-1)
+    return torch.cat([tau, phi], dim=-1)
+
+
 def _se3_exp(x: torch.Tensor) -> torch.Tensor:
     tau, phi = x[..., :3], x[..., 3:6]
     t = (_so3_jl(phi) @ tau.unsqueeze(-1)).squeeze(-1)
@@ -214,6 +245,13 @@ class LieTensor(torch.Tensor):
         assert self.ltype is so3_type
         return LieTensor(_so3_exp(d), ltype=SO3_type)
 
+    def Log(self) -> "LieTensor":
+        d = _raw(self)
+        if self.ltype is SE3_type:
+            return LieTensor(_se3_log(d), ltype=se3_type)
+        assert self.ltype is SO3_type
+        return LieTensor(_so3_log(d), ltype=so3_type)
+
     def _compose(self, other: "LieTensor") -> "LieTensor":
         a, b = _raw(self), _raw(other)
         if self.ltype is SO3_type:
@@ -304,7 +342,18 @@ def _unavailable(name):
     return f
 
 
-cumops = _unavailable("cumops")
+def cumops(input, dim, ops):
+    """Inclusive left fold along `dim`: y_0 = x_0, y_i = ops(y_{i-1}, x_i) (pypose 0.6.8 `cumops`; the library evaluates it
+    as a doubling scan, which gives the same result for an associative `ops`). Only dim = 0 is needed
+    (Module/MapProcessor.py:75)."""
+    assert dim == 0
+    if input.shape[0] == 0:
+        return input
+    out = [input[0:1]]
+    for i in range(1, input.shape[0]):
+        out.append(ops(out[-1], input[i:i + 1]))
+    raw = torch.cat([_raw(o) for o in out], dim=0)
+    return LieTensor(raw, ltype=input.ltype) if isinstance(input, LieTensor) else raw
 
 
 def _mat2quat(R: torch.Tensor) -> torch.Tensor:

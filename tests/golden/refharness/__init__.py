@@ -19,7 +19,7 @@ import types
 REFERENCE_ROOT = os.environ.get("MACVO_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(os.path.dirname(os.path.dirname(_HERE)))
-_AUTO_STUB_ROOTS = ("matplotlib", "evo", "rerun", "flow_vis", "mpl_toolkits", "cv2", "wandb", "kornia")
+_AUTO_STUB_ROOTS = ("matplotlib", "evo", "flow_vis", "mpl_toolkits", "cv2", "wandb", "kornia")   # rerun is optional in MAC-VO (ImportError -> None)
 
 
 def available() -> bool:
