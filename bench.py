@@ -39,6 +39,7 @@ CONFIGS = {
     "fast": dict(enc_dtype="fp16", dec_dtype="bf16", num_point=200),           # Config/Experiment/MACVO/MACVO_Fast.yaml
 }
 SEQ_LEN = 8     # distinct synthetic frames, cycled (forwards / backwards) by the timed loop
+SHARDED = dict(H=720, W=1280, num_point=4096)          # BASELINE configs[3]: one 1280x720 stream, GN blocks over N GPUs
 
 
 def workload_name(cfg: dict) -> str:
@@ -288,17 +289,123 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
     return out if rank == 0 else {}
 
 
+def run_sharded(steps: int, warmup: int) -> dict:
+    """BASELINE configs[3]: ONE 1280x720 stream, 4096 keypoints, on N GPUs. Rank 0 owns the frontend, the selection and the
+    device-side observation building; per frame it broadcasts the five LM input arrays (NCCL, 80 B per keypoint slot) and
+    every rank solves its shard of residual blocks with the all-reduce of the 55-double accumulator fused into the persistent
+    LM kernel over NVLink peer memory (sharded_pgo.FusedShardedPGO). Strong scaling of a 0.8 ms solve: reported to show where
+    the exchange sits, not because it pays at K = 4096 (DESIGN.md §6 has the crossover table)."""
+    import torch.distributed as dist
+    rank, world, local = _dist()
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    from types import SimpleNamespace as NS
+    from macvo_b200 import build, ops, plugins, synthetic
+    from macvo_b200.pipeline import FusedTwoFrameOdometry
+    from macvo_b200.sharded_pgo import FusedShardedPGO
+    build.build(verbose=False)
+    ops.load_library()
+    Hs, Ws, KP = SHARDED["H"], SHARDED["W"], SHARDED["num_point"]
+    fused = FusedShardedPGO() if world > 1 else None
+    solver = (lambda obs, intr, pose_io, stats, min_k: fused.solve_packed(obs, intr, pose_io, stats, min_k)) if fused else None
+    frames = synthetic.make_sequence(4, Hs, Ws, pin=True)
+    n_total = warmup + steps
+    intr = None
+    if rank == 0:
+        fe = plugins.B200_FlowFormerCovFrontend(NS(weight="synthetic:0", device=device, enc_dtype="fp32", dec_dtype="fp32",
+                                                   decoder_depth=12, enforce_positive_disparity=False, cuda_graph=True))
+        sel = plugins.B200_CovAwareSelector_NoDepth(NS(device=device, kernel_size=7, mask_width=32, max_match_cov=100.0))
+        msel = plugins.B200_MappingPointSelector(NS(max_depth=5.0, max_depth_cov=0.005, mask_width=32))
+        cov = plugins.B200_MatchCovariance(NS(device=device, kernel_size=31, match_cov_default=0.25, min_depth_cov=0.05, min_flow_cov=0.25))
+        pgo = plugins.B200_TwoFrame_PGO(NS(graph_type="disp", device=device, vectorize=True, parallel=False, autodiff=False))
+        torch.manual_seed(5)
+        odo = FusedTwoFrameOdometry(fe, sel, cov, pgo, num_point=KP, map_selector=msel, solver=solver)
+        odo.initialize(frames[0])
+    else:
+        obs = ops.ObservationBuffers(KP, device)
+        pose_io = torch.zeros(7, dtype=torch.float64, device=device)
+        stats = torch.zeros(8, dtype=torch.float64, device=device)
+        K = frames[0].frame_K
+        intr = (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]),
+                float(torch.as_tensor(frames[0].frame_baseline, dtype=torch.float32).double().reshape(-1)[0]))
+
+    def step(i):
+        if rank == 0:
+            odo.run_pair(frames[1 + (i % 3)])
+            return odo.latest_pose()
+        fused.solve_packed(obs, intr, pose_io, stats, 10)
+        return None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    with ClockSampler(local) as clk:
+        for i in range(warmup):
+            step(i)
+        barrier()
+        ops.LAUNCHES[0] = 0
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        last = None
+        for i in range(warmup, n_total):
+            last = step(i)
+        e.record()
+        barrier()
+    ms = s.elapsed_time(e)
+    poses_equal = None
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        mine = odo.pose_dev[-1].clone() if rank == 0 else pose_io.clone()
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        poses_equal = all(torch.equal(g, gathered[0]) for g in gathered)
+    out = {}
+    if rank == 0:
+        o = odo.observations()
+        out = {"metric": "stereo frames/sec @1280x720, 4096 keypoints, GN residual blocks sharded over the GPUs",
+               "value": steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+               "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic (seeded smoothed-noise 1280x720 stereo sequence, synthetic:0 network weights)",
+               "config": {"workload": "1280x720 synthetic stereo stream, 4096 keypoints, decoder_depth 12, GN/LM residual blocks "
+                                      "sharded over the GPUs, BASELINE configs[3]",
+                          "parallelism": ("1 GPU: persistent LM kernel" if world == 1 else
+                                          f"rank 0: frontend + observation building; per frame 2 NCCL broadcasts (LM inputs {80 * KP} B, "
+                                          f"count+pose 64 B); {world} ranks: fused peer-memory all-reduce inside the LM kernel "
+                                          "(no NCCL call inside the solve)"),
+                          "num_obs_last_frame": o["num_obs"], "poses_bit_identical_on_all_ranks": poses_equal},
+               "e2e": {"value": steps / (ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 2 * 3 * Hs * Ws * 4,
+                       "d2h_bytes_per_step": 7 * 8 + (31 * KP + 4) * 8},
+               "gpu_launches": ops.LAUNCHES[0], "clocks": clk.summary()}
+    if fused is not None:
+        fused.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return out
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="performant", choices=list(CONFIGS))
+    ap.add_argument("--config", default="performant", choices=list(CONFIGS) + ["sharded"])
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
-    cfg = CONFIGS[a.config]
     rank, world, _ = _dist()
+    if a.config == "sharded":
+        out = run_sharded(a.steps, a.warmup)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+        return
+    cfg = CONFIGS[a.config]
     if a.impl == "reference":
         if rank != 0:
             return                                   # rank 0 alone runs the CPU arm

@@ -217,11 +217,33 @@ int macvo_pgo_solve_counted(const double* pos_Tw, const double* kp2_uv, const do
                             const double* disp_cov, int k_capacity, const int* k_dev, int min_k, const double* intr,
                             double* pose_io, const macvo_pgo_params_t* params, double* stats, void* stream);
 
+/* Multi-GPU solve (BASELINE config 4): the K residual blocks are sharded across `world` ranks (one process
+ * per GPU), every rank launches this with ITS shard and the same pose_io / params; the all-reduce of the 55-double
+ * accumulator happens INSIDE the persistent kernel through peer memory (stores into every rank's exchange buffer over
+ * NVLink + system-scope release / acquire flags, summed in rank order -> identical bits on every rank), once per
+ * evaluation; no NCCL call and no host round trip inside the LM loop. exchange_bufs: HOST array of `world` device
+ * pointers, entry r = rank r's exchange buffer (macvo_pgo_exchange_bytes(world) bytes, zero-initialised, allocated with
+ * macvo_p2p_alloc and mapped into this process with macvo_p2p_open; entry `rank` = this rank's own allocation).
+ * All ranks must launch the same sequence of solves. A peer that never arrives traps after ~3 s instead of hanging. */
+size_t macvo_pgo_exchange_bytes(int world);
+int macvo_p2p_alloc(size_t bytes, void** dev_ptr, unsigned char* ipc_handle64);       /* cudaMalloc + zero + cudaIpcGetMemHandle */
+int macvo_p2p_open(const unsigned char* ipc_handle64, void** peer_ptr);               /* cudaIpcOpenMemHandle (peer access) */
+int macvo_p2p_close(void* peer_ptr);
+int macvo_p2p_free(void* dev_ptr);
+/* k_total_dev (optional device int, the same value on every rank): only the first *k_total_dev blocks of the GLOBAL
+ * array are valid and this rank's k_shard blocks start at global index k_offset -> it uses
+ * clamp(*k_total_dev - k_offset, 0, k_shard) of them; fewer than min_k valid blocks in total: every rank skips. */
+int macvo_pgo_solve_sharded(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp, const double* uv_cov,
+                            const double* disp_cov, int k_shard, const int* k_total_dev, int k_offset, int min_k,
+                            const double* intr, double* pose_io, const macvo_pgo_params_t* params, double* stats,
+                            void* const* exchange_bufs, int world, int rank, void* stream);
+
 /* One evaluation of the packed normal-equation accumulator for a SHARD of residual blocks
  * (multi-GPU: each rank reduces its blocks, ranks all-reduce the 55 doubles):
  * acc = [A upper 6x6 (21) | b (6) | G = Js^T Js upper (21) | h = Js^T Rs (6) | robust loss (1)].
  */
 #define MACVO_PGO_ACC 55
+#define MACVO_PGO_MAX_RANKS 8
 int macvo_pgo_accumulate(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp, const double* uv_cov,
                          const double* disp_cov, int k, const double* intr, const double* pose, double huber_delta,
                          double* acc, void* stream);

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <math_constants.h>
+#include <cstring>
 
 namespace cg = cooperative_groups;
 
@@ -80,6 +81,7 @@ struct Shared {
     double pose[7], trial[7];
     double Rm[9];                  // rotation matrix of the linearisation pose (dynamic indexing)
     int flag_inner, flag_cont;
+    unsigned long long round;      // next cross-GPU exchange round (identical in every CTA and every rank)
 };
 
 // fixed-order reduction of per-lane accumulators (entry e lives in lane e%32, slot e/32) to Shared::total
@@ -103,12 +105,28 @@ __device__ void reduce_all(Shared& S, cg::cluster_group& cluster, double acc0, d
     cluster.sync();     // partials may be overwritten only after every CTA has read them
 }
 
+// exchange buffer of one rank (in ITS OWN memory; peers write into it):
+//   [0, 2 * R * 56)                    data[parity][src rank][56]  partial accumulators (55 used)
+//   [2 * R * 56, 2 * R * 56 + 2 * R)   flag[parity][src rank]      round number (as a double-sized u64) the slot holds
+constexpr int XSLOT = 56;
+//   [.., + 1)                          next round number (persists across launches; every rank runs the same number of rounds)
+__host__ __device__ constexpr size_t xbuf_doubles(int world) { return (size_t)2 * world * XSLOT + 2 * world + 1; }
+
+struct Problem;
+__device__ void exchange_ranks(const Problem& P, Shared& S, cg::cluster_group& cluster);
+
 struct Problem {
     const double *pos, *uv, *disp, *uvcov, *dcov;
     int k;
     const int* k_dev;          // optional device-side block count (<= k): the observation kernel's survivor count
-    int min_k;                 // fewer blocks than this: leave the pose untouched (Odometry/MACVO.py:300-305)
+    int k_offset;              // sharded + k_dev: this rank owns global blocks [k_offset, k_offset + k) of the *k_dev valid ones
+    int min_k;                 // fewer (global) blocks than this: leave the pose untouched (Odometry/MACVO.py:300-305)
     double* singular_flag;     // stats + 7 or nullptr
+    // multi-GPU (residual blocks sharded across ranks, one process per GPU): every rank's exchange buffer, mapped into
+    // this process through CUDA IPC (peer memory over NVLink / NVSwitch); xbuf[rank] is this GPU's own buffer
+    double* xbuf[MACVO_PGO_MAX_RANKS];
+    int world, rank;
+
     Intr K;
     double delta;
 };
@@ -215,6 +233,7 @@ __device__ void accumulate_full(const Problem& P, const double* posevec, Shared&
         __syncwarp();
     }
     reduce_all(S, cluster, acc0, acc1, warp, lane);
+    if (P.world > 1) exchange_ranks(P, S, cluster);
 }
 
 // robust loss only: lane-per-residual-block
@@ -231,7 +250,56 @@ __device__ double evaluate_loss(const Problem& P, const double* posevec, Shared&
     }
     acc = warp_sum(acc);                     // butterfly: every lane holds the same bits
     reduce_all(S, cluster, 0.0, lane == 22 ? acc : 0.0, warp, lane);   // packed entry 54 = lane 22, slot 1
+    if (P.world > 1) exchange_ranks(P, S, cluster);
     return 0.0;
+}
+
+// All-reduce of the 55-double accumulator ACROSS GPUS inside the persistent kernel, over peer memory (the compute step and
+// its collective are one launch; no NCCL call, no host round trip per evaluation):
+//   CTA 0 of every rank's cluster stores its rank-local total into slot [parity][my rank] of EVERY rank's exchange buffer
+//   (plain st.global to IPC-mapped peer memory -> NVLink), fences at system scope, then releases one flag per peer holding
+//   the round number; it then spins (bounded) on the `world` flags of its own buffer, and every rank sums the partials in
+//   rank order -> identical bits everywhere, so the redundant accept / reject logic cannot diverge between GPUs.
+//   Two parities: a rank can run at most one round ahead of the slowest peer (it needs that peer's next partial to go on).
+__device__ void exchange_ranks(const Problem& P, Shared& S, cg::cluster_group& cluster) {
+    const unsigned long long round = S.round;          // stable: the caller's reduction ended with a cluster-wide sync
+    const int parity = (int)(round & 1ull);
+    const unsigned crank = cluster.block_rank();
+    if (crank == 0) {
+        const int W = P.world;
+        if (threadIdx.x < NACC) {
+            const double v = S.total[threadIdx.x];
+            for (int p = 0; p < W; ++p)
+                asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(P.xbuf[p] + ((size_t)parity * W + P.rank) * XSLOT + threadIdx.x), "d"(v) : "memory");
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < W) {
+            unsigned long long* peer_flag = reinterpret_cast<unsigned long long*>(P.xbuf[threadIdx.x] + (size_t)2 * W * XSLOT) + parity * W + P.rank;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(round + 1) : "memory");
+            const unsigned long long* my_flag = reinterpret_cast<const unsigned long long*>(P.xbuf[P.rank] + (size_t)2 * W * XSLOT) + parity * W + threadIdx.x;
+            const long long t0 = clock64();
+            unsigned long long seen;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(my_flag) : "memory");
+                if (seen != round + 1 && clock64() - t0 > 6000000000LL) __trap();     // ~3 s: a lost peer must not hang the GPU
+            } while (seen != round + 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < NACC) {
+            double s = 0.0;
+            for (int p = 0; p < W; ++p) {
+                double v;
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(P.xbuf[P.rank] + ((size_t)parity * W + p) * XSLOT + threadIdx.x) : "memory");
+                s += v;
+            }
+            S.total[threadIdx.x] = s;
+        }
+    }
+    cluster.sync();
+    if (crank != 0 && threadIdx.x < NACC) S.total[threadIdx.x] = cluster.map_shared_rank(&S.total[0], 0)[threadIdx.x];
+    if (threadIdx.x == 0) S.round = round + 1;
+    cluster.sync();
 }
 
 // ---- small dense algebra (thread 0 of each CTA) --------------------------------------------------------
@@ -323,8 +391,14 @@ pgo_lm_kernel(Problem P, double* __restrict__ pose_io, macvo_pgo_params_t prm, d
     const int gthread = rank * THREADS + threadIdx.x, nthreads = nblk * THREADS;
 
     if (threadIdx.x < 7) S.pose[threadIdx.x] = pose_io[threadIdx.x];
-    if (P.k_dev != nullptr) P.k = min(P.k, max(*P.k_dev, 0));
-    if (P.k < P.min_k) {        // lost track: every CTA of the cluster takes this branch together
+    if (threadIdx.x == 0)
+        S.round = P.world > 1 ? *reinterpret_cast<const unsigned long long*>(P.xbuf[P.rank] + xbuf_doubles(P.world) - 1) : 0ull;
+    int k_total = P.k;
+    if (P.k_dev != nullptr) {
+        k_total = max(*P.k_dev, 0);                                   // same value on every rank (broadcast with the data)
+        P.k = min(P.k, max(k_total - P.k_offset, 0));
+    }
+    if (k_total < P.min_k) {    // lost track: every CTA of the cluster (and every rank) takes this branch together
         if (rank == 0 && threadIdx.x == 0 && stats) {
             for (int i = 0; i < 6; ++i) stats[i] = 0.0;
             stats[6] = 1.0;                                       // skipped
@@ -424,6 +498,8 @@ pgo_lm_kernel(Problem P, double* __restrict__ pose_io, macvo_pgo_params_t prm, d
             stats[4] = reject_count; stats[5] = damping; stats[6] = 0;      // stats[7]: singular-block flag (set above)
         }
     }
+    if (P.world > 1 && rank == 0 && threadIdx.x == 0)
+        *reinterpret_cast<unsigned long long*>(P.xbuf[P.rank] + xbuf_doubles(P.world) - 1) = S.round;
     cluster.sync();     // no CTA may exit while a peer can still read its shared memory
 }
 
@@ -460,7 +536,7 @@ int launch_cluster(const void* fn, int cluster, void** args, cudaStream_t st) {
 static int pgo_solve_impl(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
                           const double* uv_cov, const double* disp_cov, int k, const int* k_dev, int min_k,
                           const double* intr, double* pose_io, const macvo_pgo_params_t* params, double* stats,
-                          void* stream) {
+                          void* stream, void* const* peer_bufs = nullptr, int world = 1, int rank = 0, int k_offset = 0) {
     if (k < 0 || !intr || !pose_io || !params) return MACVO_E_ARG;
     if (k > 0 && (!pos_Tw || !kp2_uv || !kp2_disp || !uv_cov || !disp_cov)) return MACVO_E_ARG;
     macvo_pgo_params_t prm = *params;
@@ -470,7 +546,16 @@ static int pgo_solve_impl(const double* pos_Tw, const double* kp2_uv, const doub
     if (cluster > 8) cluster = 8;
     Problem P;
     P.pos = pos_Tw; P.uv = kp2_uv; P.disp = kp2_disp; P.uvcov = uv_cov; P.dcov = disp_cov; P.k = k;
-    P.k_dev = k_dev; P.min_k = min_k; P.singular_flag = stats ? stats + 7 : nullptr;
+    P.k_dev = k_dev; P.k_offset = k_offset; P.min_k = min_k; P.singular_flag = stats ? stats + 7 : nullptr;
+    P.world = 1; P.rank = 0;
+    if (peer_bufs != nullptr) {
+        if (world < 2 || world > MACVO_PGO_MAX_RANKS || rank < 0 || rank >= world) return MACVO_E_ARG;
+        P.world = world; P.rank = rank;
+        for (int r = 0; r < world; ++r) {
+            if (!peer_bufs[r]) return MACVO_E_ARG;
+            P.xbuf[r] = static_cast<double*>(peer_bufs[r]);
+        }
+    }
     // intr is HOST memory: {fx, fy, cx, cy, baseline}
     P.K.fx = intr[0]; P.K.fy = intr[1]; P.K.cx = intr[2]; P.K.cy = intr[3]; P.K.bl = intr[4];
     P.delta = prm.huber_delta;
@@ -493,6 +578,53 @@ extern "C" int macvo_pgo_solve_counted(const double* pos_Tw, const double* kp2_u
                           stats, stream);
 }
 
+// ---- multi-GPU: sharded residual blocks, all-reduce fused into the persistent kernel over peer memory ---------------------
+extern "C" size_t macvo_pgo_exchange_bytes(int world) {
+    return world >= 1 && world <= MACVO_PGO_MAX_RANKS ? xbuf_doubles(world) * sizeof(double) : 0;
+}
+
+extern "C" int macvo_p2p_alloc(size_t bytes, void** dev_ptr, unsigned char* ipc_handle64) {
+    if (!dev_ptr || !ipc_handle64 || bytes == 0) return MACVO_E_ARG;
+    void* p = nullptr;
+    MACVO_CUDA_TRY(cudaMalloc(&p, bytes));
+    MACVO_CUDA_TRY(cudaMemset(p, 0, bytes));
+    MACVO_CUDA_TRY(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    MACVO_CUDA_TRY(cudaIpcGetMemHandle(&h, p));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    memcpy(ipc_handle64, &h, 64);
+    *dev_ptr = p;
+    return MACVO_OK;
+}
+
+extern "C" int macvo_p2p_open(const unsigned char* ipc_handle64, void** peer_ptr) {
+    if (!ipc_handle64 || !peer_ptr) return MACVO_E_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, 64);
+    MACVO_CUDA_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MACVO_OK;
+}
+
+extern "C" int macvo_p2p_close(void* peer_ptr) {
+    if (peer_ptr) MACVO_CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr));
+    return MACVO_OK;
+}
+
+extern "C" int macvo_p2p_free(void* dev_ptr) {
+    if (dev_ptr) MACVO_CUDA_TRY(cudaFree(dev_ptr));
+    return MACVO_OK;
+}
+
+extern "C" int macvo_pgo_solve_sharded(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
+                                       const double* uv_cov, const double* disp_cov, int k_shard, const int* k_total_dev,
+                                       int k_offset, int min_k, const double* intr, double* pose_io,
+                                       const macvo_pgo_params_t* params, double* stats, void* const* exchange_bufs,
+                                       int world, int rank, void* stream) {
+    if (!exchange_bufs || k_offset < 0 || min_k < 0) return MACVO_E_ARG;
+    return pgo_solve_impl(pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov, k_shard, k_total_dev, min_k, intr, pose_io, params, stats,
+                          stream, exchange_bufs, world, rank, k_offset);
+}
+
 extern "C" int macvo_pgo_accumulate(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
                                     const double* uv_cov, const double* disp_cov, int k, const double* intr,
                                     const double* pose, double huber_delta, double* acc, void* stream) {
@@ -500,7 +632,7 @@ extern "C" int macvo_pgo_accumulate(const double* pos_Tw, const double* kp2_uv, 
     if (k > 0 && (!pos_Tw || !kp2_uv || !kp2_disp || !uv_cov || !disp_cov)) return MACVO_E_ARG;
     Problem P;
     P.pos = pos_Tw; P.uv = kp2_uv; P.disp = kp2_disp; P.uvcov = uv_cov; P.dcov = disp_cov; P.k = k;
-    P.k_dev = nullptr; P.min_k = 0; P.singular_flag = nullptr;
+    P.k_dev = nullptr; P.k_offset = 0; P.min_k = 0; P.singular_flag = nullptr; P.world = 1; P.rank = 0;
     P.K.fx = intr[0]; P.K.fy = intr[1]; P.K.cx = intr[2]; P.K.cy = intr[3]; P.K.bl = intr[4];
     P.delta = huber_delta;
     void* args[] = {&P, &pose, &acc};

@@ -71,6 +71,13 @@ EXPORTS = {
     "macvo_observe_packed_doubles": (C.c_size_t, [C.c_int]),
     "macvo_observe_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p] * 2
                            + [C.c_int] + [C.c_float] * 3 + [C.c_void_p] * 6 + [C.c_size_t, C.c_void_p]),
+    "macvo_pgo_exchange_bytes": (C.c_size_t, [C.c_int]),
+    "macvo_p2p_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "macvo_p2p_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "macvo_p2p_close": (C.c_int, [C.c_void_p]),
+    "macvo_p2p_free": (C.c_int, [C.c_void_p]),
+    "macvo_pgo_solve_sharded": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 2
+                                + [C.POINTER(_PgoParams)] + [C.c_void_p] * 2 + [C.c_int, C.c_int, C.c_void_p]),
     "macvo_pgo_accumulate": (C.c_int, [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2 + [C.c_double]
                              + [C.c_void_p] * 2),
     "macvo_layer_norm": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
@@ -584,6 +591,73 @@ def pgo_solve_counted(buf: ObservationBuffers, intr: tuple[float, float, float, 
                                      C.byref(prm), stats.data_ptr(), _stream())
     _check(rc, "macvo_pgo_solve_counted")
     LAUNCHES[0] += 1
+
+
+class PeerExchange:
+    """This rank's exchange buffer for the sharded LM kernel + the peers' buffers mapped through CUDA IPC.
+
+    `handle` (64 bytes) must be all-gathered across the ranks (any transport: torch.distributed object / tensor gather),
+    then `connect(handles)` maps every peer. One process per GPU; all ranks of one node (NVLink / NVSwitch peer access)."""
+
+    def __init__(self, world: int, rank: int):
+        lib = load_library()
+        self.world, self.rank = int(world), int(rank)
+        self.nbytes = int(lib.macvo_pgo_exchange_bytes(self.world))
+        if self.nbytes == 0:
+            raise MacvoB200Error(f"PeerExchange: world size {world} not in [1, 8]")
+        ptr = C.c_void_p()
+        hbuf = C.create_string_buffer(64)
+        _check(lib.macvo_p2p_alloc(self.nbytes, C.byref(ptr), hbuf), "macvo_p2p_alloc")
+        self.own, self.handle = ptr.value, hbuf.raw
+        self.ptrs = None
+        self._opened: list[int] = []
+
+    def connect(self, handles: list[bytes]) -> None:
+        lib = load_library()
+        arr = (C.c_void_p * self.world)()
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                arr[r] = self.own
+                continue
+            p = C.c_void_p()
+            _check(lib.macvo_p2p_open(C.create_string_buffer(bytes(h), 64), C.byref(p)), "macvo_p2p_open")
+            arr[r] = p.value
+            self._opened.append(p.value)
+        self.ptrs = arr
+
+    def close(self) -> None:
+        lib = load_library()
+        for p in self._opened:
+            lib.macvo_p2p_close(p)
+        self._opened = []
+        if self.own:
+            lib.macvo_p2p_free(self.own)
+            self.own = None
+
+
+def pgo_solve_sharded(shard: list[Tensor], intr: tuple[float, float, float, float, float], init_pose: Tensor,
+                      exchange: PeerExchange, cluster: int = 0, k_total: Tensor | None = None, k_offset: int = 0,
+                      min_k: int = 0, pose_io: Tensor | None = None, stats: Tensor | None = None, **kw):
+    """This rank's part of the multi-GPU solve (csrc/pgo.cu: all-reduce fused into the persistent kernel over peer
+    memory). shard = this rank's [pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov] CUDA float64 slices; every rank must call
+    this with the same init_pose / parameters. Returns (pose (7,) float64 CUDA, stats (8,)); identical on all ranks."""
+    lib = load_library()
+    if exchange.ptrs is None:
+        raise MacvoB200Error("pgo_solve_sharded: PeerExchange.connect() has not been called")
+    P = [_dev(t, torch.float64, f"pgo_solve_sharded arg{i}") for i, t in enumerate(shard)]
+    K = P[0].shape[0]
+    pose = pose_io if pose_io is not None else _dev(init_pose, torch.float64, "pgo_solve_sharded init_pose").reshape(7).clone()
+    if stats is None:
+        stats = torch.zeros((8,), dtype=torch.float64, device=pose.device)
+    intr_c = (C.c_double * 5)(*[float(v) for v in intr])
+    prm = _pgo_params(cluster=cluster, **kw)
+    rc = lib.macvo_pgo_solve_sharded(*(t.data_ptr() for t in P), K, None if k_total is None else k_total.data_ptr(),
+                                     int(k_offset), int(min_k), C.cast(intr_c, C.c_void_p), pose.data_ptr(),
+                                     C.byref(prm), stats.data_ptr(), C.cast(exchange.ptrs, C.c_void_p), exchange.world,
+                                     exchange.rank, _stream())
+    _check(rc, "macvo_pgo_solve_sharded")
+    LAUNCHES[0] += 1
+    return pose, stats
 
 
 # ---- frontend "next" rows: memory-bound perceiver layers (csrc/nn_kernels.cu) ------------------------------

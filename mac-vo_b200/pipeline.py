@@ -160,9 +160,12 @@ class FusedTwoFrameOdometry:
 
     def __init__(self, frontend, kp_selector, cov_model, optimizer, num_point: int = 200, edgewidth: int = 32,
                  match_cov_default: float = 0.25, mapping: bool = True, map_selector=None, min_num_point: int = 10,
-                 num_map_point: int = 2000, keep_debug: bool = False):
+                 num_map_point: int = 2000, keep_debug: bool = False, solver=None):
         from . import ops
         self.ops = ops
+        # solver(obs, intr5, pose_io, stats, min_k): the LM solve on the packed observation buffer; default = one persistent
+        # launch on this GPU. bench.py --config sharded plugs in the multi-GPU solve (broadcast + sharded_pgo.FusedShardedPGO)
+        self.solver = solver
         self.frontend, self.kp_selector, self.cov_model, self.optimizer = frontend, kp_selector, cov_model, optimizer
         self.map_selector = map_selector
         self.num_point, self.edgewidth, self.match_cov_default = num_point, edgewidth, match_cov_default
@@ -216,7 +219,10 @@ class FusedTwoFrameOdometry:
                          match_cov_default=self.match_cov_default, **self.cov_args)
         bl = float(torch.as_tensor(frame1.frame_baseline, dtype=torch.float32).double().reshape(-1)[0])
         stats.zero_()
-        ops.pgo_solve_counted(obs, (*i1, bl), next_pose, stats, min_k=self.min_num_point, cluster=self.cluster)
+        if self.solver is not None:
+            self.solver(obs, (*i1, bl), next_pose, stats, self.min_num_point)
+        else:
+            ops.pgo_solve_counted(obs, (*i1, bl), next_pose, stats, min_k=self.min_num_point, cluster=self.cluster)
         self.pose_dev.append(next_pose)
         n_map = 0
         if self.mapping:

@@ -116,8 +116,70 @@ def lm_solve_sharded(accumulate: Callable[[np.ndarray], np.ndarray], allreduce: 
     return pose, {"steps": steps, "evaluations": evals, "collectives": collectives, "loss": loss}
 
 
+class FusedShardedPGO:
+    """The product path for BASELINE config 4: residual blocks sharded across the ranks of a `torch.distributed` group
+    (one process per GPU, one node), the whole Levenberg-Marquardt loop ONE persistent launch per rank with the
+    all-reduce of the 55-double accumulator fused into it over NVLink peer memory (`ops.pgo_solve_sharded`,
+    csrc/pgo.cu::exchange_ranks). torch.distributed is used once, at construction, to exchange the 64-byte CUDA IPC
+    handles of the exchange buffers; the solves themselves issue no collective call."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        from . import ops
+        self.ops, self.group = ops, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.exchange = ops.PeerExchange(self.world, self.rank)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.exchange.handle, group=group)
+        self.exchange.connect(handles)
+        dist.barrier(group)
+
+    def solve(self, pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov, intr, init_pose, cluster: int = 0):
+        """every rank passes the FULL (K, .) CUDA float64 arrays (e.g. after a broadcast of the packed observation buffer)
+        and works on its contiguous shard; returns (pose (7,) float64 CUDA, stats) — the same bits on every rank."""
+        lo, hi = shard_bounds(pos_Tw.shape[0], self.world, self.rank)
+        shard = [t[lo:hi].contiguous() for t in (pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov)]
+        return self.ops.pgo_solve_sharded(shard, intr, init_pose, self.exchange, cluster=cluster)
+
+    # ---- one stream, N GPUs (BASELINE config 4): rank `src` owns the frontend and the observation buffer ----------------
+    def solve_packed(self, obs, intr, pose_io, stats, min_k: int, src: int = 0):
+        """Collective over the group. Rank `src` passes its filled `ops.ObservationBuffers` + the initial pose in `pose_io`;
+        the other ranks pass their own (same capacity) buffers as receive space. Two NCCL broadcasts ship the five LM input
+        arrays (80 B per keypoint slot) and [survivor count | initial pose]; then every rank solves its capacity-shard with the
+        fused peer-memory all-reduce; `pose_io` holds the same optimised pose on every rank afterwards."""
+        import torch
+        import torch.distributed as dist
+        c = obs.capacity
+        if getattr(self, "_meta", None) is None:
+            self._meta = torch.zeros(8, dtype=torch.float64, device=obs.packed.device)
+            self._n = torch.zeros(1, dtype=torch.int32, device=obs.packed.device)
+        meta = self._meta
+        if self.rank == src:
+            meta[0:1] = obs.n_obs
+            meta[1:8] = pose_io
+        dist.broadcast(obs.packed[:10 * c], src=src, group=self.group)
+        dist.broadcast(meta, src=src, group=self.group)
+        if self.rank != src:
+            pose_io.copy_(meta[1:8])
+        self._n.copy_(meta[0:1])
+        lo, hi = shard_bounds(c, self.world, self.rank)
+        shard = [obs.section("pos_Tw")[lo:hi], obs.section("pixel2_uv")[lo:hi], obs.section("pixel2_disp")[lo:hi],
+                 obs.section("pixel2_uv_cov")[lo:hi], obs.section("pixel2_disp_cov")[lo:hi]]
+        self.ops.pgo_solve_sharded(shard, intr, None, self.exchange, k_total=self._n, k_offset=lo, min_k=min_k,
+                                   pose_io=pose_io, stats=stats)
+        return pose_io
+
+    def close(self) -> None:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier(self.group)          # no rank unmaps / frees a buffer a peer's kernel may still write
+        self.exchange.close()
+
+
 def solve_on_gpus(pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov, intr, init_pose, group=None):
-    """torch.distributed entry point: every rank passes the FULL (K, .) CUDA float64 tensors (or its own copy),
+    """NCCL baseline of `FusedShardedPGO` (host-driven LM loop, one `dist.all_reduce` + one device->host read per evaluation):
+    every rank passes the FULL (K, .) CUDA float64 tensors (or its own copy),
     works on its shard and all-reduces over NCCL. Returns (pose tensor (7,) float64 on the device, stats)."""
     import torch
     import torch.distributed as dist
