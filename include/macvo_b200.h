@@ -322,6 +322,9 @@ int macvo_query_prep(const float* query, const float* ln_weight, const float* ln
  * (the first five sections are exactly the arrays macvo_pgo_solve_counted reads). *n_obs = survivors (device int).
  * *status (zeroed by the caller): 1 = a covariance patch left the image (the reference raises IndexError).
  */
+/* CovarianceSanityFilter.filter (Module/OutlierFilter.py:91-100) on device-resident (k,3,3) float64 covariances:
+ * good[i] = 1 iff neither matrix of observation i holds a NaN / Inf. */
+int macvo_cov_sanity_filter(const double* obs1_cov, const double* obs2_cov, int k, uint8_t* good, void* stream);
 size_t macvo_observe_workspace_bytes(int capacity);
 size_t macvo_observe_packed_doubles(int capacity);
 int macvo_observe_pack(const int64_t* kp0_uv, int k, int capacity, const float* flow, const float* match_cov,

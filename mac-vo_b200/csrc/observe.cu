@@ -161,7 +161,26 @@ pack_kernel(const float* __restrict__ rec, const int64_t* __restrict__ kp0, int 
     }
 }
 
+// CovarianceSanityFilter.filter (Module/OutlierFilter.py:91-100) for device-resident covariances: one thread per observation
+__global__ void cov_sanity_kernel(const double* __restrict__ c1, const double* __restrict__ c2, int k, uint8_t* __restrict__ good) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    bool ok = true;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) ok &= isfinite(c1[9LL * i + e]) && isfinite(c2[9LL * i + e]);
+    good[i] = ok ? 1 : 0;
+}
+
 }  // namespace
+
+extern "C" int macvo_cov_sanity_filter(const double* obs1_cov, const double* obs2_cov, int k, uint8_t* good, void* stream) {
+    if (k < 0) return MACVO_E_ARG;
+    if (k == 0) return MACVO_OK;
+    if (!obs1_cov || !obs2_cov || !good) return MACVO_E_ARG;
+    cov_sanity_kernel<<<ceil_div(k, 256), 256, 0, as_stream(stream)>>>(obs1_cov, obs2_cov, k, good);
+    MACVO_LAUNCH_CHECK();
+    return MACVO_OK;
+}
 
 extern "C" size_t macvo_observe_workspace_bytes(int capacity) {
     return (size_t)capacity * REC * sizeof(float);

@@ -185,6 +185,23 @@ class ICovariance2to3(ABC, _Registry):
     def estimate(self, frame: StereoData, kp: torch.Tensor, depth_est, depth_cov, flow_cov) -> torch.Tensor: ...
 
 
+class IObservationFilter(ABC, _Registry):
+    """Module/OutlierFilter.py:13-41"""
+    _IS_INTERFACE = True
+
+    def __init__(self, config: SimpleNamespace) -> None:
+        self.config = config
+
+    def verify_shape(self, value) -> bool:
+        return all(k in value.data.keys() for k in self.required_keys)
+
+    def set_meta(self, meta) -> None:
+        return None
+
+    @abstractmethod
+    def filter(self, values, device: torch.device) -> torch.Tensor: ...
+
+
 class IOptimizer(ABC, _Registry):
     """Sequential-mode subset of Module/Optimization/Interface.py (a GPU optimiser runs `parallel: false`:
     its asynchrony is the CUDA stream, not a spawned process)."""

@@ -67,6 +67,7 @@ EXPORTS = {
                         + [C.c_void_p] * 2),
     "macvo_pgo_solve_counted": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 2
                                 + [C.POINTER(_PgoParams)] + [C.c_void_p] * 2),
+    "macvo_cov_sanity_filter": (C.c_int, [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2),
     "macvo_observe_workspace_bytes": (C.c_size_t, [C.c_int]),
     "macvo_observe_packed_doubles": (C.c_size_t, [C.c_int]),
     "macvo_observe_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p] * 2
@@ -544,6 +545,17 @@ class ObservationBuffers:
         """ONE asynchronous device->host copy of the whole frame's observations; `self.ready` fires when it landed."""
         self.host.copy_(self.packed, non_blocking=True)
         self.ready.record()
+
+
+def cov_sanity_filter(obs1_cov: Tensor, obs2_cov: Tensor) -> Tensor:
+    """(K,3,3) float64 CUDA x2 -> bool (K,) mask of observations whose covariances are finite (OutlierFilter.py:91-100)"""
+    a, b = _dev(obs1_cov, torch.float64, "cov_sanity_filter obs1"), _dev(obs2_cov, torch.float64, "cov_sanity_filter obs2")
+    k = a.shape[0]
+    good = torch.empty((k,), dtype=torch.uint8, device=a.device)
+    _check(load_library().macvo_cov_sanity_filter(a.data_ptr(), b.data_ptr(), k, good.data_ptr(), _stream()),
+           "macvo_cov_sanity_filter")
+    LAUNCHES[0] += 1
+    return good.bool()
 
 
 def observe_pack(buf: ObservationBuffers, kp0_uv: Tensor, flow: Tensor, match_cov: Tensor, depth0: Tensor, depth1: Tensor,

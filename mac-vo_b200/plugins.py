@@ -5,6 +5,7 @@
     B200_CovAwareSelector            IKeypointSelector  replaces CovAwareSelector (KeypointSelector.py:250-347)
     B200_MappingPointSelector        IKeypointSelector  replaces MappingPointSelector (KeypointSelector.py:78-100)
     B200_MatchCovariance             ICovariance2to3    replaces MatchCovariance (Covariance/Project2to3.py:114-182)
+    B200_CovarianceSanityFilter      IObservationFilter replaces CovarianceSanityFilter (OutlierFilter.py:91-100)
     B200_TwoFrame_PGO                IOptimizer         replaces TwoFrame_PGO (Optimization/TwoFramePGO/Optimizer.py:23-108)
 
 Same constructor signature (`__init__(config: SimpleNamespace)`), same `is_valid_config` contract
@@ -35,12 +36,14 @@ if _REF:   # subclass MAC-VO's own interfaces so that importing this module regi
     from Module.Frontend.Matching import IMatcher  # type: ignore
     from Module.KeypointSelector import IKeypointSelector  # type: ignore
     from Module.Covariance.Project2to3 import ICovariance2to3  # type: ignore
+    from Module.OutlierFilter import IObservationFilter  # type: ignore
     from Module.Optimization.TwoFramePGO.Optimizer import TwoFrame_PGO as _PGOBase  # type: ignore
     from Module.Optimization.TwoFramePGO.Graphs import GraphOutput as _RefGraphOutput  # type: ignore
 else:
     StereoData = _local.StereoData
     IFrontend, IStereoDepth, IMatcher = _local.IFrontend, _local.IStereoDepth, _local.IMatcher
     IKeypointSelector, ICovariance2to3 = _local.IKeypointSelector, _local.ICovariance2to3
+    IObservationFilter = _local.IObservationFilter
     _PGOBase = _local.IOptimizer
 
 _DTYPES = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
@@ -388,6 +391,35 @@ class B200_MatchCovariance(ICovariance2to3):
 
 
 # ================================================================================================
+# Observation filter
+# ================================================================================================
+class B200_CovarianceSanityFilter(IObservationFilter):
+    """Replacement of CovarianceSanityFilter (Module/OutlierFilter.py:91-100): drops observations whose 3x3 covariances
+    hold a NaN / Inf. Device-resident covariances (a caller that keeps MatchObs on the GPU, e.g.
+    `pipeline.FusedTwoFrameOdometry`, where the same test runs inside `observe_kernel`) go through
+    `macvo_cov_sanity_filter`; the CPU float64 tensors `Odometry/MACVO.py:246-270` builds are tested where they live —
+    uploading 2 x K x 72 bytes to test them would cost more than the test."""
+
+    @property
+    def required_keys(self) -> set:
+        return {"obs1_covTc", "obs2_covTc"}
+
+    @torch.inference_mode()
+    def filter(self, values, device: torch.device) -> torch.Tensor:
+        c1, c2 = values.data["obs1_covTc"], values.data["obs2_covTc"]
+        c1 = c1.tensor if hasattr(c1, "tensor") and not isinstance(c1, torch.Tensor) else c1
+        c2 = c2.tensor if hasattr(c2, "tensor") and not isinstance(c2, torch.Tensor) else c2
+        if c1.is_cuda and c2.is_cuda and c1.dtype == torch.float64 and c2.dtype == torch.float64:
+            return ops.cov_sanity_filter(c1, c2).to(device)
+        bad = c1.isnan().any(dim=(-1, -2)) | c1.isinf().any(dim=(-1, -2)) | c2.isnan().any(dim=(-1, -2)) | c2.isinf().any(dim=(-1, -2))
+        return (~bad).to(device)
+
+    @classmethod
+    def is_valid_config(cls, config: SimpleNamespace | None) -> None:
+        return
+
+
+# ================================================================================================
 # Two-frame pose-graph optimisation
 # ================================================================================================
 @dataclass
@@ -468,5 +500,6 @@ PLUGINS = {
     "keypoint_depth": B200_CovAwareSelector,
     "mappoint": B200_MappingPointSelector,
     "cov": B200_MatchCovariance,
+    "outlier": B200_CovarianceSanityFilter,
     "optimizer": B200_TwoFrame_PGO,
 }
