@@ -179,7 +179,8 @@ def time_corr_kernel(device: str, iters: int = 10) -> dict:
         times.append(s.elapsed_time(e) * 1e-3)
     n = (H // 8) * (W // 8)
     algo_bytes = 2 * (4 * n * n + 8 * n * 256)                             # 4 N^2 + 2*4*N*D per pair
-    return {"seconds": sum(times) / len(times), "bytes": algo_bytes}
+    mode = ops.default_corr_mode(256, n)
+    return {"seconds": sum(times) / len(times), "bytes": algo_bytes, "mode": ops.CORR_MODE_NAMES[mode]}
 
 
 def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
@@ -251,10 +252,15 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(REPO, "profiles", "corr_tc_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    if os.path.exists(tpath):       # NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture
+        tj = json.load(open(tpath))
+        traffic = tj.get(corr["mode"], tj).get("dram_bytes_per_launch")
+        traffic_src = tj.get(corr["mode"], tj).get("source")
+    kernel_names = {"tf32": "macvo_corr_build: corr_tc_kernel<2> (tcgen05 kind::tf32, one pass over the fp32 K-major features, no pre-pass)",
+                    "tc3": "macvo_corr_build: fp16 hi/lo operand split + corr_tc_kernel<3>",
+                    "tc1": "macvo_corr_build: fp16 operand rounding + corr_tc_kernel<1>", "simt": "corr_simt_kernel"}
     achieved = corr["bytes"] / corr["seconds"] / 1e9
     out = {
         "metric": METRIC, "value": world * steps / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": steps,
@@ -265,8 +271,10 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
                    "streams": world, "parallelism": "replicas only (one independent stream per GPU, no collective)",
                    "l2": "per-frame working set (184 MB correlation volume + >1 GB activations) exceeds the 126 MB L2; "
                          "the corr roofline loop flushes L2 with a 256 MB write between launches",
-                   "matmul_precision": "TF32 for the cuDNN/cuBLAS layers like the reference frontend (Frontend.py:275-277); "
-                                       "correlation volume fp32-class (3 x fp16 split, fp32 accumulate)"},
+                   "matmul_precision": "TF32 like the reference GPU frontend (Frontend.py:275-277): cuDNN / cuBLAS layers, our attention / "
+                                       "PatchEmbed kernels and the correlation volume (kind::tf32); token path, LayerNorm, lookup, "
+                                       "post-processing, covariance fp32; LM fp64. Parity of this mode at this shape: "
+                                       "tests/test_gpu_parity_ladder.py (flow 9e-4 of its scale vs float64 truth; strict-fp32 mode 2.5e-6)"},
         # e2e: pinned HOST images in, optimised pose + the frame's packed observations / mapping points out, through the
         # package's public driver (FusedTwoFrameOdometry over the C ABI); each image crosses PCIe once (2 per frame)
         "e2e": {"value": world * steps / (ms_e2e * 1e-3), "unit": "frames/s",
@@ -277,8 +285,10 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
         "e2e_plugin_api": {"value": world * steps / (ms_api * 1e-3), "unit": "frames/s"},
         "gpu_launches": launches,
         "clocks": clk.summary(),
-        "roofline": {"kernel": "macvo_corr_build (fp16 hi/lo operand split + corr_tc_kernel<3>), B=2 D=256 N=4800, channels_last features", "bound": "hbm",
+        "roofline": {"kernel": kernel_names[corr["mode"]] + ", B=2 D=256 N=4800, channels_last features (the mode the frontend "
+                               "uses under its allow_tf32 setting)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": corr["bytes"],
                      "launch_seconds": corr["seconds"]},
     }

@@ -347,6 +347,15 @@ size_t macvo_decoder_token_blob_floats(void);
 int macvo_decoder_token(const float* cost_forward, const float* coords, const float* key, const float* value,
                         const float* weight_blob, float* out, int batch, int n1, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (f4) trajectory post-process at terminate(): MotionInterpolate.elaborate_map (Module/MapProcessor.py:52-79) with
+ *      interpolate_pose / NormalizeQuat (Utility/Math.py:96-135). poses (F,7) fp32 [t, q_xyzw] updated in place
+ *      (row 0 untouched), need_interp (F) bytes; *n_interp (optional) = number of interpolated relative motions.
+ */
+size_t macvo_motion_interpolate_workspace_bytes(int num_frames);
+int macvo_motion_interpolate(float* poses, const uint8_t* need_interp, int num_frames, int* n_interp, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -202,6 +202,17 @@ class IObservationFilter(ABC, _Registry):
     def filter(self, values, device: torch.device) -> torch.Tensor: ...
 
 
+class IMapProcessor(ABC, _Registry):
+    """Module/MapProcessor.py:12-25"""
+    _IS_INTERFACE = True
+
+    def __init__(self, config: SimpleNamespace | None) -> None:
+        self.config = config
+
+    @abstractmethod
+    def elaborate_map(self, frames): ...
+
+
 class IOptimizer(ABC, _Registry):
     """Sequential-mode subset of Module/Optimization/Interface.py (a GPU optimiser runs `parallel: false`:
     its asynchrony is the CUDA stream, not a spawned process)."""

@@ -67,6 +67,8 @@ EXPORTS = {
                         + [C.c_void_p] * 2),
     "macvo_pgo_solve_counted": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 2
                                 + [C.POINTER(_PgoParams)] + [C.c_void_p] * 2),
+    "macvo_motion_interpolate_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "macvo_motion_interpolate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "macvo_cov_sanity_filter": (C.c_int, [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2),
     "macvo_observe_workspace_bytes": (C.c_size_t, [C.c_int]),
     "macvo_observe_packed_doubles": (C.c_size_t, [C.c_int]),
@@ -545,6 +547,26 @@ class ObservationBuffers:
         """ONE asynchronous device->host copy of the whole frame's observations; `self.ready` fires when it landed."""
         self.host.copy_(self.packed, non_blocking=True)
         self.ready.record()
+
+
+def motion_interpolate_(poses: Tensor, need_interp: Tensor) -> Tensor:
+    """MotionInterpolate.elaborate_map (Module/MapProcessor.py:52-79) in place on (F,7) fp32 CUDA poses; need_interp (F,)
+    bool / uint8. Returns the device int32 count of interpolated motions."""
+    lib = load_library()
+    p = poses
+    if not (p.is_cuda and p.dtype == torch.float32 and p.dim() == 2 and p.shape[1] == 7 and p.is_contiguous()):
+        raise MacvoB200Error("motion_interpolate_: poses must be a contiguous (F,7) fp32 CUDA tensor")
+    ni = _dev(need_interp.to(torch.uint8) if need_interp.dtype != torch.uint8 else need_interp, torch.uint8, "need_interp")
+    F_ = p.shape[0]
+    if ni.numel() != F_:
+        raise MacvoB200Error("motion_interpolate_: need_interp must have one flag per frame")
+    count = torch.zeros((1,), dtype=torch.int32, device=p.device)
+    nbytes = lib.macvo_motion_interpolate_workspace_bytes(F_)
+    ws = _workspace("motion", nbytes, p.device) if nbytes else None
+    _check(lib.macvo_motion_interpolate(p.data_ptr(), ni.data_ptr(), F_, count.data_ptr(),
+                                        ws.data_ptr() if ws is not None else None, nbytes, _stream()), "macvo_motion_interpolate")
+    LAUNCHES[0] += 1
+    return count
 
 
 def cov_sanity_filter(obs1_cov: Tensor, obs2_cov: Tensor) -> Tensor:

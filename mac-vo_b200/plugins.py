@@ -6,6 +6,7 @@
     B200_MappingPointSelector        IKeypointSelector  replaces MappingPointSelector (KeypointSelector.py:78-100)
     B200_MatchCovariance             ICovariance2to3    replaces MatchCovariance (Covariance/Project2to3.py:114-182)
     B200_CovarianceSanityFilter      IObservationFilter replaces CovarianceSanityFilter (OutlierFilter.py:91-100)
+    B200_MotionInterpolate           IMapProcessor      replaces MotionInterpolate (MapProcessor.py:52-79)
     B200_TwoFrame_PGO                IOptimizer         replaces TwoFrame_PGO (Optimization/TwoFramePGO/Optimizer.py:23-108)
 
 Same constructor signature (`__init__(config: SimpleNamespace)`), same `is_valid_config` contract
@@ -37,13 +38,14 @@ if _REF:   # subclass MAC-VO's own interfaces so that importing this module regi
     from Module.KeypointSelector import IKeypointSelector  # type: ignore
     from Module.Covariance.Project2to3 import ICovariance2to3  # type: ignore
     from Module.OutlierFilter import IObservationFilter  # type: ignore
+    from Module.MapProcessor import IMapProcessor  # type: ignore
     from Module.Optimization.TwoFramePGO.Optimizer import TwoFrame_PGO as _PGOBase  # type: ignore
     from Module.Optimization.TwoFramePGO.Graphs import GraphOutput as _RefGraphOutput  # type: ignore
 else:
     StereoData = _local.StereoData
     IFrontend, IStereoDepth, IMatcher = _local.IFrontend, _local.IStereoDepth, _local.IMatcher
     IKeypointSelector, ICovariance2to3 = _local.IKeypointSelector, _local.ICovariance2to3
-    IObservationFilter = _local.IObservationFilter
+    IObservationFilter, IMapProcessor = _local.IObservationFilter, _local.IMapProcessor
     _PGOBase = _local.IOptimizer
 
 _DTYPES = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
@@ -420,6 +422,39 @@ class B200_CovarianceSanityFilter(IObservationFilter):
 
 
 # ================================================================================================
+# Map post-processing
+# ================================================================================================
+class B200_MotionInterpolate(IMapProcessor):
+    """Replacement of MotionInterpolate.elaborate_map (Module/MapProcessor.py:52-79), run once at `MACVO.terminate()`:
+    relative motions, se3-linear interpolation of the `need_interp` ones, re-integration with quaternion renormalisation —
+    one kernel launch (csrc/motion_interp.cu) instead of a Python loop of F pypose compositions. config: {device}."""
+
+    def __init__(self, config: SimpleNamespace | None):
+        super().__init__(config)
+        self.device = _require_cuda(getattr(config, "device", "cuda"), "B200_MotionInterpolate")
+
+    @torch.inference_mode()
+    def elaborate_map(self, frames):
+        pose_store, flag_store = frames.data["pose"], frames.data["need_interp"]
+        poses = pose_store.tensor if hasattr(pose_store, "tensor") and not isinstance(pose_store, torch.Tensor) else pose_store
+        flags = flag_store.tensor if hasattr(flag_store, "tensor") and not isinstance(flag_store, torch.Tensor) else flag_store
+        n = poses.shape[0]
+        bad = flags[1:].bool().clone()
+        bad[:2] = False
+        bad[-2:] = False
+        interp_idx = torch.nonzero(bad).flatten()
+        if n >= 2:
+            dev_poses = poses.to(device=self.device, dtype=torch.float32).contiguous()
+            ops.motion_interpolate_(dev_poses, flags.to(self.device))
+            frames.data["pose"][1:] = dev_poses[1:].to(poses.device)
+        return frames, interp_idx
+
+    @classmethod
+    def is_valid_config(cls, config: SimpleNamespace | None) -> None:
+        cls._enforce_config_spec(config, {"device": lambda d: isinstance(d, str) and "cuda" in d})
+
+
+# ================================================================================================
 # Two-frame pose-graph optimisation
 # ================================================================================================
 @dataclass
@@ -501,5 +536,6 @@ PLUGINS = {
     "mappoint": B200_MappingPointSelector,
     "cov": B200_MatchCovariance,
     "outlier": B200_CovarianceSanityFilter,
+    "postprocess": B200_MotionInterpolate,
     "optimizer": B200_TwoFrame_PGO,
 }

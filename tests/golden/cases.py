@@ -247,6 +247,24 @@ def cfgA_sample(name: str, t: Tensor) -> Tensor:
     raise KeyError(name)
 
 
+# ---- trajectory post-process (MotionInterpolate) ----------------------------------------------------------------------
+MOTION_CASES = {"f40": (40, 3, (1, 5, 6, 7, 15, 22, 23, 37, 38)), "f600": (600, 4, tuple(range(10, 590, 7)) + (300, 301, 302, 303)),
+                "f5": (5, 5, (1, 2, 3)), "f3": (3, 6, (1,))}
+
+
+def motion_inputs(F: int, seed: int, flagged: tuple) -> tuple[Tensor, Tensor]:
+    """a random-walk trajectory (F,7) fp32 [t, q_xyzw] and the need_interp flags"""
+    from oracle import pgo as opgo
+    rng = np.random.default_rng(seed)
+    poses = [np.array([0.3, -0.2, 0.1, 0, 0, 0, 1.0])]
+    for _ in range(F - 1):
+        step = np.concatenate([rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.05, 0.05, 3)])
+        poses.append(opgo.se3_mul(poses[-1], opgo.se3_exp(step)))
+    need = np.zeros(F, dtype=bool)
+    need[list(flagged)] = True
+    return torch.tensor(np.stack(poses), dtype=torch.float32), torch.tensor(need)
+
+
 def golden_input_shas() -> dict:
     """file name -> sha256 of the inputs each golden file was generated from (recomputed on THIS host)"""
     out = {}
@@ -269,4 +287,7 @@ def golden_input_shas() -> dict:
     for name, (K, seed) in PGO_CASES.items():
         c = pgo_inputs(K, seed)
         out[f"pgo_{name}.pt"] = sha(*[c[k] for k in ("pos_Tw", "kp2_uv", "kp2_disp", "uv_cov", "disp_cov")])
+    for name, (F, seed, flagged) in MOTION_CASES.items():
+        p, n = motion_inputs(F, seed, flagged)
+        out[f"motion_{name}.pt"] = sha(p, n.to(torch.uint8))
     return out

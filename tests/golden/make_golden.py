@@ -38,6 +38,11 @@ def save(name: str, obj: dict) -> None:
 
 
 def main() -> None:
+    only = sys.argv[1] if len(sys.argv) > 1 else None      # e.g. `make_golden.py motion` regenerates one family
+    global save
+    if only:
+        _save = save
+        save = lambda name, obj: _save(name, obj) if name.startswith(only) else None
     refharness.install()
     torch.set_num_threads(8)
     import Module  # noqa: F401  (registers every plugin class)
@@ -166,6 +171,19 @@ def main() -> None:
         finally:
             torch.cuda.current_stream = _cs
         save(f"pgo_{name}.pt", {"K": K, "seed": seed, "input_sha": cases.sha(*[c[k] for k in ("pos_Tw", "kp2_uv", "kp2_disp", "uv_cov", "disp_cov")]), "pose": out.motion.detach().as_subclass(torch.Tensor).clone().reshape(7)})
+
+    # ---- trajectory post-process at terminate() (f4) --------------------------------------------
+    from Module.MapProcessor import MotionInterpolate
+    from Module.Map import VisualMap, FrameNode
+    for name, (F, seed, flagged) in cases.MOTION_CASES.items():
+        poses, need = cases.motion_inputs(F, seed, flagged)
+        m = VisualMap()
+        for i in range(F):
+            m.frames.push(FrameNode.init({"pose": poses[i:i + 1].clone(), "T_BS": pp.identity_SE3(1), "need_interp": need[i:i + 1].clone(),
+                                          "time_ns": torch.tensor([i]), "K": torch.eye(3).unsqueeze(0), "baseline": torch.tensor([0.25])}))
+        _, idx = MotionInterpolate(SimpleNamespace()).elaborate_map(m.frames)
+        save(f"motion_{name}.pt", {"F": F, "seed": seed, "flagged": flagged, "out": m.frames.data["pose"].tensor.clone(),
+                                   "interp_idx": idx.clone(), "input_sha": cases.sha(poses, need.to(torch.uint8))})
 
 
 if __name__ == "__main__":

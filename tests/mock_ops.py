@@ -74,6 +74,13 @@ def install() -> None:
         return cov, None, torch.zeros(1, dtype=torch.int32)
     ops.match_covariance = match_covariance
 
+    def motion_interpolate_(poses, need_interp):
+        from oracle import map_processor as omp
+        out, idx = omp.motion_interpolate(poses.numpy(), need_interp.numpy().astype(bool))
+        poses.copy_(torch.from_numpy(out))
+        return torch.tensor([len(idx)], dtype=torch.int32)
+    ops.motion_interpolate_ = motion_interpolate_
+
     def pgo_solve(pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov, intr, init_pose, cluster=0, **kw):
         g = opgo.GraphData(pos_Tw=pos_Tw.numpy(), kp2_uv=kp2_uv.numpy(), kp2_disp=kp2_disp.numpy().reshape(-1),
                            uv_cov=uv_cov.numpy(), disp_cov=disp_cov.numpy().reshape(-1), fx=intr[0], fy=intr[1],

@@ -433,3 +433,39 @@ def test_pgo_solve_counted_reads_block_count_on_device(ops):
     stats.zero_()
     ops.pgo_solve_counted(buf, a[5], pose2, stats, min_k=10)
     assert torch.equal(pose2, a[6]) and stats[6].item() == 1.0
+
+
+# ---- (f4) trajectory post-process ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.MOTION_CASES))
+def test_motion_interpolate_kernel(ops, golden, name):
+    """csrc/motion_interp.cu vs the reference's MotionInterpolate (golden) and the fp64 oracle: fp32 output of fp64
+    arithmetic -> 2e-6 of the trajectory extent (blocked scan vs sequential fold differ at fp64 rounding only)."""
+    from oracle import map_processor as omp
+    g = golden(f"motion_{name}.pt")
+    poses, need = cases.motion_inputs(g["F"], g["seed"], g["flagged"])
+    d = poses.to(DEV).contiguous()
+    count = ops.motion_interpolate_(d, need.to(DEV))
+    tol = 2e-6 * max(1.0, float(g["out"].abs().max()))
+    np.testing.assert_allclose(d.cpu().numpy(), g["out"].numpy(), rtol=0, atol=tol)
+    ref, idx = omp.motion_interpolate(poses.numpy(), need.numpy())
+    np.testing.assert_allclose(d.cpu().numpy(), ref, rtol=0, atol=tol)
+    assert int(count.item()) == len(idx) and torch.equal(d[0].cpu(), poses[0])
+
+
+def test_motion_interpolate_long_sequence_blocked_scan(ops):
+    """F = 5000 (chunks of 5 motions per thread): the blocked scan must equal the sequential fold of the oracle"""
+    from oracle import map_processor as omp
+    poses, need = cases.motion_inputs(5000, 11, tuple(range(50, 4900, 13)))
+    d = poses.to(DEV).contiguous()
+    ops.motion_interpolate_(d, need.to(DEV))
+    ref, _ = omp.motion_interpolate(poses.numpy(), need.numpy())
+    np.testing.assert_allclose(d.cpu().numpy(), ref, rtol=0, atol=3e-6 * float(np.abs(ref).max()))
+
+
+def test_cov_sanity_filter_kernel(ops):
+    g = torch.Generator().manual_seed(1)
+    c1, c2 = torch.randn(300, 3, 3, generator=g).double(), torch.randn(300, 3, 3, generator=g).double()
+    c1[5, 1, 2] = float("nan"); c2[17, 0, 0] = float("inf"); c1[200, 2, 2] = -float("inf"); c2[299, 1, 1] = float("nan")
+    good = ops.cov_sanity_filter(c1.to(DEV), c2.to(DEV)).cpu()
+    bad = c1.isnan().any(dim=(-1, -2)) | c1.isinf().any(dim=(-1, -2)) | c2.isnan().any(dim=(-1, -2)) | c2.isinf().any(dim=(-1, -2))
+    assert torch.equal(good, ~bad) and int((~good).sum()) == 4

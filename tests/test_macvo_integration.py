@@ -46,7 +46,7 @@ def config(b200):
                                                            NS(device="cpu", max_depth=5.0, max_depth_cov=0.005, mask_width=32))),
         frontend=NS(type=t("FlowFormerCovFrontend"), args=fe_args),
         motion=NS(type="StaticMotionModel", args=NS()), outlier=NS(type=t("CovarianceSanityFilter"), args=NS()),
-        postprocess=NS(type="MotionInterpolate", args=NS()), keyframe=NS(type="AllKeyframe", args=NS()),
+        postprocess=NS(type=t("MotionInterpolate"), args=(NS(device="cpu") if b200 else NS())), keyframe=NS(type="AllKeyframe", args=NS()),
         optimizer=NS(type=t("TwoFrame_PGO"), args=NS(device="cpu", vectorize=True, parallel=False, graph_type="disp", autodiff=False))))
 
 def run(b200):

@@ -196,3 +196,17 @@ def test_golden_inputs_reproduce_bit_for_bit(golden):
     on the GPU hosts."""
     for name, digest in cases.golden_input_shas().items():
         assert golden(name)["input_sha"] == digest, f"{name}: inputs generated on this host differ from the fixture's"
+
+
+@pytest.mark.parametrize("name", list(cases.MOTION_CASES))
+def test_motion_interpolate_oracle_matches_reference(golden, name):
+    """oracle/map_processor.py vs the reference's MotionInterpolate.elaborate_map (MapProcessor.py:52-79) executed on the
+    pypose shim: incl. runs of consecutive lost frames, flags inside the protected first / last two motions, F = 3 and 5."""
+    from oracle import map_processor as omp
+    g = golden(f"motion_{name}.pt")
+    poses, need = cases.motion_inputs(g["F"], g["seed"], g["flagged"])
+    out, idx = omp.motion_interpolate(poses.numpy(), need.numpy())
+    np.testing.assert_allclose(out, g["out"].numpy(), rtol=0, atol=2e-6 * max(1.0, float(g["out"].abs().max())))
+    assert idx.tolist() == g["interp_idx"].tolist()
+    flagged_motion = [i - 1 for i in g["flagged"] if 2 <= i - 1 < g["F"] - 3]
+    assert idx.tolist() == sorted(flagged_motion)
