@@ -36,7 +36,7 @@ METRIC = "stereo frames/sec @640x480"
 H, W = 480, 640
 CONFIGS = {
     "performant": dict(enc_dtype="fp32", dec_dtype="fp32", num_point=200),     # Config/Experiment/MACVO/MACVO_Performant.yaml
-    "fast": dict(enc_dtype="fp16", dec_dtype="bf16", num_point=200),           # Config/Experiment/MACVO/MACVO_Fast.yaml
+    "fast": dict(enc_dtype="fp16", dec_dtype="bf16", num_point=2048),          # MACVO_Fast.yaml dtypes, BASELINE configs[2]: 2048 keypoints
 }
 SEQ_LEN = 8     # distinct synthetic frames, cycled (forwards / backwards) by the timed loop
 SHARDED = dict(H=720, W=1280, num_point=4096)          # BASELINE configs[3]: one 1280x720 stream, GN blocks over N GPUs
@@ -44,8 +44,9 @@ SHARDED = dict(H=720, W=1280, num_point=4096)          # BASELINE configs[3]: on
 
 def workload_name(cfg: dict) -> str:
     """one name for the workload, shared by both arms' `config`"""
-    return (f"640x480 synthetic stereo sequence, MACVO_{'Performant' if cfg['enc_dtype'] == 'fp32' else 'Fast'} settings "
-            f"({cfg['num_point']} keypoints, mapping on, decoder_depth 12), BASELINE configs[1]")
+    fast = cfg["enc_dtype"] != "fp32"
+    return (f"640x480 synthetic stereo sequence, MACVO_{'Fast' if fast else 'Performant'} settings "
+            f"({cfg['num_point']} keypoints, mapping on, decoder_depth 12), BASELINE configs[{2 if fast else 1}]")
 
 
 def _dist():
@@ -265,7 +266,7 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
     out = {
         "metric": METRIC, "value": world * steps / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if cfg["enc_dtype"] == "fp32" else "f16/bf16 mixed",
+        "vs_baseline": None, "dtype": "f32" if cfg["enc_dtype"] == "fp32" else "f32 (MACVO_Fast fp16/bf16 request served by the TF32 pipeline, half_precision=tf32)",
         "data": "synthetic (seeded smoothed-noise TartanAir-shape stereo sequence, synthetic:0 network weights)",
         "config": {"workload": workload_name(cfg),
                    "streams": world, "parallelism": "replicas only (one independent stream per GPU, no collective)",

@@ -274,6 +274,7 @@ def golden_input_shas() -> dict:
         out[f"lookup_{name}.pt"] = sha(*lookup_inputs(B, H1, W1))
     for name, (B, H, W) in NET_CASES.items():
         out[f"net_{name}.pt"] = sha(*net_inputs(B, H, W))
+    out["net_fast_small.pt"] = sha(*net_inputs(*NET_CASES["small"]))
     for name, (H, W) in DENSE_CASES.items():
         for epd in (0, 1):
             out[f"dense_{name}_{epd}.pt"] = sha(*dense_inputs(H, W))

@@ -85,6 +85,21 @@ def main() -> None:
         flow, cov = model.inference(img1, img2)
         save(f"net_{name}.pt", {"shape": (B, H, W), "flow": flow.clone(), "cov": cov.clone(), "input_sha": cases.sha(img1, img2)})
 
+    # ---- MACVO_Fast numerics (enc fp16 / dec bf16) of the reference + float64 truth of the same input ----------------
+    from oracle import frontend as _ofe
+    from macvo_b200.flowformer_cov import FlowFormerCovNet as _Net
+    fast = build_flowformer(cfg, torch.float16, torch.bfloat16).eval()
+    fast.load_state_dict(synthetic_state_dict(0))
+    B, H, W = cases.NET_CASES["small"]
+    img1, img2 = cases.net_inputs(B, H, W)
+    ff, fc = fast.inference(img1, img2)
+    net64 = _Net(synthetic_state_dict(0), "cpu", torch.float64, torch.float64, corr_fn=_ofe.corr_volume, lookup_fn=_ofe.window_lookup)
+    tf, tc = net64.inference(img1.double(), img2.double())
+    save("net_fast_small.pt", {"shape": (B, H, W), "flow": ff.float().clone(), "cov": fc.float().clone(), "truth_flow": tf.clone(),
+                               "truth_cov": tc.clone(), "input_sha": cases.sha(img1, img2),
+                               "floor": {"flow_rel": ((ff.double() - tf).abs().max() / tf.abs().mean()).item(),
+                                         "cov_rel_max": ((fc.double() - tc).abs() / tc.abs()).max().item()}})
+
     # ---- dense post-processing (a7) ---------------------------------------------------------
     def stereo(H, W, fx, bl):
         return StereoData(T_BS=None, K=torch.tensor([[[fx, 0., W / 2], [0., fx, H / 2], [0., 0., 1.]]]),
