@@ -256,6 +256,9 @@ int macvo_pgo_accumulate(const double* pos_Tw, const double* kp2_uv, const doubl
 /* y = LayerNorm(x) over the last dim; x, y (rows, channels) contiguous; channels in {64, 128, 256, 512}. */
 int macvo_layer_norm(const float* x, const float* weight, const float* bias, float* y, long long rows,
                      int channels, float eps, void* stream);
+/* sum_out = x + resid; y = LayerNorm(sum_out) in one pass (channels in {128, 256, 512}); sum_out may alias x or resid. */
+int macvo_add_layer_norm(const float* x, const float* resid, const float* weight, const float* bias, float* sum_out,
+                         float* y, long long rows, int channels, float eps, void* stream);
 /* maps (n_maps, 1, h, w) -> out (n_maps, ho, wo, 16) [NHWC], ho = ceil8(h)/2, wo = ceil8(w)/2:
  * ReLU(conv2d(zero-pad to multiples of 8, weight (16,1,6,6), stride 2, padding 2) + bias).
  * allow_tf32 != 0: TF32 tensor-core implicit GEMM (what cuDNN does for the reference under cudnn.allow_tf32), else fp32 FMA. */

@@ -19,7 +19,8 @@ namespace {
 template <int VPL>
 __global__ void __launch_bounds__(256)
 layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                  float* __restrict__ y, long long rows, float eps) {
+                  float* __restrict__ y, long long rows, float eps, const float* __restrict__ resid = nullptr,
+                  float* __restrict__ sum_out = nullptr) {
     constexpr int C = 32 * VPL;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -29,7 +30,12 @@ layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL / 4; ++i) {                           // lane owns float4 chunks lane + 32 i
-        const float4 t = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
+        float4 t = *reinterpret_cast<const float4*>(xr + (lane + 32 * i) * 4);
+        if (resid) {   // fused residual: LN(x + r), the sum written out as the new residual stream (one pass instead of add + LN)
+            const float4 r = *reinterpret_cast<const float4*>(resid + row * C + (lane + 32 * i) * 4);
+            t = make_float4(t.x + r.x, t.y + r.y, t.z + r.z, t.w + r.w);
+            *reinterpret_cast<float4*>(sum_out + row * C + (lane + 32 * i) * 4) = t;
+        }
         v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         s += (t.x + t.y) + (t.z + t.w);
     }
@@ -705,6 +711,23 @@ extern "C" int macvo_layer_norm(const float* x, const float* weight, const float
         case 128: layer_norm_kernel<4><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps); break;
         case 256: layer_norm_kernel<8><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps); break;
         case 512: layer_norm_kernel<16><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps); break;
+        default: return MACVO_E_UNSUPPORTED;
+    }
+    MACVO_LAUNCH_CHECK();
+    return MACVO_OK;
+}
+
+// sum_out = x + resid;  y = LayerNorm(sum_out)   (the residual-add that precedes every norm2 of the transformer blocks)
+extern "C" int macvo_add_layer_norm(const float* x, const float* resid, const float* weight, const float* bias, float* sum_out,
+                                    float* y, long long rows, int channels, float eps, void* stream) {
+    if (!x || !resid || !weight || !bias || !sum_out || !y || rows < 0) return MACVO_E_ARG;
+    if (rows == 0) return MACVO_OK;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    cudaStream_t st = as_stream(stream);
+    switch (channels) {
+        case 128: layer_norm_kernel<4><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps, resid, sum_out); break;
+        case 256: layer_norm_kernel<8><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps, resid, sum_out); break;
+        case 512: layer_norm_kernel<16><<<grid, 256, 0, st>>>(x, weight, bias, y, rows, eps, resid, sum_out); break;
         default: return MACVO_E_UNSUPPORTED;
     }
     MACVO_LAUNCH_CHECK();

@@ -330,6 +330,13 @@ class FlowFormerCovNet:
             return self._ops.layer_norm(x, self.W[p + ".weight"], self.W[p + ".bias"], eps)
         return F.layer_norm(x, (x.shape[-1],), self.W[p + ".weight"], self.W[p + ".bias"], eps)
 
+    def _add_ln(self, x: Tensor, y: Tensor, p: str, eps: float = 1e-5) -> tuple[Tensor, Tensor]:
+        """(x + y, LayerNorm(x + y)): the residual add in front of every norm2, fused into the LayerNorm pass"""
+        if self._native(x) and x.shape[-1] in (128, 256, 512) and x.shape == y.shape:
+            return self._ops.add_layer_norm(x, y, self.W[p + ".weight"], self.W[p + ".bias"], eps)
+        s = x + y
+        return s, self._ln(s, p, eps)
+
     def _native(self, x: Tensor) -> bool:
         """fp32 CUDA activations go through csrc/nn_kernels.cu; half-precision ones (MACVO_Fast) and the CPU
         golden-parity runs of this class keep the torch ops."""
@@ -367,15 +374,15 @@ class FlowFormerCovNet:
             x = self._ln(x.flatten(2).transpose(1, 2), p + f"patch_embeds.{s}.norm")
             b0, b1 = p + f"blocks.{s}.0.", p + f"blocks.{s}.1."
             # block 0: locally-grouped attention (7x7 windows, zero padded after the norm)
-            x = x + self._svt_local_attn(self._ln(x, b0 + "norm1", 1e-6), (H, W), b0 + "attn.", heads)
-            x = x + self._mlp(self._ln(x, b0 + "norm2", 1e-6), b0 + "mlp.")
+            x, xn = self._add_ln(x, self._svt_local_attn(self._ln(x, b0 + "norm1", 1e-6), (H, W), b0 + "attn.", heads), b0 + "norm2", 1e-6)
+            x = x + self._mlp(xn, b0 + "mlp.")
             # PEG: depthwise 3x3 + identity
             t = x.transpose(1, 2).reshape(B, C, H, W)          # channels-last view of the token matrix
             t = self._conv(t, p + f"pos_block.{s}.proj.0", padding=1, groups=C) + t
             x = t.flatten(2).transpose(1, 2)
             # block 1: globally sub-sampled attention
-            x = x + self._svt_global_attn(self._ln(x, b1 + "norm1", 1e-6), (H, W), b1 + "attn.", heads, sr)
-            x = x + self._mlp(self._ln(x, b1 + "norm2", 1e-6), b1 + "mlp.")
+            x, xn = self._add_ln(x, self._svt_global_attn(self._ln(x, b1 + "norm1", 1e-6), (H, W), b1 + "attn.", heads, sr), b1 + "norm2", 1e-6)
+            x = x + self._mlp(xn, b1 + "mlp.")
             x = x.reshape(B, H, W, C).permute(0, 3, 1, 2)      # (B, C, H, W) logical, channels-last in memory
         return x
 
@@ -456,8 +463,8 @@ class FlowFormerCovNet:
         """SelfAttentionLayer over the 8 latent tokens of each source pixel (core/encoder.py:97-140)."""
         y = self._ln(x, p + "norm1")
         a = self._attn(self._lin(y, p + "q"), self._lin(y, p + "k"), self._lin(y, p + "v"), 8)
-        x = x + self._lin(a, p + "proj")
-        return x + self._lin(F.gelu(self._lin(self._ln(x, p + "norm2"), p + "ffn.0")), p + "ffn.3")
+        x, xn = self._add_ln(x, self._lin(a, p + "proj"), p + "norm2")
+        return x + self._lin(F.gelu(self._lin(xn, p + "ffn.0")), p + "ffn.3")
 
     def _context_tokens(self, context: Tensor, p: str, reps: int) -> Tensor:
         """context_proj of the context map, tiled like `context.repeat(B//b, 1, 1, 1)` (twins.py:55-58):
@@ -563,8 +570,8 @@ class FlowFormerCovNet:
 
     def _vert_block(self, x: Tensor, size, context: Tensor, p: str, local: bool) -> Tensor:
         attn = self._vert_local_attn if local else self._vert_global_attn
-        x = x + attn(self._ln(x, p + "norm1"), size, context, p + "attn.")
-        return x + self._mlp(self._ln(x, p + "norm2"), p + "mlp.")
+        x, xn = self._add_ln(x, attn(self._ln(x, p + "norm1"), size, context, p + "attn."), p + "norm2")
+        return x + self._mlp(xn, p + "mlp.")
 
     def cost_perceiver(self, cost_volume: Tensor, context: Tensor) -> tuple[Tensor, Tensor]:
         c = "memory_encoder.cost_perceiver_encoder."

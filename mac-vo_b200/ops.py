@@ -84,6 +84,7 @@ EXPORTS = {
     "macvo_pgo_accumulate": (C.c_int, [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2 + [C.c_double]
                              + [C.c_void_p] * 2),
     "macvo_layer_norm": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
+    "macvo_add_layer_norm": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
     "macvo_patch_embed_conv1": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "macvo_add_rows_relu": (C.c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "macvo_small_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
@@ -711,6 +712,21 @@ def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5) -> Te
     _check(rc, "macvo_layer_norm")
     LAUNCHES[0] += 1
     return y
+
+
+def add_layer_norm(x: Tensor, resid: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5) -> tuple[Tensor, Tensor]:
+    """(x + resid, LayerNorm(x + resid)) in one pass over contiguous fp32 CUDA tensors of C in {128, 256, 512} channels."""
+    x, resid = _dev(x, torch.float32, "add_layer_norm x"), _dev(resid, torch.float32, "add_layer_norm resid")
+    c = x.shape[-1]
+    if c not in (128, 256, 512) or x.shape != resid.shape:
+        raise MacvoB200Error(f"add_layer_norm: channels {c} / shapes {tuple(x.shape)} vs {tuple(resid.shape)} unsupported")
+    s, y = torch.empty_like(x), torch.empty_like(x)
+    rc = load_library().macvo_add_layer_norm(x.data_ptr(), resid.data_ptr(), _dev(weight, torch.float32, "ln weight").data_ptr(),
+                                             _dev(bias, torch.float32, "ln bias").data_ptr(), s.data_ptr(), y.data_ptr(),
+                                             x.numel() // c, c, float(eps), _stream())
+    _check(rc, "macvo_add_layer_norm")
+    LAUNCHES[0] += 1
+    return s, y
 
 
 def patch_embed_conv1(maps: Tensor, weight: Tensor, bias: Tensor, allow_tf32: bool | None = None) -> Tensor:

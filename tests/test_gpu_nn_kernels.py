@@ -214,3 +214,14 @@ def test_decoder_token_kernel(ops, b, h, w):
     gl = gl + lin(F.gelu(lin(F.layer_norm(gl, (64,), W[ca + "norm2.weight"], W[ca + "norm2.bias"], 1e-5), ca + "ffn.0")), ca + "ffn.3")
     err = (got[:, :64].double() - gl).abs().max().item()
     assert err <= 1e-5 * gl.abs().max().item(), err / gl.abs().max().item()
+
+
+@pytest.mark.parametrize("rows,c", [(7, 128), (76800, 128), (4801, 256), (65, 512)])
+def test_add_layer_norm(ops, rows, c):
+    g = torch.Generator().manual_seed(rows + c)
+    x, r = (torch.randn(rows, c, generator=g) * 2).to(DEV), torch.randn(rows, c, generator=g).to(DEV)
+    w, b = torch.randn(c, generator=g).to(DEV), torch.randn(c, generator=g).to(DEV)
+    s, y = ops.add_layer_norm(x, r, w, b, 1e-6)
+    assert torch.equal(s, x + r)
+    ref = F.layer_norm((x + r).double(), (c,), w.double(), b.double(), 1e-6)
+    assert (y.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
