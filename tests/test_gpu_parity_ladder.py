@@ -13,7 +13,7 @@ the flow by any faithful fp32 implementation and is AT the fp32 noise floor for 
            convolutions): cuDNN / cuBLAS TF32, our attention / PatchEmbed kernels with TF32 operands, kind::tf32
            correlation volume, fp16 GMA attention matrix. TF32 keeps 10 mantissa bits (2^-11 = 4.9e-4 per operand):
            the encoders already differ by 3.5e-3 of their scale, the refinement contracts that to 6e-4 on the flow.
-           Bounds = 1.6 x the measured ladder (profiles/r02_parity_ladder.json), so that one dropped mantissa bit
+           Bounds = 1.5 x the measured ladder (profiles/r02_parity_ladder_v3.json), so that one dropped mantissa bit
            (2 x the error) fails the test.
 """
 import os
@@ -29,10 +29,10 @@ pytestmark = pytest.mark.gpu
 BOUNDS = {
     # stage: (strict, tf32)   error = max |x - truth| / mean |truth| over the fixture's strided sample
     "context": (2e-5, 6e-3), "feats": (2e-5, 6e-3), "corr_rows": (1e-5, 3e-3), "cost_memory": (1e-5, 2.5e-3),
-    "flow_iter": (6e-5, 3e-3), "cov_iter": (1e-4, 1.6e-3),
-    "flow": (6e-6, 1.1e-3),            # strict: 2.3 x the reference's own 2.6e-6
-    "cov_rel_max": (3e-4, 1.4e-2),     # strict: 2.3 x the reference's own 1.3e-4
-    "flow_vs_ref32": (1e-5, 1.1e-3), "cov_rel_vs_ref32": (2e-4, 1.4e-2),
+    "flow_iter": (6e-5, 3.2e-3), "cov_iter": (1e-4, 1.6e-3),
+    "flow": (6e-6, 1.35e-3),           # strict: 2.3 x the reference's own 2.6e-6; tf32: 1.5 x the measured 8.9e-4
+    "cov_rel_max": (3e-4, 1.8e-2),     # strict: 2.3 x the reference's own 1.3e-4; tf32: 1.5 x the measured 1.2e-2
+    "flow_vs_ref32": (1e-5, 1.35e-3), "cov_rel_vs_ref32": (2e-4, 1.8e-2),
 }
 
 
