@@ -327,7 +327,9 @@ def run_sharded(steps: int, warmup: int) -> dict:
     if rank == 0:
         fe = plugins.B200_FlowFormerCovFrontend(NS(weight="synthetic:0", device=device, enc_dtype="fp32", dec_dtype="fp32",
                                                    decoder_depth=12, enforce_positive_disparity=False, cuda_graph=True))
-        sel = plugins.B200_CovAwareSelector_NoDepth(NS(device=device, kernel_size=7, mask_width=32, max_match_cov=100.0))
+        # NMS window 3 instead of MACVO_Performant's 7: with the random-weight stand-in network the 7x7 non-minimum suppression
+        # leaves only ~200 candidates in a 1280x720 frame; 3x3 leaves > 4096, so that the solve really has 4096 residual blocks
+        sel = plugins.B200_CovAwareSelector_NoDepth(NS(device=device, kernel_size=3, mask_width=32, max_match_cov=100.0))
         msel = plugins.B200_MappingPointSelector(NS(max_depth=5.0, max_depth_cov=0.005, mask_width=32))
         cov = plugins.B200_MatchCovariance(NS(device=device, kernel_size=31, match_cov_default=0.25, min_depth_cov=0.05, min_flow_cov=0.25))
         pgo = plugins.B200_TwoFrame_PGO(NS(graph_type="disp", device=device, vectorize=True, parallel=False, autodiff=False))

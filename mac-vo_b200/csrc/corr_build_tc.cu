@@ -341,6 +341,15 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             // (an event trace showed it being held 1.5 us — the smem transpose + stores of the first half — while the
             // MMAs of the tile after next were waiting for it); the transposes / stores then overlap the next MMAs.
             uint32_t r[4][32];
+            if (dbg & 64) {                               // profiling aid: no TMEM drain, no transposes, no stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * acc, 0);
+                acc_phase ^= 1;
+                col += 2;
+                while (col >= nt) { col -= nt; ++row; }
+                continue;
+            }
             {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
                 tmem_ld_32x32b_x32(taddr, r[0]);

@@ -120,15 +120,52 @@ decoder_token_kernel(const float* __restrict__ cf, const float* __restrict__ coo
     const long long p0 = (long long)blockIdx.x * TP;
     const int valid = (int)min((long long)TP, pixels - p0);
 
-    for (int e = tid; e < BLOB / 4; e += NT)
-        reinterpret_cast<float4*>(sm)[e] = __ldg(reinterpret_cast<const float4*>(blob) + e);
     float* X0 = sm + S_X0;        // cost_forward tile, [81][LD]
     float* CAT = sm + S_CAT;      // rows 0..63: q -> a -> LN(g);  rows 64..127: query -> FFN hidden
     float* A = sm + S_A;          // token hidden -> q_in -> g
+    // ---- asynchronous fill: with one 8-warp CTA per SM every synchronous load round trip is exposed, so
+    //   * the 119 KB weight blob arrives by ONE bulk copy (TMA engine) signalled on an mbarrier,
+    //   * the (64 x 81) lookup rows are staged with 16-byte cp.async into the (still unused) CAT buffer and transposed
+    //     shared -> shared afterwards,
+    //   * this tile's keys / values (256 KB, needed ~10 us later) are pulled into L2 with prefetch hints.
+    __shared__ __align__(8) unsigned long long s_bar;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BLOB * 4) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(sm)), "l"(blob), "r"(BLOB * 4), "r"(bar) : "memory");
+    }
     const float* cft = cf + p0 * CF;
-    for (int e = tid; e < TP * CF; e += NT) {
+    const int nfl = valid * CF;                                        // contiguous floats of this tile's lookup rows
+    {
+        const uint32_t stage = (uint32_t)__cvta_generic_to_shared(CAT);
+        for (int e = tid; e < nfl / 4; e += NT)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + 16 * e), "l"(cft + 4 * e) : "memory");
+        for (int e = (nfl / 4) * 4 + tid; e < nfl; e += NT) CAT[e] = __ldg(cft + e);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const char* kb = reinterpret_cast<const char*>(key + p0 * 8 * C);
+        const char* vb = reinterpret_cast<const char*>(value + p0 * 8 * C);
+        for (int l = tid; l < valid * 16; l += NT) {                   // 8 tokens x 64 floats = 2 KB = 16 lines per pixel
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + 128 * l));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + 128 * l));
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    for (int e = tid; e < TP * CF; e += NT) {                          // staged rows -> channel-major [k][pixel]
         const int px = e / CF, k = e - px * CF;
-        X0[k * LD + px] = px < valid ? __ldg(cft + e) : 0.f;
+        X0[k * LD + px] = px < valid ? CAT[e] : 0.f;
+    }
+    {   // weights landed?
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar) : "memory");
     }
     __syncthreads();
 

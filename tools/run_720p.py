@@ -33,7 +33,8 @@ def main() -> None:
     frames = synthetic.make_sequence(4, H, W, pin=True)
     fe = plugins.B200_FlowFormerCovFrontend(NS(weight="synthetic:0", device=dev, enc_dtype="fp32", dec_dtype="fp32",
                                                decoder_depth=12, enforce_positive_disparity=False, cuda_graph=True))
-    sel = plugins.B200_CovAwareSelector_NoDepth(NS(device=dev, kernel_size=7, mask_width=32, max_match_cov=100.0))
+    sel = plugins.B200_CovAwareSelector_NoDepth(NS(device=dev, kernel_size=3,   # 3x3 NMS: > 4096 candidates with the stand-in network
+                                                    mask_width=32, max_match_cov=100.0))
     msel = plugins.B200_MappingPointSelector(NS(max_depth=5.0, max_depth_cov=0.005, mask_width=32))
     cov = plugins.B200_MatchCovariance(NS(device=dev, kernel_size=31, match_cov_default=0.25, min_depth_cov=0.05, min_flow_cov=0.25))
     pgo = plugins.B200_TwoFrame_PGO(NS(graph_type="disp", device=dev, vectorize=True, parallel=False, autodiff=False))
