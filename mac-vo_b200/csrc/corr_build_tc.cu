@@ -136,6 +136,16 @@ split_kmajor_kernel(const float* __restrict__ f1, const float* __restrict__ f2, 
     }
 }
 
+__device__ __forceinline__ void stg128(float* p, float4 v, int mode, uint64_t policy) {
+    if (mode == 0)
+        asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                     ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
+    else if (mode == 2)
+        asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    else
+        *reinterpret_cast<float4*>(p) = v;
+}
+
 // ---- kernel 2 -----------------------------------------------------------------------------------------------
 // PASSES 3: fp16 hi*hi + hi*lo + lo*hi (fp32-class)    1: fp16 hi*hi    2: ONE kind::tf32 pass straight over the fp32
 // K-major features (no operand pre-pass, no workspace): map_a_hi / map_b_hi are fp32 maps with 32-element (128 B) boxes,
@@ -325,6 +335,12 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // 8 KB XOR-swizzled shared-memory buffer and writes 2 rows x 256 contiguous bytes per instruction.
         const int quarter = warp & 3;
         const int group = (warp - 2) >> 2;
+        // L2 policy of the output stores. The 184 MB volume does not fit the 126 MB L2: with default (evict-normal) stores the
+        // first ~100 MB only dirty the L2 and DRAM write-back starts once it is full, so the tail of the kernel runs at
+        // write-back speed; evict-first lines are written back from the start, overlapped with the whole kernel.
+        const int store_mode = (dbg >> 8) & 3;                  // 0: evict-first policy (default)  1: plain  2: st.global.cs
+        uint64_t store_policy = 0;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(store_policy));
         const float unscale = PASSES == 3 ? SPLIT_UNSCALE : 1.f;
         const uint32_t tb = smem_u32(smem_epi + (warp - 2) * EPI_WARP_BYTES);
         const int acc = group;
@@ -379,11 +395,18 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const int ocol = col * BLOCK_N + h * EPI_COLS + (lane & 15) * 4;
                 float* dst0 = corr + ((long long)b * n + orow0) * n + ocol;
                 if (!(dbg & 1)) {
+                    // all 16 shared loads first (asm volatile statements keep their order: interleaved with the stores every
+                    // store waited for the shared load in front of it), then 16 stores carrying the L2 policy
+                    float4 t[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int rr = 2 * i + (lane >> 4);
-                        const float4 v = lds128(tb + rr * 256 + (((lane & 15) ^ (rr & 7)) << 4));
-                        if (orow0 + rr < n && ocol < n) *reinterpret_cast<float4*>(dst0 + (long long)rr * n) = v;   // n % 8 == 0
+                        t[i] = lds128(tb + rr * 256 + (((lane & 15) ^ (rr & 7)) << 4));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int rr = 2 * i + (lane >> 4);
+                        if (orow0 + rr < n && ocol < n) stg128(dst0 + (long long)rr * n, t[i], store_mode, store_policy);   // n % 8 == 0
                     }
                 }
                 __syncwarp();                                             // buffer is reused by the next half

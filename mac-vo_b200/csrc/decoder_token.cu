@@ -20,9 +20,9 @@
 
 namespace {
 
-constexpr int TP = 64;            // pixels per CTA
-constexpr int LD = 68;            // row stride of the [channel][pixel] activation buffers (16-B aligned rows)
-constexpr int NT = 256;
+// TP pixels per CTA (template parameter: 64 or 72 — the host picks the one that needs fewer waves of one-CTA-per-SM blocks:
+// 9600 pixels are 150 tiles of 64 = TWO waves on 148 SMs, but 134 tiles of 72 = one), LD = TP + 4 row stride of the
+// [channel][pixel] activation buffers (16-B aligned rows), 4 threads per pixel.
 constexpr int C = 64, CF = 81, OUTC = 160;
 // weight blob (floats): transposed matrices [K][64], then 10 vectors of 64, then 16 frequencies
 constexpr int W_FTE0 = 0, W_FTE2 = W_FTE0 + CF * C, W_Q = W_FTE2 + C * C, W_PROJ = W_Q + C * C,
@@ -30,14 +30,17 @@ constexpr int W_FTE0 = 0, W_FTE2 = W_FTE0 + CF * C, W_Q = W_FTE2 + C * C, W_PROJ
 constexpr int V_BFTE0 = W_END, V_BFTE2 = V_BFTE0 + C, V_LN1W = V_BFTE2 + C, V_LN1B = V_LN1W + C, V_BQ = V_LN1B + C,
               V_BPROJ = V_BQ + C, V_LN2W = V_BPROJ + C, V_LN2B = V_LN2W + C, V_BFFN0 = V_LN2B + C, V_BFFN3 = V_BFFN0 + C,
               V_FREQ = V_BFFN3 + C, BLOB = V_FREQ + 16;
-constexpr int S_X0 = BLOB, S_CAT = S_X0 + CF * LD, S_A = S_CAT + 2 * C * LD, S_END = S_A + C * LD;
-static_assert(BLOB % 4 == 0 && S_X0 % 4 == 0 && S_CAT % 4 == 0 && S_A % 4 == 0, "float4 alignment");
-static_assert(S_END * 4 <= 227 * 1024, "shared memory budget");
+template <int TP> struct Lay {
+    static constexpr int LD = TP + 4, NT = 4 * TP;
+    static constexpr int S_X0 = BLOB, S_CAT = S_X0 + CF * LD, S_A = S_CAT + 2 * C * LD, S_END = S_A + C * LD;
+    static_assert(BLOB % 4 == 0 && S_X0 % 4 == 0 && S_CAT % 4 == 0 && S_A % 4 == 0, "float4 alignment");
+    static_assert(S_END * 4 <= 227 * 1024, "shared memory budget");
+};
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 // acc[o][p] += sum_k WT[k][4 og + o] * X[k][4 pg + p]
-template <int K>
+template <int K, int LD>
 __device__ __forceinline__ void gemm_tile(const float* __restrict__ WT, const float* __restrict__ X, int og, int pg,
                                           float (&acc)[4][4]) {
 #pragma unroll 4
@@ -58,7 +61,7 @@ __device__ __forceinline__ void gemm_tile(const float* __restrict__ WT, const fl
 enum Epi { EPI_BIAS, EPI_GELU, EPI_RESID };
 
 // Y[4 og + o][4 pg + p] = epi(acc + bias [+ R])
-template <int EPI>
+template <int EPI, int LD>
 __device__ __forceinline__ void store_tile(float* __restrict__ Y, const float* __restrict__ bias,
                                            const float* __restrict__ R, int og, int pg, float (&acc)[4][4]) {
 #pragma unroll
@@ -82,6 +85,7 @@ __device__ __forceinline__ void zero(float (&acc)[4][4]) {
 }
 
 // LayerNorm over the 64 channels of each pixel column of X, optional sine embedding added; 4 threads per pixel.
+template <int LD>
 __device__ __forceinline__ void layer_norm_cols(const float* __restrict__ X, float* __restrict__ Y,
                                                 const float* __restrict__ w, const float* __restrict__ b, float eps,
                                                 int px, int quarter, bool add_sine, float coord,
@@ -111,11 +115,14 @@ __device__ __forceinline__ void layer_norm_cols(const float* __restrict__ X, flo
     }
 }
 
-__global__ void __launch_bounds__(NT, 1)
+template <int TP>
+__global__ void __launch_bounds__(4 * TP, 1)
 decoder_token_kernel(const float* __restrict__ cf, const float* __restrict__ coords, const float* __restrict__ key,
                      const float* __restrict__ value, const float* __restrict__ blob, float* __restrict__ out,
                      long long pixels, int n1, float eps) {
     extern __shared__ __align__(16) float sm[];
+    using L = Lay<TP>;
+    constexpr int LD = L::LD, NT = L::NT, S_X0 = L::S_X0, S_CAT = L::S_CAT, S_A = L::S_A;
     const int tid = threadIdx.x;
     const long long p0 = (long long)blockIdx.x * TP;
     const int valid = (int)min((long long)TP, pixels - p0);
@@ -175,12 +182,12 @@ decoder_token_kernel(const float* __restrict__ cf, const float* __restrict__ coo
 
     // token MLP: hidden = GELU(W0 cf + b0) -> A ; query = W2 hidden + b2 -> CAT[64..]
     zero(acc);
-    gemm_tile<CF>(sm + W_FTE0, X0, og, pg, acc);
-    store_tile<EPI_GELU>(A, sm + V_BFTE0, nullptr, og, pg, acc);
+    gemm_tile<CF, LD>(sm + W_FTE0, X0, og, pg, acc);
+    store_tile<EPI_GELU, LD>(A, sm + V_BFTE0, nullptr, og, pg, acc);
     __syncthreads();
     zero(acc);
-    gemm_tile<C>(sm + W_FTE2, A, og, pg, acc);
-    store_tile<EPI_BIAS>(CAT + C * LD, sm + V_BFTE2, nullptr, og, pg, acc);
+    gemm_tile<C, LD>(sm + W_FTE2, A, og, pg, acc);
+    store_tile<EPI_BIAS, LD>(CAT + C * LD, sm + V_BFTE2, nullptr, og, pg, acc);
     __syncthreads();
 
     // q_in = LayerNorm(query) + sine(coords1) -> A
@@ -191,13 +198,13 @@ decoder_token_kernel(const float* __restrict__ cf, const float* __restrict__ coo
             const long long bi = p / n1, pi = p - bi * n1;
             coord = coords[(bi * 2 + (quarter >> 1)) * n1 + pi];        // quarters 0,1 embed x; 2,3 embed y
         }
-        layer_norm_cols(CAT + C * LD, A, sm + V_LN1W, sm + V_LN1B, eps, px, quarter, true, coord, sm + V_FREQ);
+        layer_norm_cols<LD>(CAT + C * LD, A, sm + V_LN1W, sm + V_LN1B, eps, px, quarter, true, coord, sm + V_FREQ);
     }
     __syncthreads();
     // q = Wq q_in + bq -> CAT[0..63]
     zero(acc);
-    gemm_tile<C>(sm + W_Q, A, og, pg, acc);
-    store_tile<EPI_BIAS>(CAT, sm + V_BQ, nullptr, og, pg, acc);
+    gemm_tile<C, LD>(sm + W_Q, A, og, pg, acc);
+    store_tile<EPI_BIAS, LD>(CAT, sm + V_BQ, nullptr, og, pg, acc);
     __syncthreads();
 
     // cross attention of this pixel's query to its own 8 cost-memory tokens; this thread: heads 2*quarter, 2*quarter+1
@@ -245,19 +252,19 @@ decoder_token_kernel(const float* __restrict__ cf, const float* __restrict__ coo
 
     // g = query + Wp [a | query] + bp -> A
     zero(acc);
-    gemm_tile<2 * C>(sm + W_PROJ, CAT, og, pg, acc);
-    store_tile<EPI_RESID>(A, sm + V_BPROJ, CAT + C * LD, og, pg, acc);
+    gemm_tile<2 * C, LD>(sm + W_PROJ, CAT, og, pg, acc);
+    store_tile<EPI_RESID, LD>(A, sm + V_BPROJ, CAT + C * LD, og, pg, acc);
     __syncthreads();
     // LN(g) -> CAT[0..63];  hidden = GELU(F0 LN(g) + b) -> CAT[64..];  g += F3 hidden + b (in place)
-    layer_norm_cols(A, CAT, sm + V_LN2W, sm + V_LN2B, eps, px, quarter, false, 0.f, nullptr);
+    layer_norm_cols<LD>(A, CAT, sm + V_LN2W, sm + V_LN2B, eps, px, quarter, false, 0.f, nullptr);
     __syncthreads();
     zero(acc);
-    gemm_tile<C>(sm + W_FFN0, CAT, og, pg, acc);
-    store_tile<EPI_GELU>(CAT + C * LD, sm + V_BFFN0, nullptr, og, pg, acc);
+    gemm_tile<C, LD>(sm + W_FFN0, CAT, og, pg, acc);
+    store_tile<EPI_GELU, LD>(CAT + C * LD, sm + V_BFFN0, nullptr, og, pg, acc);
     __syncthreads();
     zero(acc);
-    gemm_tile<C>(sm + W_FFN3, CAT + C * LD, og, pg, acc);
-    store_tile<EPI_RESID>(A, sm + V_BFFN3, A, og, pg, acc);
+    gemm_tile<C, LD>(sm + W_FFN3, CAT + C * LD, og, pg, acc);
+    store_tile<EPI_RESID, LD>(A, sm + V_BFFN3, A, og, pg, acc);
     __syncthreads();
 
     // out rows [g | cost_forward | 0]: coalesced (consecutive threads -> consecutive floats of the (P,160) matrix)
@@ -272,17 +279,26 @@ decoder_token_kernel(const float* __restrict__ cf, const float* __restrict__ coo
 
 extern "C" size_t macvo_decoder_token_blob_floats(void) { return BLOB; }
 
+template <int TP>
+static int launch_token(const float* cf, const float* coords, const float* key, const float* value, const float* blob,
+                        float* out, long long pixels, int n1, float eps, cudaStream_t st) {
+    constexpr int smem = Lay<TP>::S_END * 4;
+    MACVO_CUDA_TRY(cudaFuncSetAttribute(decoder_token_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    decoder_token_kernel<TP><<<(unsigned)((pixels + TP - 1) / TP), 4 * TP, smem, st>>>(cf, coords, key, value, blob, out, pixels, n1, eps);
+    MACVO_LAUNCH_CHECK();
+    return MACVO_OK;
+}
+
 extern "C" int macvo_decoder_token(const float* cost_forward, const float* coords, const float* key, const float* value,
                                    const float* weight_blob, float* out, int batch, int n1, float eps, void* stream) {
     if (!cost_forward || !coords || !key || !value || !weight_blob || !out || batch <= 0 || n1 <= 0) return MACVO_E_ARG;
     const long long pixels = (long long)batch * n1;
-    static bool configured = false;
-    if (!configured) {
-        MACVO_CUDA_TRY(cudaFuncSetAttribute(decoder_token_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_END * 4));
-        configured = true;
-    }
-    decoder_token_kernel<<<(unsigned)((pixels + TP - 1) / TP), NT, S_END * 4, as_stream(stream)>>>(
-        cost_forward, coords, key, value, weight_blob, out, pixels, n1, eps);
-    MACVO_LAUNCH_CHECK();
-    return MACVO_OK;
+    int dev = 0, sms = 148;
+    MACVO_CUDA_TRY(cudaGetDevice(&dev));
+    MACVO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // one CTA per SM: cost ~ waves x pixels-per-tile
+    auto cost = [&](int tp) { const long long tiles = (pixels + tp - 1) / tp; return ((tiles + sms - 1) / sms) * tp; };
+    cudaStream_t st = as_stream(stream);
+    return cost(72) < cost(64) ? launch_token<72>(cost_forward, coords, key, value, weight_blob, out, pixels, n1, eps, st)
+                               : launch_token<64>(cost_forward, coords, key, value, weight_blob, out, pixels, n1, eps, st);
 }
