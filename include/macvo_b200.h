@@ -261,7 +261,10 @@ int macvo_add_layer_norm(const float* x, const float* resid, const float* weight
                          float* y, long long rows, int channels, float eps, void* stream);
 /* maps (n_maps, 1, h, w) -> out (n_maps, ho, wo, 16) [NHWC], ho = ceil8(h)/2, wo = ceil8(w)/2:
  * ReLU(conv2d(zero-pad to multiples of 8, weight (16,1,6,6), stride 2, padding 2) + bias).
- * allow_tf32 != 0: TF32 tensor-core implicit GEMM (what cuDNN does for the reference under cudnn.allow_tf32), else fp32 FMA. */
+ * allow_tf32 bit 0: TF32 tensor-core implicit GEMM (what cuDNN does for the reference under cudnn.allow_tf32), else fp32 FMA.
+ * allow_tf32 bit 1 (needs bit 0): write the result space-to-depth, i.e. as the NHWC tensor (n_maps, ho/2, wo/2, 64) whose channel
+ *   block (y & 1) * 2 + (x & 1) holds pixel (y, x): PatchEmbed's next 6x6 / stride-2 convolution over 16 channels becomes a
+ *   3x3 / stride-1 convolution over 64 channels (same arithmetic, full K blocks for the implicit GEMM). */
 int macvo_patch_embed_conv1(const float* maps, const float* weight, const float* bias, float* out,
                             long long n_maps, int h, int w, int allow_tf32, void* stream);
 /* in place x[r, :] = relu(x[r, :] + term[r % period, :]); x (rows, channels), term (period, channels), channels % 4 == 0

@@ -413,7 +413,7 @@ attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const f
 // (neighbouring lanes read overlapping pixels -> broadcasts, no conflicts); the 16 x 40 filter lives in 20 registers.
 __global__ void __launch_bounds__(256)
 patch_conv1_tc_kernel(const float* __restrict__ maps, const float* __restrict__ wgt, const float* __restrict__ bias,
-                      float* __restrict__ out, int h, int w, int ho, int wo) {
+                      float* __restrict__ out, int h, int w, int ho, int wo, int s2d) {
     extern __shared__ float sm[];
     uint32_t* s_map = reinterpret_cast<uint32_t*>(sm);   // tf32 map with a 2-pixel zero frame on the top / left, (2ho+4) x (2wo+4)
     const int hp = 2 * ho + 4, wp = 2 * wo + 4;
@@ -451,13 +451,24 @@ patch_conv1_tc_kernel(const float* __restrict__ maps, const float* __restrict__ 
             mma_tf32(c0, a, bw[ks][0][0], bw[ks][0][1]);
             mma_tf32(c1, a, bw[ks][1][0], bw[ks][1][1]);
         }
+        // output position -> row offset (in units of 16 channels). s2d: the NHWC tensor is written space-to-depth, i.e. as the
+        // (ho/2, wo/2, 4 x 16) tensor whose channel block (y & 1) * 2 + (x & 1) holds pixel (y, x): the following 6x6 / stride-2
+        // convolution over 16 channels is then a 3x3 / stride-1 convolution over 64 channels — the same arithmetic with full
+        // 32-channel K blocks for the implicit GEMM instead of half-empty ones (PatchEmbed proj.2, encoder.py:24-27)
+        auto row_of = [&](int p) -> long long {
+            if (!s2d) return p;
+            const int y = p / wo, x = p - y * wo;
+            return ((long long)(y >> 1) * (wo >> 1) + (x >> 1)) * 4 + ((y & 1) * 2 + (x & 1));
+        };
         if (p0 + g < npos) {
-            *reinterpret_cast<float2*>(dst + (long long)(p0 + g) * PE_C + 2 * t) = make_float2(fmaxf(c0[0], 0.f), fmaxf(c0[1], 0.f));
-            *reinterpret_cast<float2*>(dst + (long long)(p0 + g) * PE_C + 8 + 2 * t) = make_float2(fmaxf(c1[0], 0.f), fmaxf(c1[1], 0.f));
+            float* o = dst + row_of(p0 + g) * PE_C;
+            *reinterpret_cast<float2*>(o + 2 * t) = make_float2(fmaxf(c0[0], 0.f), fmaxf(c0[1], 0.f));
+            *reinterpret_cast<float2*>(o + 8 + 2 * t) = make_float2(fmaxf(c1[0], 0.f), fmaxf(c1[1], 0.f));
         }
         if (p0 + g + 8 < npos) {
-            *reinterpret_cast<float2*>(dst + (long long)(p0 + g + 8) * PE_C + 2 * t) = make_float2(fmaxf(c0[2], 0.f), fmaxf(c0[3], 0.f));
-            *reinterpret_cast<float2*>(dst + (long long)(p0 + g + 8) * PE_C + 8 + 2 * t) = make_float2(fmaxf(c1[2], 0.f), fmaxf(c1[3], 0.f));
+            float* o = dst + row_of(p0 + g + 8) * PE_C;
+            *reinterpret_cast<float2*>(o + 2 * t) = make_float2(fmaxf(c0[2], 0.f), fmaxf(c0[3], 0.f));
+            *reinterpret_cast<float2*>(o + 8 + 2 * t) = make_float2(fmaxf(c1[2], 0.f), fmaxf(c1[3], 0.f));
         }
     }
 }
@@ -743,9 +754,10 @@ extern "C" int macvo_patch_embed_conv1(const float* maps, const float* weight, c
     const size_t smem = (size_t)(2 * ho + 4) * (2 * wo + 4) * sizeof(float);
     if (smem > 200 * 1024) return MACVO_E_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
-    if (allow_tf32) {
+    if ((allow_tf32 & 2) && !(allow_tf32 & 1)) return MACVO_E_UNSUPPORTED;      // space-to-depth output: tensor-core variant only
+    if (allow_tf32 & 1) {
         MACVO_CUDA_TRY(cudaFuncSetAttribute(patch_conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        patch_conv1_tc_kernel<<<(unsigned)n_maps, 256, smem, st>>>(maps, weight, bias, out, h, w, ho, wo);
+        patch_conv1_tc_kernel<<<(unsigned)n_maps, 256, smem, st>>>(maps, weight, bias, out, h, w, ho, wo, (allow_tf32 >> 1) & 1);
         MACVO_LAUNCH_CHECK();
         return MACVO_OK;
     }

@@ -429,11 +429,20 @@ class FlowFormerCovNet:
         p = "memory_encoder.cost_perceiver_encoder.patch_embed."
         M, _, H2, W2 = cost_maps.shape
         if self._native(cost_maps) and (H2 + 7) // 8 * 8 * ((W2 + 7) // 8 * 8) <= 96 * 160:
-            x = self._ops.patch_embed_conv1(cost_maps, self.W[p + "proj.0.weight"], self.W[p + "proj.0.bias"])
+            if torch.backends.cudnn.allow_tf32 and self._fused_conv_relu:
+                # conv1 written space-to-depth -> proj.2 (6x6 / s2 over 16 channels, half-empty K blocks in the implicit GEMM)
+                # runs as the equivalent 3x3 / s1 convolution over 64 channels
+                x = self._ops.patch_embed_conv1(cost_maps, self.W[p + "proj.0.weight"], self.W[p + "proj.0.bias"], s2d=True)
+                w2 = self._memo(("pe_w2_s2d", x.device), lambda: self._ops.space_to_depth_filter(self.W[p + "proj.2.weight"])
+                                .contiguous(memory_format=torch.channels_last))
+                x = torch.cudnn_convolution_relu(x, w2, self.W[p + "proj.2.bias"], (1, 1), (1, 1), (1, 1), 1)
+            else:
+                x = self._ops.patch_embed_conv1(cost_maps, self.W[p + "proj.0.weight"], self.W[p + "proj.0.bias"])
+                x = self._conv_relu(x, p + "proj.2", stride=2, padding=2)
         else:
             x = F.pad(cost_maps, (0, (8 - W2 % 8) % 8, 0, (8 - H2 % 8) % 8))
             x = self._conv_relu(x, p + "proj.0", stride=2, padding=2)
-        x = self._conv_relu(x, p + "proj.2", stride=2, padding=2)
+            x = self._conv_relu(x, p + "proj.2", stride=2, padding=2)
         native = self._native(x)
         # proj.4 has no activation after it, so its bias b4 only enters through ffn_with_coord.0: W0x (x + b4) — on the
         # native path it is folded into the per-position term and the conv runs bias-free (saves a 0.13 ms bias pass)

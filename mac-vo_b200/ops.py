@@ -729,21 +729,34 @@ def add_layer_norm(x: Tensor, resid: Tensor, weight: Tensor, bias: Tensor, eps: 
     return s, y
 
 
-def patch_embed_conv1(maps: Tensor, weight: Tensor, bias: Tensor, allow_tf32: bool | None = None) -> Tensor:
-    """(M,1,H,W) cost maps -> ReLU(conv 6x6/2 (+ pad to x8)) as a logical (M,16,Ho,Wo) channels_last tensor."""
+def patch_embed_conv1(maps: Tensor, weight: Tensor, bias: Tensor, allow_tf32: bool | None = None, s2d: bool = False) -> Tensor:
+    """(M,1,H,W) cost maps -> ReLU(conv 6x6/2 (+ pad to x8)) as a logical (M,16,Ho,Wo) channels_last tensor; s2d=True (TF32
+    variant only): the same values space-to-depth, a logical (M,64,Ho/2,Wo/2) channels_last tensor with channel
+    ((y & 1) * 2 + (x & 1)) * 16 + c (see `space_to_depth_filter` for the matching 3x3 filter of the next convolution)."""
     maps = _dev(maps, torch.float32, "patch_embed maps")
     m, one, h, w = maps.shape
     if one != 1 or tuple(weight.shape) != (16, 1, 6, 6):
         raise MacvoB200Error("patch_embed_conv1: expects (M,1,H,W) maps and a (16,1,6,6) weight")
     ho, wo = (h + 7) // 8 * 4, (w + 7) // 8 * 4
-    out = torch.empty(m, ho, wo, 16, dtype=torch.float32, device=maps.device)
+    tf32 = bool(torch.backends.cudnn.allow_tf32 if allow_tf32 is None else allow_tf32)
+    if s2d and not tf32:
+        raise MacvoB200Error("patch_embed_conv1: the space-to-depth output exists for the TF32 tensor-core variant only")
+    out = torch.empty((m, ho // 2, wo // 2, 64) if s2d else (m, ho, wo, 16), dtype=torch.float32, device=maps.device)
     rc = load_library().macvo_patch_embed_conv1(maps.data_ptr(), _dev(weight, torch.float32, "w").data_ptr(),
                                                 _dev(bias, torch.float32, "b").data_ptr(), out.data_ptr(),
-                                                m, h, w, int(torch.backends.cudnn.allow_tf32 if allow_tf32 is None else allow_tf32),
-                                                _stream())
+                                                m, h, w, int(tf32) | (2 if s2d else 0), _stream())
     _check(rc, "macvo_patch_embed_conv1")
     LAUNCHES[0] += 1
     return out.permute(0, 3, 1, 2)
+
+
+def space_to_depth_filter(weight: Tensor) -> Tensor:
+    """(O, C, 6, 6) stride-2 / padding-2 filter -> the (O, 4C, 3, 3) stride-1 / padding-1 filter that gives the same output on
+    the space-to-depth input: W'[o, (dy*2+dx)*C + c, a, b] = W[o, c, 2a+dy, 2b+dx]."""
+    o, c, kh, kw = weight.shape
+    if (kh, kw) != (6, 6):
+        raise MacvoB200Error("space_to_depth_filter: expects a 6x6 filter")
+    return weight.reshape(o, c, 3, 2, 3, 2).permute(0, 3, 5, 1, 2, 4).reshape(o, 4 * c, 3, 3)
 
 
 def small_attention(q: Tensor, k: Tensor, v: Tensor, heads: int, allow_tf32: bool | None = None) -> Tensor:

@@ -43,6 +43,15 @@ def test_patch_embed_conv1(ops, m, h, w):
     assert (got.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
     got = ops.patch_embed_conv1(maps, wt, b, allow_tf32=True)          # TF32 operands, fp32 accumulate (cuDNN's TF32 class)
     assert (got.double() - ref).abs().max().item() <= 3e-3 * ref.abs().max().item()
+    # space-to-depth output: same bits, channel block (y & 1) * 2 + (x & 1) of the (ho/2, wo/2, 64) tensor
+    s2d = ops.patch_embed_conv1(maps, wt, b, allow_tf32=True, s2d=True)
+    ho, wo = got.shape[-2:]
+    expect = got.reshape(m, 16, ho // 2, 2, wo // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(m, 64, ho // 2, wo // 2)
+    assert s2d.shape == expect.shape and s2d.is_contiguous(memory_format=torch.channels_last) and torch.equal(s2d, expect)
+    w2 = torch.randn(32, 16, 6, 6, generator=g).to(DEV)
+    a = F.conv2d(got.double(), w2.double(), None, stride=2, padding=2)
+    bb = F.conv2d(s2d.double(), ops.space_to_depth_filter(w2).double(), None, stride=1, padding=1)
+    assert (a - bb).abs().max().item() <= 1e-9 * a.abs().max().item()
 
 
 def _ref_attention(q, k, v, heads):
