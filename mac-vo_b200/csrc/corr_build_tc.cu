@@ -335,9 +335,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // 8 KB XOR-swizzled shared-memory buffer and writes 2 rows x 256 contiguous bytes per instruction.
         const int quarter = warp & 3;
         const int group = (warp - 2) >> 2;
-        // L2 policy of the output stores. The 184 MB volume does not fit the 126 MB L2: with default (evict-normal) stores the
-        // first ~100 MB only dirty the L2 and DRAM write-back starts once it is full, so the tail of the kernel runs at
-        // write-back speed; evict-first lines are written back from the start, overlapped with the whole kernel.
+        // L2 policy of the output stores: evict-first (the volume is consumed once, by PatchEmbed / the lookups, and does not fit
+        // the 126 MB L2 anyway). Measured: no effect at N = 4800 (the kernel is not write-back bound), 2-3 % at N = 14400.
         const int store_mode = (dbg >> 8) & 3;                  // 0: evict-first policy (default)  1: plain  2: st.global.cs
         uint64_t store_policy = 0;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(store_policy));
@@ -395,18 +394,13 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const int ocol = col * BLOCK_N + h * EPI_COLS + (lane & 15) * 4;
                 float* dst0 = corr + ((long long)b * n + orow0) * n + ocol;
                 if (!(dbg & 1)) {
-                    // all 16 shared loads first (asm volatile statements keep their order: interleaved with the stores every
-                    // store waited for the shared load in front of it), then 16 stores carrying the L2 policy
-                    float4 t[16];
+                    // (batching the 16 shared loads ahead of the 16 stores costs 64 more live registers and measured 8 us
+                    // SLOWER — r2_corr_probe_3.log — so loads and stores stay interleaved)
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int rr = 2 * i + (lane >> 4);
-                        t[i] = lds128(tb + rr * 256 + (((lane & 15) ^ (rr & 7)) << 4));
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int rr = 2 * i + (lane >> 4);
-                        if (orow0 + rr < n && ocol < n) stg128(dst0 + (long long)rr * n, t[i], store_mode, store_policy);   // n % 8 == 0
+                        const float4 v = lds128(tb + rr * 256 + (((lane & 15) ^ (rr & 7)) << 4));
+                        if (orow0 + rr < n && ocol < n) stg128(dst0 + (long long)rr * n, v, store_mode, store_policy);   // n % 8 == 0
                     }
                 }
                 __syncwarp();                                             // buffer is reused by the next half
