@@ -469,3 +469,26 @@ def test_cov_sanity_filter_kernel(ops):
     good = ops.cov_sanity_filter(c1.to(DEV), c2.to(DEV)).cpu()
     bad = c1.isnan().any(dim=(-1, -2)) | c1.isinf().any(dim=(-1, -2)) | c2.isnan().any(dim=(-1, -2)) | c2.isinf().any(dim=(-1, -2))
     assert torch.equal(good, ~bad) and int((~good).sum()) == 4
+
+
+@pytest.mark.parametrize("name", ["depth_small", "depth_masked", "depth_nan"])
+def test_depth_aware_selector_plugin_class(ops, golden, name):
+    """the PLUGIN class `B200_CovAwareSelector` (not just the ops): constructed from a YAML-shaped config with
+    `max_depth: auto`, fed `IStereoDepth.Output` / `IMatcher.Output`-shaped objects like MACVO.py does"""
+    from types import SimpleNamespace as NS
+    from macvo_b200 import plugins as P
+    g = golden(f"selector_{name}.pt")
+    H, W = g["shape"]
+    (f0, c0), (f1, c1) = cases.selector_depth_inputs(H, W, g["variant"])
+    d0 = ops.dense_postproc(f0.to(DEV), c0.to(DEV), 0.25 * 320.0, g["variant"] == "masked")
+    d1 = ops.dense_postproc(f1.to(DEV), c1.to(DEV), 0.25 * 320.0, False)
+    cfg = NS(device=DEV, mask_width=32, max_depth="auto", kernel_size=7, max_depth_cov=250.0, max_match_cov=100.0)
+    P.B200_CovAwareSelector.is_valid_config(cfg)
+    sel = P.B200_CovAwareSelector(cfg)
+    depth0 = NS(depth=d0["depth"], cov=d0["depth_cov"], mask=(~d0["depth_mask"] if g["variant"] == "masked" else None))
+    depth1 = NS(depth=d1["depth"], cov=d1["depth_cov"], mask=None)
+    match = NS(flow=d1["flow"], cov=d1["flow_cov"], mask=(cases.selector_match_mask(H, W).to(DEV) if g["variant"] == "masked" else None))
+    frame = NS(fx=320.0, frame_baseline=0.25)
+    torch.manual_seed(cases.SELECTOR_RNG_SEED)
+    kp = sel.select_point(frame, g["num"], depth0, depth1, match)
+    assert torch.equal(kp.cpu(), g["kp"]) and sel.config.max_depth == 80.0
