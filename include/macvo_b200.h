@@ -209,6 +209,20 @@ int macvo_pgo_solve(const double* pos_Tw, const double* kp2_uv, const double* kp
                     const double* disp_cov, int k, const double* intr, double* pose_io,
                     const macvo_pgo_params_t* params, double* stats, void* stream);
 
+/* The other graph types of TwoFrame_PGO (TwoFramePGO/Optimizer.py:51-68, analytic Jacobians Graphs.py:151-198):
+ *   MACVO_PGO_DISP   (0) reprojection + disparity  (= macvo_pgo_solve)
+ *   MACVO_PGO_REPROJ (1) reprojection only: kp2_disp / disp_cov unused (may be NULL)
+ *   MACVO_PGO_ICP    (2) r = T p_c - p_w with p_c = pc_obs (k,3) [pixel2point_NED(pixel2_uv, pixel2_d), camera frame], block
+ *                        covariance R obs_cov R^T + pts_cov ((k,3,3) float64 each: obs2_covTc, cov_Tw), re-inverted at every
+ *                        linearisation like the reference's driver loop; kp2_uv / kp2_disp / uv_cov / disp_cov unused. */
+#define MACVO_PGO_DISP 0
+#define MACVO_PGO_REPROJ 1
+#define MACVO_PGO_ICP 2
+int macvo_pgo_solve_graph(int graph_type, const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
+                          const double* uv_cov, const double* disp_cov, const double* pc_obs, const double* obs_cov,
+                          const double* pts_cov, int k, const double* intr, double* pose_io,
+                          const macvo_pgo_params_t* params, double* stats, void* stream);
+
 /* Same solve with the residual-block count read on the DEVICE (k = min(*k_dev, k_capacity)), so that the
  * observation kernel's survivor count never visits the host; fewer than min_k blocks ("lost track",
  * Odometry/MACVO.py:300-305: the optimiser is not started) leaves pose_io untouched and sets stats[6] = 1.

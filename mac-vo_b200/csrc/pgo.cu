@@ -117,6 +117,11 @@ __device__ void exchange_ranks(const Problem& P, Shared& S, cg::cluster_group& c
 
 struct Problem {
     const double *pos, *uv, *disp, *uvcov, *dcov;
+    // graph type (TwoFramePGO/Optimizer.py:51-68): 0 "disp" reprojection + disparity (Graphs.py:121-148), 1 "reproj"
+    // reprojection only (:76-118), 2 "icp" point alignment (:33-73) with pc_obs (k,3) = pixel2point_NED(pixel2_uv, pixel2_d),
+    // obs_cov / pts_cov (k,3,3) = obs2_covTc / cov_Tw: covariance R Sigma_obs R^T + Sigma_pts, re-inverted at every linearisation
+    int gtype;
+    const double *pc_obs, *obs_cov, *pts_cov;
     int k;
     const int* k_dev;          // optional device-side block count (<= k): the observation kernel's survivor count
     int k_offset;              // sharded + k_dev: this rank owns global blocks [k_offset, k_offset + k) of the *k_dev valid ones
@@ -157,63 +162,99 @@ __device__ void accumulate_full(const Problem& P, const double* posevec, Shared&
     kind1 = classify(e1, i1, j1);
 
     for (int k = gwarp; k < P.k; k += nwarps) {
-        double pc[3], r[3];
-        to_camera(T, P.pos + 3 * k, pc);
-        residual3(P.K, pc, P.uv[2 * k], P.uv[2 * k + 1], P.disp[k], r);
-        const double x = pc[0], y = pc[1], z = pc[2], ix = 1.0 / x, ix2 = ix * ix;
-        // J_p = [-R^T | R^T [p_w]x]  (3x6);  J = [J_h J_p ; (-bl fx / x^2) J_p[0,:]]
-        const double* pw = P.pos + 3 * k;
-        // column c of J_p for this lane (lanes 0..17 own (row a, column c) of the 3x6 Jacobian)
-        const int ja = lane / 6, jc = lane - ja * 6;
-        double jp0 = 0.0, jp1 = 0.0, jp2 = 0.0;                                   // J_p[0..2][jc]
-        if (lane < 18) {
-            if (jc < 3) {                                                          // -R^T: (R^T)[a][c] = R[c][a]
-                jp0 = -S.Rm[3 * jc + 0]; jp1 = -S.Rm[3 * jc + 1]; jp2 = -S.Rm[3 * jc + 2];
-            } else {                                                               // R^T [p_w]x
-                const int m = jc - 3, n1 = (m + 1) % 3, n2 = (m + 2) % 3;
-                const double p1 = pw[n2], p2 = pw[n1];
-                jp0 = S.Rm[3 * n1 + 0] * p1 - S.Rm[3 * n2 + 0] * p2;
-                jp1 = S.Rm[3 * n1 + 1] * p1 - S.Rm[3 * n2 + 1] * p2;
-                jp2 = S.Rm[3 * n1 + 2] * p1 - S.Rm[3 * n2 + 2] * p2;
+        double r[3];
+        const int ja = lane / 6, jc = lane - ja * 6;     // lanes 0..17 own (row ja, column jc) of the 3x6 Jacobian
+        double j0v = 0.0, j1v = 0.0, j2v = 0.0;          // column jc of J (rows 0..2)
+        double w00, w01, w02 = 0.0, w11, w12 = 0.0, w22; // symmetric information matrix of the block
+        bool singular = false;
+        if (P.gtype == 2) {
+            // ---- icp: r = T p_c - p_w,  J = [I | -[T p_c]x],  W = pinv(R Sigma_obs R^T + Sigma_pts) ----
+            const double* p = P.pc_obs + 3 * k;
+            const double* pw = P.pos + 3 * k;
+            double q[3];
+            for (int a = 0; a < 3; ++a) q[a] = S.Rm[3 * a] * p[0] + S.Rm[3 * a + 1] * p[1] + S.Rm[3 * a + 2] * p[2] + T.t[a];
+            r[0] = q[0] - pw[0]; r[1] = q[1] - pw[1]; r[2] = q[2] - pw[2];
+            if (lane < 18) {
+                if (jc < 3) { j0v = jc == 0; j1v = jc == 1; j2v = jc == 2; }
+                else if (jc == 3) { j0v = 0.0; j1v = -q[2]; j2v = q[1]; }       // -[q]x columns
+                else if (jc == 4) { j0v = q[2]; j1v = 0.0; j2v = -q[0]; }
+                else { j0v = -q[1]; j1v = q[0]; j2v = 0.0; }
             }
+            const double* So = P.obs_cov + 9LL * k;
+            const double* Sp = P.pts_cov + 9LL * k;
+            double RS[9], M[9];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) RS[3 * i + j] = S.Rm[3 * i] * So[j] + S.Rm[3 * i + 1] * So[3 + j] + S.Rm[3 * i + 2] * So[6 + j];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    M[3 * i + j] = RS[3 * i] * S.Rm[3 * j] + RS[3 * i + 1] * S.Rm[3 * j + 1] + RS[3 * i + 2] * S.Rm[3 * j + 2] + Sp[3 * i + j];
+            // inverse of the (symmetrised) 3x3 by cofactors; torch.pinverse == inverse for the positive-definite blocks of this
+            // path; a singular block gets zero weight and is flagged
+            const double m00 = M[0], m01 = 0.5 * (M[1] + M[3]), m02 = 0.5 * (M[2] + M[6]), m11 = M[4], m12 = 0.5 * (M[5] + M[7]), m22 = M[8];
+            const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
+            const double det = m00 * c00 + m01 * c01 + m02 * c02;
+            const double scl = fabs(m00 * m11 * m22) + 1e-300;
+            if (fabs(det) > 1e-13 * scl && isfinite(det)) {
+                const double id = 1.0 / det;
+                w00 = c00 * id; w01 = c01 * id; w02 = c02 * id;
+                w11 = (m00 * m22 - m02 * m02) * id; w12 = (m01 * m02 - m00 * m12) * id; w22 = (m00 * m11 - m01 * m01) * id;
+            } else { w00 = w01 = w02 = w11 = w12 = w22 = 0.0; singular = true; }
+        } else {
+            double pc[3];
+            to_camera(T, P.pos + 3 * k, pc);
+            residual3(P.K, pc, P.uv[2 * k], P.uv[2 * k + 1], P.gtype == 0 ? P.disp[k] : 0.0, r);
+            const double x = pc[0], y = pc[1], z = pc[2], ix = 1.0 / x, ix2 = ix * ix;
+            // J_p = [-R^T | R^T [p_w]x]  (3x6);  J = [J_h J_p ; (-bl fx / x^2) J_p[0,:]]
+            const double* pw = P.pos + 3 * k;
+            double jp0 = 0.0, jp1 = 0.0, jp2 = 0.0;                                   // J_p[0..2][jc]
+            if (lane < 18) {
+                if (jc < 3) {                                                          // -R^T: (R^T)[a][c] = R[c][a]
+                    jp0 = -S.Rm[3 * jc + 0]; jp1 = -S.Rm[3 * jc + 1]; jp2 = -S.Rm[3 * jc + 2];
+                } else {                                                               // R^T [p_w]x
+                    const int m = jc - 3, n1 = (m + 1) % 3, n2 = (m + 2) % 3;
+                    const double p1 = pw[n2], p2 = pw[n1];
+                    jp0 = S.Rm[3 * n1 + 0] * p1 - S.Rm[3 * n2 + 0] * p2;
+                    jp1 = S.Rm[3 * n1 + 1] * p1 - S.Rm[3 * n2 + 1] * p2;
+                    jp2 = S.Rm[3 * n1 + 2] * p1 - S.Rm[3 * n2 + 2] * p2;
+                }
+            }
+            const double h00 = -P.K.fx * y * ix2, h01 = P.K.fx * ix, h10 = -P.K.fy * z * ix2, h12 = P.K.fy * ix;
+            const double hd = P.gtype == 0 ? -(P.K.bl * P.K.fx) * ix2 : 0.0;     // reproj: no disparity row
+            if (P.gtype == 1) r[2] = 0.0;
+            j0v = h00 * jp0 + h01 * jp1;
+            j1v = h10 * jp0 + h12 * jp2;
+            j2v = hd * jp0;
+            // information matrix of the block: inverse of [[a, c, 0], [c, b, 0], [0, 0, e]]
+            const double ca = P.uvcov[3 * k], cb = P.uvcov[3 * k + 1], cc = P.uvcov[3 * k + 2], ce = P.gtype == 0 ? P.dcov[k] : 1.0;
+            // the reference takes torch.pinverse of every covariance block (Optimizer.py:96-99): identical to the inverse
+            // for the positive-definite blocks of this path; a rank-deficient block gets its Moore-Penrose weight (rank-1
+            // symmetric M: M / trace(M)^2; zero block: zero weight) instead of inf / NaN, and is reported in stats[7]
+            const double det = ca * cb - cc * cc, scale2 = ca * cb + cc * cc;
+            if (fabs(det) > 1e-14 * scale2 && isfinite(det)) {
+                const double idet = 1.0 / det;
+                w00 = cb * idet; w11 = ca * idet; w01 = -cc * idet;
+            } else {
+                const double tr = ca + cb, itr2 = (tr * tr > 0.0 && isfinite(tr)) ? 1.0 / (tr * tr) : 0.0;
+                w00 = ca * itr2; w11 = cb * itr2; w01 = cc * itr2;
+                singular = true;
+            }
+            if (fabs(ce) > 0.0 && isfinite(ce)) w22 = 1.0 / ce; else { w22 = 0.0; singular = true; }
         }
-        const double h00 = -P.K.fx * y * ix2, h01 = P.K.fx * ix, h10 = -P.K.fy * z * ix2, h12 = P.K.fy * ix;
-        const double hd = -(P.K.bl * P.K.fx) * ix2;
         const double nrm2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
         const double sn = sqrt(nrm2);
         const double s = sn < P.delta ? 1.0 : sqrt(P.delta / sn);              // FastTriggs: sqrt(rho'(|r|^2))
-        // information matrix of the block: inverse of [[a, c, 0], [c, b, 0], [0, 0, e]]
-        const double ca = P.uvcov[3 * k], cb = P.uvcov[3 * k + 1], cc = P.uvcov[3 * k + 2], ce = P.dcov[k];
-        // the reference takes torch.pinverse of every 3x3 covariance block (Graphs.py:139-148): identical to the inverse
-        // for the positive-definite blocks of this path; a rank-deficient block gets its Moore-Penrose weight (rank-1
-        // symmetric M: M / trace(M)^2; zero block: zero weight) instead of inf / NaN, and is reported in stats[7]
-        const double det = ca * cb - cc * cc, scale2 = ca * cb + cc * cc;
-        double w00, w11, w01, w22;
-        bool singular = false;
-        if (fabs(det) > 1e-14 * scale2 && isfinite(det)) {
-            const double idet = 1.0 / det;
-            w00 = cb * idet; w11 = ca * idet; w01 = -cc * idet;
-        } else {
-            const double tr = ca + cb, itr2 = (tr * tr > 0.0 && isfinite(tr)) ? 1.0 / (tr * tr) : 0.0;
-            w00 = ca * itr2; w11 = cb * itr2; w01 = cc * itr2;
-            singular = true;
-        }
-        if (fabs(ce) > 0.0 && isfinite(ce)) w22 = 1.0 / ce; else { w22 = 0.0; singular = true; }
         if (singular && lane == 0 && P.singular_flag) *P.singular_flag = 1.0;
         if (lane < 18) {
             const int a = ja;
-            const double j0v = h00 * jp0 + h01 * jp1;
-            const double j1v = h10 * jp0 + h12 * jp2;
-            const double j2v = hd * jp0;
-            const double jv = (a == 0 ? j0v : (a == 1 ? j1v : j2v)) * s;
-            S.sJ[warp][lane] = jv;
+            S.sJ[warp][lane] = (a == 0 ? j0v : (a == 1 ? j1v : j2v)) * s;
             // (W Js)[a][c]
-            const double wj = a == 0 ? (w00 * j0v + w01 * j1v) * s : (a == 1 ? (w01 * j0v + w11 * j1v) * s : w22 * j2v * s);
-            S.sWJ[warp][lane] = wj;
+            S.sWJ[warp][lane] = (a == 0 ? (w00 * j0v + w01 * j1v + w02 * j2v)
+                                        : (a == 1 ? (w01 * j0v + w11 * j1v + w12 * j2v) : (w02 * j0v + w12 * j1v + w22 * j2v))) * s;
         } else if (lane < 21) {
             const int a = lane - 18;
             S.sR[warp][a] = r[a] * s;
-            S.sWR[warp][a] = (a == 0 ? (w00 * r[0] + w01 * r[1]) : (a == 1 ? (w01 * r[0] + w11 * r[1]) : w22 * r[2])) * s;
+            S.sWR[warp][a] = (a == 0 ? (w00 * r[0] + w01 * r[1] + w02 * r[2])
+                                     : (a == 1 ? (w01 * r[0] + w11 * r[1] + w12 * r[2]) : (w02 * r[0] + w12 * r[1] + w22 * r[2]))) * s;
         }
         __syncwarp();
         auto entry = [&](int kind, int i, int j) -> double {
@@ -244,8 +285,15 @@ __device__ double evaluate_loss(const Problem& P, const double* posevec, Shared&
     double acc = 0.0;
     for (int k = gthread; k < P.k; k += nthreads) {
         double pc[3], r[3];
-        to_camera(T, P.pos + 3 * k, pc);
-        residual3(P.K, pc, P.uv[2 * k], P.uv[2 * k + 1], P.disp[k], r);
+        if (P.gtype == 2) {
+            const double* p = P.pc_obs + 3 * k;
+            for (int a = 0; a < 3; ++a)
+                r[a] = T.R[3 * a] * p[0] + T.R[3 * a + 1] * p[1] + T.R[3 * a + 2] * p[2] + T.t[a] - P.pos[3 * k + a];
+        } else {
+            to_camera(T, P.pos + 3 * k, pc);
+            residual3(P.K, pc, P.uv[2 * k], P.uv[2 * k + 1], P.gtype == 0 ? P.disp[k] : 0.0, r);
+            if (P.gtype == 1) r[2] = 0.0;
+        }
         acc += huber(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], P.delta);
     }
     acc = warp_sum(acc);                     // butterfly: every lane holds the same bits
@@ -533,12 +581,18 @@ int launch_cluster(const void* fn, int cluster, void** args, cudaStream_t st) {
 
 }  // namespace
 
+struct GraphExtra { int gtype; const double *pc_obs, *obs_cov, *pts_cov; };
+
 static int pgo_solve_impl(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
                           const double* uv_cov, const double* disp_cov, int k, const int* k_dev, int min_k,
                           const double* intr, double* pose_io, const macvo_pgo_params_t* params, double* stats,
-                          void* stream, void* const* peer_bufs = nullptr, int world = 1, int rank = 0, int k_offset = 0) {
-    if (k < 0 || !intr || !pose_io || !params) return MACVO_E_ARG;
-    if (k > 0 && (!pos_Tw || !kp2_uv || !kp2_disp || !uv_cov || !disp_cov)) return MACVO_E_ARG;
+                          void* stream, void* const* peer_bufs = nullptr, int world = 1, int rank = 0, int k_offset = 0,
+                          GraphExtra gx = GraphExtra{0, nullptr, nullptr, nullptr}) {
+    if (k < 0 || !intr || !pose_io || !params || gx.gtype < 0 || gx.gtype > 2) return MACVO_E_ARG;
+    if (k > 0 && !pos_Tw) return MACVO_E_ARG;
+    if (k > 0 && gx.gtype == 0 && (!kp2_uv || !kp2_disp || !uv_cov || !disp_cov)) return MACVO_E_ARG;
+    if (k > 0 && gx.gtype == 1 && (!kp2_uv || !uv_cov)) return MACVO_E_ARG;
+    if (k > 0 && gx.gtype == 2 && (!gx.pc_obs || !gx.obs_cov || !gx.pts_cov)) return MACVO_E_ARG;
     macvo_pgo_params_t prm = *params;
     if (prm.max_steps < 1 || prm.radius <= 0 || prm.huber_delta <= 0) return MACVO_E_ARG;
     int cluster = prm.cluster;
@@ -547,6 +601,7 @@ static int pgo_solve_impl(const double* pos_Tw, const double* kp2_uv, const doub
     Problem P;
     P.pos = pos_Tw; P.uv = kp2_uv; P.disp = kp2_disp; P.uvcov = uv_cov; P.dcov = disp_cov; P.k = k;
     P.k_dev = k_dev; P.k_offset = k_offset; P.min_k = min_k; P.singular_flag = stats ? stats + 7 : nullptr;
+    P.gtype = gx.gtype; P.pc_obs = gx.pc_obs; P.obs_cov = gx.obs_cov; P.pts_cov = gx.pts_cov;
     P.world = 1; P.rank = 0;
     if (peer_bufs != nullptr) {
         if (world < 2 || world > MACVO_PGO_MAX_RANKS || rank < 0 || rank >= world) return MACVO_E_ARG;
@@ -567,6 +622,14 @@ extern "C" int macvo_pgo_solve(const double* pos_Tw, const double* kp2_uv, const
                                const double* uv_cov, const double* disp_cov, int k, const double* intr,
                                double* pose_io, const macvo_pgo_params_t* params, double* stats, void* stream) {
     return pgo_solve_impl(pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov, k, nullptr, 0, intr, pose_io, params, stats, stream);
+}
+
+extern "C" int macvo_pgo_solve_graph(int graph_type, const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
+                                     const double* uv_cov, const double* disp_cov, const double* pc_obs,
+                                     const double* obs_cov, const double* pts_cov, int k, const double* intr,
+                                     double* pose_io, const macvo_pgo_params_t* params, double* stats, void* stream) {
+    return pgo_solve_impl(pos_Tw, kp2_uv, kp2_disp, uv_cov, disp_cov, k, nullptr, 0, intr, pose_io, params, stats, stream,
+                          nullptr, 1, 0, 0, GraphExtra{graph_type, pc_obs, obs_cov, pts_cov});
 }
 
 extern "C" int macvo_pgo_solve_counted(const double* pos_Tw, const double* kp2_uv, const double* kp2_disp,
@@ -633,6 +696,7 @@ extern "C" int macvo_pgo_accumulate(const double* pos_Tw, const double* kp2_uv, 
     Problem P;
     P.pos = pos_Tw; P.uv = kp2_uv; P.disp = kp2_disp; P.uvcov = uv_cov; P.dcov = disp_cov; P.k = k;
     P.k_dev = nullptr; P.k_offset = 0; P.min_k = 0; P.singular_flag = nullptr; P.world = 1; P.rank = 0;
+    P.gtype = 0; P.pc_obs = P.obs_cov = P.pts_cov = nullptr;
     P.K.fx = intr[0]; P.K.fy = intr[1]; P.K.cx = intr[2]; P.K.cy = intr[3]; P.K.bl = intr[4];
     P.delta = huber_delta;
     void* args[] = {&P, &pose, &acc};

@@ -65,6 +65,8 @@ EXPORTS = {
                                + [C.c_float] * 4 + [C.c_int] + [C.c_float] * 3 + [C.c_void_p] * 4),
     "macvo_pgo_solve": (C.c_int, [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2 + [C.POINTER(_PgoParams)]
                         + [C.c_void_p] * 2),
+    "macvo_pgo_solve_graph": (C.c_int, [C.c_int] + [C.c_void_p] * 8 + [C.c_int] + [C.c_void_p] * 2 + [C.POINTER(_PgoParams)]
+                              + [C.c_void_p] * 2),
     "macvo_pgo_solve_counted": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 2
                                 + [C.POINTER(_PgoParams)] + [C.c_void_p] * 2),
     "macvo_motion_interpolate_workspace_bytes": (C.c_size_t, [C.c_int]),
@@ -498,6 +500,32 @@ def pgo_solve(pos_Tw: Tensor, kp2_uv: Tensor, kp2_disp: Tensor, uv_cov: Tensor, 
     rc = lib.macvo_pgo_solve(*(t.data_ptr() for t in P), K, C.cast(intr_c, C.c_void_p), pose.data_ptr(),
                              C.byref(prm), stats.data_ptr(), _stream())
     _check(rc, "macvo_pgo_solve")
+    LAUNCHES[0] += 1
+    return pose, stats
+
+
+PGO_GRAPH_TYPES = {"disp": 0, "reproj": 1, "icp": 2}
+
+
+def pgo_solve_graph(graph_type: str, pos_Tw: Tensor, intr: tuple[float, float, float, float, float], init_pose: Tensor,
+                    kp2_uv: Tensor | None = None, kp2_disp: Tensor | None = None, uv_cov: Tensor | None = None,
+                    disp_cov: Tensor | None = None, pc_obs: Tensor | None = None, obs_cov: Tensor | None = None,
+                    pts_cov: Tensor | None = None, cluster: int = 0, **kw):
+    """TwoFrame_PGO for any of its graph types ("disp" | "reproj" | "icp", Optimizer.py:51-68); CUDA float64 inputs."""
+    lib = load_library()
+    gt = PGO_GRAPH_TYPES[graph_type]
+    d = lambda t, w: None if t is None else _dev(t, torch.float64, f"pgo_solve_graph {w}")
+    pos = d(pos_Tw, "pos_Tw")
+    arrs = [d(kp2_uv, "kp2_uv"), d(kp2_disp, "kp2_disp"), d(uv_cov, "uv_cov"), d(disp_cov, "disp_cov"), d(pc_obs, "pc_obs"),
+            d(obs_cov, "obs_cov"), d(pts_cov, "pts_cov")]
+    K = pos.shape[0]
+    pose = _dev(init_pose, torch.float64, "pgo_solve_graph init_pose").reshape(7).clone()
+    stats = torch.zeros((8,), dtype=torch.float64, device=pose.device)
+    intr_c = (C.c_double * 5)(*[float(v) for v in intr])
+    prm = _pgo_params(cluster=cluster, **kw)
+    rc = lib.macvo_pgo_solve_graph(gt, pos.data_ptr(), *(None if a is None else a.data_ptr() for a in arrs), K,
+                                   C.cast(intr_c, C.c_void_p), pose.data_ptr(), C.byref(prm), stats.data_ptr(), _stream())
+    _check(rc, "macvo_pgo_solve_graph")
     LAUNCHES[0] += 1
     return pose, stats
 

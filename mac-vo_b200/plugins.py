@@ -480,6 +480,10 @@ class PGOInput:
     init_pose: torch.Tensor     # (7,) [t, q_xyzw]
     frame_idx: torch.Tensor | None = None
     from_idx: torch.Tensor | None = None
+    # graph type "icp" (Graphs.py:33-73) additionally reads:
+    kp2_d: torch.Tensor | None = None       # (K,) or (K,1) pixel2_d
+    obs_cov: torch.Tensor | None = None     # (K,3,3) float64 obs2_covTc
+    pts_cov: torch.Tensor | None = None     # (K,3,3) float64 cov_Tw
 
 
 @dataclass
@@ -490,27 +494,40 @@ class PGOOutput:
     stats: torch.Tensor | None = None
 
 
-def solve_two_frame_pgo(inp: PGOInput, device, cluster: int = 0) -> tuple[torch.Tensor, torch.Tensor]:
+def solve_two_frame_pgo(inp: PGOInput, device, cluster: int = 0, graph_type: str = "disp") -> tuple[torch.Tensor, torch.Tensor]:
     """fp32 map values -> float64 (the reference's `.to(dtype=torch.double)`, Optimizer.py:85) -> one launch."""
     f64 = lambda t: t.detach().to(device=device, dtype=torch.float64, non_blocking=True).contiguous()
     K = inp.K.detach().double().cpu()
     intr = (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]),
             float(torch.as_tensor(inp.baseline, dtype=torch.float32).double().reshape(-1)[0]))
-    return ops.pgo_solve(f64(inp.pos_Tw), f64(inp.kp2_uv), f64(inp.kp2_disp).reshape(-1), f64(inp.uv_cov),
-                         f64(inp.disp_cov).reshape(-1), intr, f64(inp.init_pose).reshape(7), cluster=cluster)
+    if graph_type == "disp":
+        return ops.pgo_solve(f64(inp.pos_Tw), f64(inp.kp2_uv), f64(inp.kp2_disp).reshape(-1), f64(inp.uv_cov),
+                             f64(inp.disp_cov).reshape(-1), intr, f64(inp.init_pose).reshape(7), cluster=cluster)
+    if graph_type == "reproj":
+        return ops.pgo_solve_graph("reproj", f64(inp.pos_Tw), intr, f64(inp.init_pose).reshape(7), kp2_uv=f64(inp.kp2_uv),
+                                   uv_cov=f64(inp.uv_cov), cluster=cluster)
+    # icp: points_Tc = pixel2point_NED(pixel2_uv, pixel2_d, K) is a registered fp32 buffer of the reference graph (Graphs.py:49-51)
+    uv = inp.kp2_uv.detach().to(device=device, dtype=torch.float32)
+    d = inp.kp2_d.detach().to(device=device, dtype=torch.float32).reshape(-1)
+    Kf = inp.K.detach().to(device=device, dtype=torch.float32)
+    pc = torch.stack([d, (uv[:, 0] - Kf[0, 2]) / Kf[0, 0] * d, (uv[:, 1] - Kf[1, 2]) / Kf[1, 1] * d], dim=-1)
+    return ops.pgo_solve_graph("icp", f64(inp.pos_Tw), intr, f64(inp.init_pose).reshape(7), pc_obs=pc.double().contiguous(),
+                               obs_cov=f64(inp.obs_cov), pts_cov=f64(inp.pts_cov), cluster=cluster)
 
 
 class B200_TwoFrame_PGO(_PGOBase):
-    """Replacement of TwoFrame_PGO (graph_type "disp", analytic Jacobian): the whole Levenberg-Marquardt loop is
+    """Replacement of TwoFrame_PGO (graph types "disp" / "reproj" / "icp", analytic Jacobians): the whole Levenberg-Marquardt loop is
     one persistent kernel launch; `start_optimize` returns immediately and `write_map` synchronises on the
     result, which preserves the frontend / optimiser overlap MAC-VO gets from its spawned CPU process."""
 
     @staticmethod
     def init_context(config) -> dict:
-        if getattr(config, "graph_type", "disp") != "disp" or getattr(config, "autodiff", False):
-            raise ValueError("B200_TwoFrame_PGO implements graph_type 'disp' with the analytic Jacobian "
-                             "(the MACVO_Performant / MACVO_Fast configuration)")
-        return {"device": _require_cuda(config.device, "B200_TwoFrame_PGO"), "cluster": int(getattr(config, "cluster", 0))}
+        gt = getattr(config, "graph_type", "disp")
+        if gt not in ("disp", "reproj", "icp") or getattr(config, "autodiff", False):
+            raise ValueError("B200_TwoFrame_PGO implements graph_type 'disp' / 'reproj' / 'icp' with the analytic Jacobians "
+                             "(autodiff: false)")
+        return {"device": _require_cuda(config.device, "B200_TwoFrame_PGO"), "cluster": int(getattr(config, "cluster", 0)),
+                "graph_type": gt}
 
     @staticmethod
     def _optimize(context: dict, graph_data):
@@ -522,7 +539,9 @@ class B200_TwoFrame_PGO(_PGOBase):
                            uv_cov=obs["pixel2_uv_cov"], disp_cov=obs["pixel2_disp_cov"], K=graph_data.images_intrinsic,
                            baseline=graph_data.baseline, init_pose=torch.as_tensor(graph_data.init_motion).reshape(-1)[:7],
                            frame_idx=graph_data.frame_idx, from_idx=graph_data.from_idx)
-        pose, stats = solve_two_frame_pgo(inp, context["device"], context["cluster"])
+            if context.get("graph_type") == "icp":
+                inp.kp2_d, inp.obs_cov, inp.pts_cov = obs["pixel2_d"], obs["obs2_covTc"], pts["cov_Tw"]
+        pose, stats = solve_two_frame_pgo(inp, context["device"], context["cluster"], context.get("graph_type", "disp"))
         if _REF and not isinstance(graph_data, PGOInput):
             return context, _RefGraphOutput(motion=pose.reshape(1, 7), frame_idx=inp.frame_idx, from_idx=inp.from_idx)
         return context, PGOOutput(motion=pose.reshape(1, 7), frame_idx=inp.frame_idx, from_idx=inp.from_idx, stats=stats)

@@ -125,29 +125,49 @@ class GraphData:
     cy: float
     baseline: float
     init_pose: np.ndarray   # (7,)
+    # graph type (TwoFramePGO/Optimizer.py:51-68): "disp" = reprojection + disparity (Graphs.py:121-148, MACVO_Performant /
+    # _Fast), "reproj" = reprojection only (:76-118), "icp" = 3-D point alignment (:33-73, Paper_Reproduce.yaml)
+    graph_type: str = "disp"
+    pc_obs: np.ndarray | None = None     # icp: (K,3) observed points in the camera frame = pixel2point_NED(pixel2_uv, pixel2_d)
+    obs_cov: np.ndarray | None = None    # icp: (K,3,3) obs2_covTc
+    pts_cov: np.ndarray | None = None    # icp: (K,3,3) cov_Tw of the map points
 
-    def cov_blocks(self) -> np.ndarray:
+    def cov_blocks(self, pose: np.ndarray | None = None) -> np.ndarray:
+        """`covariance_array()` of the graph; pose dependent for icp (R Sigma_obs R^T + Sigma_pts, Graphs.py:61-66)"""
         K = self.pos_Tw.shape[0]
+        if self.graph_type == "icp":
+            R = quat_matrix((self.init_pose if pose is None else pose)[3:])
+            return R @ self.obs_cov @ R.T + self.pts_cov
         c = np.zeros((K, 3, 3))
         c[:, 0, 0], c[:, 1, 1] = self.uv_cov[:, 0], self.uv_cov[:, 1]
         c[:, 0, 1] = c[:, 1, 0] = self.uv_cov[:, 2]
-        c[:, 2, 2] = self.disp_cov
+        # reproj: the block is 2x2 (Graphs.py:95-101); carried as a 3x3 whose third row / column never meets a residual
+        c[:, 2, 2] = self.disp_cov if self.graph_type == "disp" else 1.0
         return c
 
 
 def residual(g: GraphData, pose: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
     """-> R (K,3), pos_Tc (K,3).  r = [fx y/x + cx - u, fy z/x + cy - v, fx bl / x - disp] (NED: x fwd)."""
+    if g.graph_type == "icp":                       # frame_pose.Act(points_Tc) - points_Tw  (Graphs.py:56-58)
+        pw = se3_act(pose, g.pc_obs)
+        return pw - g.pos_Tw, pw
     pc = se3_act(se3_inv(pose), g.pos_Tw)
     x, y, z = pc[:, 0], pc[:, 1], pc[:, 2]
+    third = (1.0 / x) * (g.fx * g.baseline) - g.kp2_disp if g.graph_type == "disp" else np.zeros_like(x)
     r = np.stack([g.fx * y / x + g.cx - g.kp2_uv[:, 0],
                   g.fy * z / x + g.cy - g.kp2_uv[:, 1],
-                  (1.0 / x) * (g.fx * g.baseline) - g.kp2_disp], axis=-1)
+                  third], axis=-1)
     return r, pc
 
 
 def jacobian(g: GraphData, pose: np.ndarray, pc: np.ndarray) -> np.ndarray:
     """(K,3,7); column 7 is identically 0 (pypose's 7-wide SE3 parameter)."""
     K = pc.shape[0]
+    if g.graph_type == "icp":                       # J = [I | -[T p_c]x]  (Graphs.py:151-167); pc holds T p_c here
+        J = np.zeros((K, 3, 7))
+        J[:, :, :3] = np.eye(3)
+        J[:, :, 3:6] = -skew(pc)
+        return J
     x, y, z = pc[:, 0], pc[:, 1], pc[:, 2]
     x2 = x ** 2
     Jh = np.zeros((K, 2, 3))
@@ -159,6 +179,8 @@ def jacobian(g: GraphData, pose: np.ndarray, pc: np.ndarray) -> np.ndarray:
     Jp[:, :, 3:6] = RT @ skew(g.pos_Tw)
     Jr = Jh @ Jp
     Jd = (-(g.baseline * g.fx) / x2).reshape(-1, 1, 1) * Jp[:, 0:1, :]
+    if g.graph_type == "reproj":
+        Jd = np.zeros_like(Jd)
     return np.concatenate([Jr, Jd], axis=1)
 
 
@@ -204,14 +226,18 @@ def lm_solve(g: GraphData, max_steps: int = 10, patience: int = 2, decreasing: f
              radius: float = 1e3, reject: int = 16, diag_min: float = 1e-6, diag_max: float = 1e32,
              trace: LMTrace | None = None) -> np.ndarray:
     """Returns the optimised pose (7,) fp64."""
-    W = np.stack([np.linalg.pinv(c, rcond=1e-15) for c in g.cov_blocks()]) if g.pos_Tw.shape[0] else np.zeros((0, 3, 3))
     pose = np.asarray(g.init_pose, dtype=np.float64).copy()
+    weights = lambda p: (np.stack([np.linalg.pinv(c, rcond=1e-15) for c in g.cov_blocks(p)]) if g.pos_Tw.shape[0]
+                         else np.zeros((0, 3, 3)))
+    W = weights(pose)
     # TrustRegion(radius) defaults: high .5, low 1e-3, up 2, down .5, factor .5, clamp [1e-3, 1e5]
     tr = {"damping": 1.0 / radius, "down": 0.5}
     TR_MIN, TR_MAX, HIGH, LOW, UP, DOWN, FACTOR = 1e-3, 1e5, 0.5, 1e-3, 2.0, 0.5, 0.5
     loss = None
     steps, patience_count = 0, 0
     while True:
+        if g.graph_type == "icp":       # the driver recomputes `weight` from covariance_array() before every step (Optimizer.py:96-100)
+            W = weights(pose)
         A, b, Js, Rs = normal_equations(g, pose, W, delta)
         if loss is None:
             loss = robust_loss(g, pose, delta)
@@ -266,7 +292,7 @@ def accumulate_packed(g: GraphData, pose: np.ndarray, delta: float = 0.1, W: np.
     """The 55-entry packed accumulator of the sharded (multi-GPU) path, for a shard `g` of residual blocks:
     [A = Js^T W Js upper 6x6 (21) | b = -Js^T W Rs (6) | G = Js^T Js upper (21) | h = Js^T Rs (6) | robust loss (1)]."""
     if W is None:
-        W = np.stack([np.linalg.pinv(c, rcond=1e-15) for c in g.cov_blocks()]) if g.pos_Tw.shape[0] else np.zeros((0, 3, 3))
+        W = np.stack([np.linalg.pinv(c, rcond=1e-15) for c in g.cov_blocks(pose)]) if g.pos_Tw.shape[0] else np.zeros((0, 3, 3))
     A, b, Js, Rs = normal_equations(g, pose, W, delta)
     iu = np.triu_indices(6)
     G = np.einsum("kai,kaj->ij", Js, Js)

@@ -192,6 +192,11 @@ class LieTensor(torch.Tensor):
                 out = type(out)(tag(o) for o in out)
             else:
                 out = tag(out)
+            # indexing a pp.Parameter (nn.Parameter disables subclass propagation) must still give a Lie element:
+            # `self.pose2opt[self.edges_index]` in the ICP graph (TwoFramePGO/Graphs.py:57,64,156)
+            if (func is torch.Tensor.__getitem__ and type(out) is torch.Tensor and out.dim() > 0
+                    and out.shape[-1] == src.ltype.dim and out.dtype.is_floating_point):
+                out = LieTensor(out, ltype=src.ltype)
         return out
 
     def __repr__(self):

@@ -209,6 +209,26 @@ def pgo_inputs(K: int, seed: int) -> dict:
     }
 
 
+PGO_TYPE_CASES = {"icp_k64": ("icp", 64, 6), "icp_k512": ("icp", 512, 6), "icp_far": ("icp", 200, 9),
+                  "reproj_k64": ("reproj", 64, 6), "reproj_k512": ("reproj", 512, 6), "reproj_far": ("reproj", 200, 9)}
+
+
+def pgo_inputs_typed(graph_type: str, K: int, seed: int) -> dict:
+    """`pgo_inputs` + what the icp graph reads (Graphs.py:46-55): pixel2_d, obs2_covTc, cov_Tw (float64 SPD blocks)"""
+    from oracle import pgo as opgo
+    c = pgo_inputs(K, seed)
+    rng = np.random.default_rng(seed * 104729 + K + len(graph_type))
+    pc = opgo.se3_act(opgo.se3_inv(c["true_pose"].numpy()), c["pos_Tw"].double().numpy())
+    c["kp2_d"] = torch.tensor(pc[:, 0] * (1 + rng.normal(size=K) * 0.01), dtype=torch.float32)
+
+    def spd(scale):
+        a = rng.normal(size=(K, 3, 3)) * scale
+        return torch.tensor(a @ a.transpose(0, 2, 1) + np.eye(3) * scale * scale * 0.5)
+    c["obs_cov"], c["pts_cov"] = spd(0.2), spd(0.1)
+    c["graph_type"] = graph_type
+    return c
+
+
 def pgo_graph(c: dict):
     """cases dict -> oracle.pgo.GraphData (fp32 values promoted to fp64, like `.to(torch.double)`)."""
     from oracle import pgo as opgo
@@ -218,7 +238,17 @@ def pgo_graph(c: dict):
         uv_cov=c["uv_cov"].double().numpy(), disp_cov=c["disp_cov"].double().numpy(),
         fx=float(K[0, 0]), fy=float(K[1, 1]), cx=float(K[0, 2]), cy=float(K[1, 2]),
         baseline=float(torch.tensor([c["baseline"]]).double().item()),
-        init_pose=c["init_pose"].double().numpy())
+        init_pose=c["init_pose"].double().numpy(), **_typed_fields(c))
+
+
+def _typed_fields(c: dict) -> dict:
+    gt = c.get("graph_type", "disp")
+    if gt != "icp":
+        return {"graph_type": gt}
+    from oracle import covariance as ocov
+    pc = ocov.pixel2point_ned(c["kp2_uv"], c["kp2_d"], c["K"])           # fp32 like the registered buffer, then .double()
+    return {"graph_type": gt, "pc_obs": pc.double().numpy(), "obs_cov": c["obs_cov"].double().numpy(),
+            "pts_cov": c["pts_cov"].double().numpy()}
 
 
 # ---- 640x480 / depth-12 network parity ladder (BASELINE configs[1] shape) -------------------------------------------
@@ -288,6 +318,9 @@ def golden_input_shas() -> dict:
     for name, (K, seed) in PGO_CASES.items():
         c = pgo_inputs(K, seed)
         out[f"pgo_{name}.pt"] = sha(*[c[k] for k in ("pos_Tw", "kp2_uv", "kp2_disp", "uv_cov", "disp_cov")])
+    for name, (gt, K, seed) in PGO_TYPE_CASES.items():
+        c = pgo_inputs_typed(gt, K, seed)
+        out[f"pgo_{name}.pt"] = sha(*[c[k] for k in ("pos_Tw", "kp2_uv", "kp2_disp", "uv_cov", "disp_cov", "kp2_d", "obs_cov", "pts_cov")])
     for name, (F, seed, flagged) in MOTION_CASES.items():
         p, n = motion_inputs(F, seed, flagged)
         out[f"motion_{name}.pt"] = sha(p, n.to(torch.uint8))

@@ -161,22 +161,23 @@ def main() -> None:
         save(f"covariance_{name}.pt", {"shape": (H, W, K), "kind": kind, "out": out,
                                        "flow_cov_after": fc, "input_sha": cases.sha(kp, depth_map, flow_cov)})
 
-    # ---- two-frame PGO (a13-a16) --------------------------------------------------------------
-    for name, (K, seed) in cases.PGO_CASES.items():
-        c = cases.pgo_inputs(K, seed)
+    # ---- two-frame PGO (a13-a16): the three graph types ------------------------------------------
+    def run_pgo(c, graph_type):
+        K = c["pos_Tw"].shape[0]
         obs = MatchObs.init({
             "pixel1_uv": torch.zeros(K, 2), "pixel2_uv": c["kp2_uv"],
-            "pixel1_d": torch.zeros(K, 1), "pixel2_d": torch.zeros(K, 1),
+            "pixel1_d": torch.zeros(K, 1), "pixel2_d": c.get("kp2_d", torch.zeros(K)).unsqueeze(-1),
             "pixel1_disp": torch.zeros(K, 1), "pixel2_disp": c["kp2_disp"].unsqueeze(-1),
             "pixel1_disp_cov": torch.zeros(K, 1), "pixel2_disp_cov": c["disp_cov"].unsqueeze(-1),
             "pixel1_d_cov": torch.zeros(K, 1), "pixel2_d_cov": torch.zeros(K, 1),
             "pixel1_uv_cov": torch.zeros(K, 3), "pixel2_uv_cov": c["uv_cov"],
-            "obs1_covTc": torch.zeros(K, 3, 3, dtype=torch.double), "obs2_covTc": torch.zeros(K, 3, 3, dtype=torch.double)})
-        pts = PointNode.init({"pos_Tw": c["pos_Tw"], "cov_Tw": torch.zeros(K, 3, 3, dtype=torch.double),
+            "obs1_covTc": torch.zeros(K, 3, 3, dtype=torch.double),
+            "obs2_covTc": c.get("obs_cov", torch.zeros(K, 3, 3, dtype=torch.double))})
+        pts = PointNode.init({"pos_Tw": c["pos_Tw"], "cov_Tw": c.get("pts_cov", torch.zeros(K, 3, 3, dtype=torch.double)),
                               "color": torch.zeros(K, 3, dtype=torch.uint8)})
         gi = GraphInput(torch.tensor([1]), torch.tensor([0]), pp.SE3(c["init_pose"].unsqueeze(0)),
                         torch.tensor([c["baseline"]]), obs, pts, c["K"], torch.zeros(K, dtype=torch.long), "cpu")
-        ctx = TwoFrame_PGO.init_context(SimpleNamespace(autodiff=False, graph_type="disp", device="cpu",
+        ctx = TwoFrame_PGO.init_context(SimpleNamespace(autodiff=False, graph_type=graph_type, device="cpu",
                                                         vectorize=True, parallel=False))
         # `_optimize` asks for torch.cuda.current_stream() only to hand it to an inactive Timer
         # (Optimizer.py:83-84); this container has no CUDA driver, so give it a placeholder.
@@ -185,7 +186,16 @@ def main() -> None:
             _, out = TwoFrame_PGO._optimize(ctx, gi)
         finally:
             torch.cuda.current_stream = _cs
-        save(f"pgo_{name}.pt", {"K": K, "seed": seed, "input_sha": cases.sha(*[c[k] for k in ("pos_Tw", "kp2_uv", "kp2_disp", "uv_cov", "disp_cov")]), "pose": out.motion.detach().as_subclass(torch.Tensor).clone().reshape(7)})
+        return out.motion.detach().as_subclass(torch.Tensor).clone().reshape(7)
+
+    for name, (K, seed) in cases.PGO_CASES.items():
+        c = cases.pgo_inputs(K, seed)
+        save(f"pgo_{name}.pt", {"K": K, "seed": seed, "input_sha": cases.sha(*[c[k] for k in ("pos_Tw", "kp2_uv", "kp2_disp", "uv_cov", "disp_cov")]),
+                                "pose": run_pgo(c, "disp")})
+    for name, (gt, K, seed) in cases.PGO_TYPE_CASES.items():
+        c = cases.pgo_inputs_typed(gt, K, seed)
+        save(f"pgo_{name}.pt", {"K": K, "seed": seed, "graph_type": gt, "pose": run_pgo(c, gt),
+                                "input_sha": cases.sha(*[c[k] for k in ("pos_Tw", "kp2_uv", "kp2_disp", "uv_cov", "disp_cov", "kp2_d", "obs_cov", "pts_cov")])})
 
     # ---- trajectory post-process at terminate() (f4) --------------------------------------------
     from Module.MapProcessor import MotionInterpolate

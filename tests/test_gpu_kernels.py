@@ -492,3 +492,27 @@ def test_depth_aware_selector_plugin_class(ops, golden, name):
     torch.manual_seed(cases.SELECTOR_RNG_SEED)
     kp = sel.select_point(frame, g["num"], depth0, depth1, match)
     assert torch.equal(kp.cpu(), g["kp"]) and sel.config.max_depth == 80.0
+
+
+@pytest.mark.parametrize("name", list(cases.PGO_TYPE_CASES))
+def test_pgo_other_graph_types(ops, golden, name):
+    """graph types "icp" / "reproj" of TwoFrame_PGO (Optimizer.py:51-68) in the same persistent kernel: pose 1e-8 vs the
+    fp64 oracle and vs the reference's LM_analytic run (golden), same accept / reject sequence; through the plugin adapter."""
+    from types import SimpleNamespace as NS
+    from macvo_b200 import plugins as P
+    g = golden(f"pgo_{name}.pt")
+    c = cases.pgo_inputs_typed(g["graph_type"], g["K"], g["seed"])
+    trace = opgo.LMTrace()
+    ref = opgo.lm_solve(cases.pgo_graph(c), trace=trace)
+    inp = P.PGOInput(pos_Tw=c["pos_Tw"], kp2_uv=c["kp2_uv"], kp2_disp=c["kp2_disp"], uv_cov=c["uv_cov"], disp_cov=c["disp_cov"],
+                     K=c["K"], baseline=c["baseline"], init_pose=c["init_pose"], kp2_d=c["kp2_d"], obs_cov=c["obs_cov"],
+                     pts_cov=c["pts_cov"])
+    for cluster in (1, 2):
+        pose, stats = P.solve_two_frame_pgo(inp, DEV, cluster, g["graph_type"])
+        np.testing.assert_allclose(pose.cpu().numpy(), ref, rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(pose.cpu().numpy(), g["pose"].double().numpy(), rtol=1e-8, atol=1e-9)
+        s = stats.cpu().numpy()
+        assert int(s[0]) == trace.steps and int(s[1]) == trace.evaluations
+    ctx = P.B200_TwoFrame_PGO.init_context(NS(device=DEV, graph_type=g["graph_type"], autodiff=False, vectorize=True, parallel=False))
+    _, out = P.B200_TwoFrame_PGO._optimize(ctx, inp)
+    np.testing.assert_allclose(out.motion.reshape(-1).cpu().numpy(), ref, rtol=1e-8, atol=1e-9)

@@ -210,3 +210,15 @@ def test_motion_interpolate_oracle_matches_reference(golden, name):
     assert idx.tolist() == g["interp_idx"].tolist()
     flagged_motion = [i - 1 for i in g["flagged"] if 2 <= i - 1 < g["F"] - 3]
     assert idx.tolist() == sorted(flagged_motion)
+
+
+@pytest.mark.parametrize("name", list(cases.PGO_TYPE_CASES))
+def test_pgo_other_graph_types_against_reference_lm(golden, name):
+    """graph types "icp" (Paper_Reproduce.yaml; pose-dependent covariance R Sigma_obs R^T + Sigma_pts re-inverted before every
+    step) and "reproj" vs the reference's LM_analytic + Analytic_ICP_TwoframePGO / Analytic_Reproj_TwoFramePGO on the shim"""
+    g = golden(f"pgo_{name}.pt")
+    c = cases.pgo_inputs_typed(g["graph_type"], g["K"], g["seed"])
+    pose = opgo.lm_solve(cases.pgo_graph(c))
+    np.testing.assert_allclose(pose, g["pose"].double().numpy(), rtol=1e-8, atol=1e-9)
+    true = c["true_pose"].numpy()
+    assert np.abs(pose[:3] - true[:3]).max() < 0.1 and np.abs(pose[3:] - true[3:]).max() < 0.02
