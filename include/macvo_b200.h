@@ -322,6 +322,49 @@ int macvo_gru_gates(const float* zr, const float* bias, const float* hx, float* 
 /* hx[:, :128] <- (1 - z) * hx[:, :128] + z * tanh(q + bias); bias (128) may be NULL; optional dense copy (pixels,128) */
 int macvo_gru_blend(const float* q, const float* bias, const float* z, float* hx, float* h_dense, long long pixels,
                     void* stream);
+/* ---- decoder convolutions on tcgen05 (csrc/conv_tc.cu): 3x3 (padding 1) / 1x1 convolutions of the motion encoder, the GMA value
+ * projection, the flow head and the covariance head (core/gru.py:6-14,45-64, gma.py:84-130, FlowFormerCov/covhead.py:20-58) as
+ * implicit GEMMs over fp16 pixel rows in "layout U" (csrc/rows_layout.cuh): image b, pixel (y, x) lives at row
+ * 2 + (b (H + 4) + y + 2)(W + 4) + x + 2 of a zero-initialised buffer of macvo_rows_count(batch, H, W, 0) rows; the kernels only
+ * write pixel rows, so the padding stays zero.
+ *   in_rows   (rows, in_channels) fp16, in_channels % 64 == 0; in_dense = 1 (ksize 1 only): plain (pixels, in_channels) rows
+ *   weights   (n_pad, ksize^2 * in_channels) fp16, K index = (ky * ksize + kx) * in_channels + c; n_pad % 32 == 0, rows >= n_valid
+ *             zero; bias (n_pad) fp32 or NULL; relu != 0 applies max(., 0)
+ *   out16     optional fp16 rows [.., out16_offset + n] with row pitch out16_pitch (elements): layout U rows, or dense pixel rows when
+ *             out16_dense; out32: optional fp32 dense pixel rows. Only columns n < n_valid are stored. */
+size_t macvo_rows_count(int batch, int height, int width, int vertical);
+int macvo_conv_tc(const void* in_rows, int in_channels, int in_dense, const void* weights, const float* bias, int n_pad,
+                  int n_valid, int ksize, int relu, int batch, int height, int width, void* out16, int out16_pitch,
+                  int out16_offset, int out16_dense, float* out32, int out32_pitch, int out32_offset, void* stream);
+/* the motion encoder's 7x7 convolution of the 2-channel flow as a GEMM operand (gru.py:50,57): rows (pixels, 128) fp16 dense,
+ * column (ky * 7 + kx) * 2 + c = (coords1 - coords0)[c, y + ky - 3, x + kx - 3], zero outside / beyond column 98; also writes the
+ * flow into channels 126, 127 of the motion-feature rows (mf32: (pixels, 128) fp32 dense, mf16_rows: layout U, 128 ch; may be NULL) */
+int macvo_flow_im2col(const float* coords1, const float* coords0, void* rows, float* mf32, void* mf16_rows, int batch,
+                      int height, int width, void* stream);
+
+/* ---- SepConvGRU on tcgen05 (csrc/gru_conv_tc.cu): the 1x5 / 5x1 gate convolutions of gru.py:22-43 as implicit GEMMs with the
+ * gate math in the epilogue, for `units` (1 or 2: flow, covariance — covhead.py:95-131) recurrent units per launch.
+ * Operands are fp16 PADDED pixel rows: pass `vertical` = 0 (1x5) uses layout U (above), `vertical` = 1 (5x1) stores pixel
+ * (b, y, x) at row 2 + (b W + x)(H + 4) + y + 2; all other rows must be zero (allocate
+ * macvo_gru_tc_operand_rows(...) zeroed rows once; the kernels only ever write pixel rows).
+ *   h_rows[u]   (rows, 128) fp16: stage 0: h, stage 1: r*h          x_rows (rows, 384) fp16: [inp | mf | mf + gamma agg]
+ *   weights[u]  (N, 5*512) fp16, K index = tap * 512 + channel of cat[h, x]; N = 256 (z | r) for stage 0, 128 (q) for stage 1
+ *   bias[u] (N) fp32;  h_master[u], z[u] (pixels, 128) fp32 in dense pixel order (the recurrent state stays fp32)
+ *   out_rows[u] (rows', 128) fp16: stage 0 writes r*h rows of THIS pass's layout, stage 1 writes the new h in the OTHER
+ *   pass's layout (the next pass's input) and updates h_master in place.
+ * stage 0: z = sigmoid(conv + b)[:128] -> z;  r*h -> out_rows.     stage 1: h <- (1 - z) h + z tanh(conv + b). */
+size_t macvo_gru_tc_operand_rows(int batch, int height, int width, int vertical);
+int macvo_gru_tc_stage(int stage, int vertical, int batch, int height, int width, int units, const void* const* h_rows,
+                       const void* x_rows, const void* const* weights, const float* const* bias, float* const* h_master,
+                       float* const* z, void* const* out_rows, void* stream);
+/* profiling aid: device buffer of 3 x 64 uint64 that the first CTA fills with globaltimer events (NULL = off, the default) */
+void macvo_gru_tc_set_trace(void* buf);
+/* fp32 dense pixel rows src (pixels, src_pitch)[:, :channels] -> fp16 operand rows dst[:, dst_offset : dst_offset + channels] */
+int macvo_gru_tc_pack(const float* src, int src_pitch, int channels, void* dst, int dst_channels, int dst_offset, int batch,
+                      int height, int width, int vertical, void* stream);
+/* per iteration: x channels [128, 384) = [mf | mf + gamma * agg] of both layouts (gma.py:84-130) */
+int macvo_gru_tc_pack_motion(const float* mf, const float* agg, const float* gamma, void* x_rows_h, void* x_rows_v, int batch,
+                             int height, int width, void* stream);
 /* out (pixels,64) = LayerNorm_64(query) + LinearPositionEmbeddingSine(coords)  (decoder.py:56-66, attention.py:71-101);
  * coords (batch, 2, n1) [x, y]; freq: the 16 fp32 frequencies k*pi/200. */
 int macvo_query_prep(const float* query, const float* ln_weight, const float* ln_bias, const float* coords,

@@ -37,6 +37,7 @@ Restructuring relative to the reference (same arithmetic per output, fewer launc
 from __future__ import annotations
 
 import math
+import os
 import zlib
 from typing import Callable
 
@@ -246,6 +247,8 @@ class FlowFormerCovNet:
                  lookup_fn: Callable[[Tensor, Tensor], Tensor] | None = None):
         self.device = torch.device(device)
         self.enc_dtype, self.dec_dtype, self.depth = enc_dtype, dec_dtype, decoder_depth
+        # TF32 mode only: SepConvGRU on the tcgen05 kernel (False / MACVO_B200_GRU_TC=0: cuDNN convolutions + glue kernels)
+        self.gru_tensor_cores = os.environ.get("MACVO_B200_GRU_TC", "1") != "0"
         self._ops = None
         self._fused_conv_relu = True
         if corr_fn is None or lookup_fn is None or self.device.type == "cuda":
@@ -674,18 +677,34 @@ class FlowFormerCovNet:
         gamma = self.W[ub + "aggregator.gamma"]
         P = B * N
         native = self._native(ctx) and dd == torch.float32
+        # TF32 mode: both SepConvGRU units run on the tcgen05 kernel (fp16 operands, fp32 state; csrc/gru_conv_tc.cu);
+        # strict mode keeps cuDNN's fp32 convolutions + the fused glue kernels
+        gru_tc = None
         if native:
+            side = self._memo(("side_stream", ctx.device), lambda: torch.cuda.Stream(ctx.device))
+            as_map = lambda t: t.view(B, H1, W1, -1).permute(0, 3, 1, 2)                   # channels_last logical map
+            inp_rows = inp.permute(0, 2, 3, 1).reshape(P, 128).contiguous()
+            net_rows = net.permute(0, 2, 3, 1).reshape(P, 128).contiguous()
+        if native and torch.backends.cudnn.allow_tf32 and torch.backends.cuda.matmul.allow_tf32 and self.gru_tensor_cores:
+            def make_gru():
+                names = [f"conv{g}{o}" for g in ("zr", "q") for o in ("1", "2")]
+                ws = [{n: self.W[pre + "gru." + n + ".weight"] for n in names} for pre in (ub, cu)]
+                bs = [{n: self.W[pre + "gru." + n + ".bias"] for n in names} for pre in (ub, cu)]
+                return self._ops.SepConvGruTC(ws, bs, B, H1, W1, ctx.device)
+            gru_tc = self._memo(("gru_tc", B, H1, W1, ctx.device), make_gru)
+            gru_tc.set_context(inp_rows)
+            gru_tc.set_state(0, net_rows)
+            gru_tc.set_state(1, net_rows)
+            net_d, cnet_d = gru_tc.h
+        elif native:
             # recurrent state in NHWC [h | x] buffers (csrc/decoder_fused.cu): x = [inp | mf | mf + gamma*agg]
             bufs = [torch.empty(P, 512, dtype=dd, device=ctx.device) for _ in range(4)]   # hx, rhx (flow) / hx, rhx (cov)
-            inp_rows = inp.permute(0, 2, 3, 1).reshape(P, 128)
             for bf in bufs:
                 bf[:, 128:256] = inp_rows
-            bufs[0][:, :128] = net.permute(0, 2, 3, 1).reshape(P, 128)
+            bufs[0][:, :128] = net_rows
             bufs[2][:, :128] = bufs[0][:, :128]
             zbuf, zbuf2 = torch.empty(P, 128, dtype=dd, device=ctx.device), torch.empty(P, 128, dtype=dd, device=ctx.device)
-            side = self._memo(("side_stream", ctx.device), lambda: torch.cuda.Stream(ctx.device))
             net_d, cnet_d = torch.empty(P, 128, dtype=dd, device=ctx.device), torch.empty(P, 128, dtype=dd, device=ctx.device)
-            as_map = lambda t: t.view(B, H1, W1, -1).permute(0, 3, 1, 2)                   # channels_last logical map
         # the N x N GMA attention matrix (184 MB at 640x480) is re-read by every iteration's aggregation GEMM, which is
         # bound by that read: when TF32 matmuls are allowed it is kept in fp16 (values in [0, 1]; no precision below TF32's)
         attention_h = attention.to(torch.float16) if native and torch.backends.cuda.matmul.allow_tf32 else None
@@ -748,20 +767,25 @@ class FlowFormerCovNet:
                 # the flow branch (GRU + flow head) and the covariance branch (GRU + cov head) only share their input:
                 # at 60x80 each conv fills about half of the 148 SMs, so the two run on forked streams (fork/join is
                 # captured into the CUDA graph as parallel branches)
-                self._ops.gru_input(mf.permute(0, 2, 3, 1), agg, gamma, bufs)
+                if gru_tc is not None:
+                    gru_tc.step(mf.permute(0, 2, 3, 1), agg, gamma)              # both units, 5 launches
+                else:
+                    self._ops.gru_input(mf.permute(0, 2, 3, 1), agg, gamma, bufs)
                 main = torch.cuda.current_stream()
                 fork = torch.cuda.Event()
                 fork.record(main)
                 with torch.cuda.stream(side):
                     side.wait_event(fork)
-                    self._gru_native(bufs[2], bufs[3], zbuf2, cu + "gru.", cnet_d, (B, H1, W1))
+                    if gru_tc is None:
+                        self._gru_native(bufs[2], bufs[3], zbuf2, cu + "gru.", cnet_d, (B, H1, W1))
                     cnet = as_map(cnet_d)
                     h = cu + "cov_head."
                     t = self._conv(self._conv_relu(cnet, h + "conv1", padding=1), h + "conv2", padding=1)
                     d_cov = self._conv(self._conv_relu(t, h + "conv3", padding=1), h + "conv4", padding=1)
                     join = torch.cuda.Event()
                     join.record(side)
-                self._gru_native(bufs[0], bufs[1], zbuf, ub + "gru.", net_d, (B, H1, W1))
+                if gru_tc is None:
+                    self._gru_native(bufs[0], bufs[1], zbuf, ub + "gru.", net_d, (B, H1, W1))
                 net = as_map(net_d)
                 d_flow = self._conv(self._conv_relu(net, ub + "flow_head.conv1", padding=1), ub + "flow_head.conv2", padding=1)
                 main.wait_event(join)

@@ -98,6 +98,15 @@ EXPORTS = {
     "macvo_gru_input": (C.c_int, [C.c_void_p] * 7 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_gates": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_blend": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
+    "macvo_rows_count": (C.c_size_t, [C.c_int] * 4),
+    "macvo_conv_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 7
+                      + [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p] + [C.c_int] * 2 + [C.c_void_p]),
+    "macvo_flow_im2col": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p]),
+    "macvo_gru_tc_operand_rows": (C.c_size_t, [C.c_int] * 4),
+    "macvo_gru_tc_set_trace": (None, [C.c_void_p]),
+    "macvo_gru_tc_stage": (C.c_int, [C.c_int] * 6 + [C.c_void_p] * 8),
+    "macvo_gru_tc_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "macvo_gru_tc_pack_motion": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p]),
 }
 
 
@@ -860,6 +869,147 @@ def gru_blend(q: Tensor, z: Tensor, hx: Tensor, h_dense: Tensor | None, bias: Te
                                         None if h_dense is None else h_dense.data_ptr(), hx.shape[0], _stream())
     _check(rc, "macvo_gru_blend")
     LAUNCHES[0] += 1
+
+
+def rows_count(batch: int, height: int, width: int, vertical: int = 0) -> int:
+    """rows of a zero-initialised padded pixel-row buffer (layout U, or the GRU's layout V): csrc/rows_layout.cuh"""
+    return int(load_library().macvo_rows_count(batch, height, width, vertical))
+
+
+def pack_conv_filter(weight: Tensor, bias: Tensor | None, in_channels: int | None = None, device=None) -> tuple[Tensor, Tensor | None, int]:
+    """(N, C, k, k) fp32 filter -> (n_pad, k*k*c_pad) fp16 GEMM operand of macvo_conv_tc (K index = (ky*k + kx)*c_pad + c), zero
+    padded to n_pad % 32 == 0 rows / c_pad % 64 == 0 channels; bias -> (n_pad) fp32. Returns (weights, bias, N)."""
+    w = weight.detach().to(device=device or weight.device, dtype=torch.float32)
+    n, c, kh, kw = w.shape
+    c_pad = in_channels or -(-c // 64) * 64
+    n_pad = -(-n // 32) * 32
+    wp = torch.zeros(n_pad, kh * kw, c_pad, dtype=torch.float32, device=w.device)
+    wp[:n, :, :c] = w.permute(0, 2, 3, 1).reshape(n, kh * kw, c)
+    bp = None
+    if bias is not None:
+        bp = torch.zeros(n_pad, dtype=torch.float32, device=w.device)
+        bp[:n] = bias.detach().to(device=w.device, dtype=torch.float32)
+    return wp.reshape(n_pad, kh * kw * c_pad).to(torch.float16).contiguous(), bp, n
+
+
+def conv_tc(in_rows: Tensor, weights: Tensor, bias: Tensor | None, n_valid: int, ksize: int, relu: bool, shape: tuple[int, int, int],
+            in_dense: bool = False, out16: Tensor | None = None, out16_offset: int = 0, out16_dense: bool = False,
+            out32: Tensor | None = None, out32_offset: int = 0) -> None:
+    """3x3 / 1x1 convolution on the tcgen05 path (csrc/conv_tc.cu): fp16 pixel rows in, fp16 rows and / or fp32 dense rows out"""
+    B, H, W = shape
+    for t, dt, what in ((in_rows, torch.float16, "in_rows"), (weights, torch.float16, "weights"), (out16, torch.float16, "out16"),
+                        (out32, torch.float32, "out32"), (bias, torch.float32, "bias")):
+        if t is not None and not (t.is_cuda and t.dtype == dt and t.is_contiguous()):
+            raise MacvoB200Error(f"conv_tc: {what} must be a contiguous CUDA {dt} tensor")
+    c_in = in_rows.shape[1]
+    if weights.shape[1] != ksize * ksize * c_in or (bias is not None and bias.numel() != weights.shape[0]):
+        raise MacvoB200Error("conv_tc: filter / bias shape does not match the input rows")
+    need = B * H * W if in_dense else rows_count(B, H, W)
+    if in_rows.shape[0] != need:
+        raise MacvoB200Error(f"conv_tc: expected {need} input rows, got {in_rows.shape[0]}")
+    for t, dense, off in ((out16, out16_dense, out16_offset), (out32, True, out32_offset)):
+        if t is not None and (t.shape[0] != (B * H * W if dense else rows_count(B, H, W)) or off + n_valid > t.shape[1]):
+            raise MacvoB200Error("conv_tc: output rows / channel range do not fit")
+    rc = load_library().macvo_conv_tc(in_rows.data_ptr(), c_in, int(in_dense), weights.data_ptr(), None if bias is None else bias.data_ptr(),
+                                      weights.shape[0], n_valid, ksize, int(relu), B, H, W,
+                                      None if out16 is None else out16.data_ptr(), 0 if out16 is None else out16.shape[1], out16_offset,
+                                      int(out16_dense), None if out32 is None else out32.data_ptr(),
+                                      0 if out32 is None else out32.shape[1], out32_offset, _stream())
+    _check(rc, "macvo_conv_tc")
+    LAUNCHES[0] += 1
+
+
+def flow_im2col(coords1: Tensor, coords0: Tensor, rows: Tensor, mf32: Tensor | None, mf16_rows: Tensor | None) -> None:
+    """7x7 neighbourhoods of flow = coords1 - coords0 as (pixels, 128) fp16 GEMM rows; flow -> channels 126, 127 of the mf rows"""
+    c1, c0 = _dev(coords1, torch.float32, "coords1"), _dev(coords0, torch.float32, "coords0")
+    B, _, H, W = c1.shape
+    rc = load_library().macvo_flow_im2col(c1.data_ptr(), c0.data_ptr(), rows.data_ptr(), None if mf32 is None else mf32.data_ptr(),
+                                          None if mf16_rows is None else mf16_rows.data_ptr(), B, H, W, _stream())
+    _check(rc, "macvo_flow_im2col")
+    LAUNCHES[0] += 1
+
+
+def pack_rows(src: Tensor, dst: Tensor, offset: int, shape: tuple[int, int, int], vertical: int = 0) -> None:
+    """fp32 dense pixel rows (pixels, C) -> fp16 padded rows dst[:, offset : offset + C] (layout U, or V when `vertical`)"""
+    B, H, W = shape
+    if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 2 and src.shape[0] == B * H * W):
+        raise MacvoB200Error("pack_rows: expected contiguous fp32 (pixels, C) rows")
+    _check(load_library().macvo_gru_tc_pack(src.data_ptr(), src.shape[1], src.shape[1], dst.data_ptr(), dst.shape[1], offset, B, H, W,
+                                            vertical, _stream()), "macvo_gru_tc_pack")
+    LAUNCHES[0] += 1
+
+
+class SepConvGruTC:
+    """The decoder's SepConvGRU units (gru.py:22-43; flow + covariance, covhead.py:95-131) on the tcgen05 path
+    (csrc/gru_conv_tc.cu): fp32 recurrent state `h[u]` (pixels, 128) in dense pixel order, fp16 padded operand rows for the two
+    passes, one `step` = pack the motion features + 4 kernel launches for all units.
+
+    weights[u]: {"convzr1": (256,512,1,5), "convq1": (128,512,1,5), "convzr2": (256,512,5,1), "convq2": (128,512,5,1)} fp32
+    filters with the z | r filters concatenated, biases[u]: the matching (N,) vectors."""
+
+    def __init__(self, weights: list[dict], biases: list[dict], batch: int, height: int, width: int, device):
+        lib = load_library()
+        self.units, self.shape, self.device = len(weights), (int(batch), int(height), int(width)), device
+        if self.units not in (1, 2):
+            raise MacvoB200Error("SepConvGruTC: 1 or 2 units")
+        P = batch * height * width
+        rows = [int(lib.macvo_gru_tc_operand_rows(batch, height, width, o)) for o in (0, 1)]
+        f16 = dict(dtype=torch.float16, device=device)
+        self.x = [torch.zeros(r, 3 * GRU_HID, **f16) for r in rows]
+        self.h_rows = [[torch.zeros(r, GRU_HID, **f16) for _ in range(self.units)] for r in rows]     # [pass][unit]
+        self.rh_rows = [[torch.zeros(r, GRU_HID, **f16) for _ in range(self.units)] for r in rows]
+        self.h = [torch.zeros(P, GRU_HID, dtype=torch.float32, device=device) for _ in range(self.units)]
+        self.z = [torch.zeros(P, GRU_HID, dtype=torch.float32, device=device) for _ in range(self.units)]
+        self.w, self.b = {}, {}
+        for u in range(self.units):
+            for o in (0, 1):
+                for st, name in ((0, f"convzr{o + 1}"), (1, f"convq{o + 1}")):
+                    w = weights[u][name].detach().to(device=device, dtype=torch.float32)
+                    n = w.shape[0]
+                    if tuple(w.shape) != ((n, GRU_IN, 1, 5) if o == 0 else (n, GRU_IN, 5, 1)) or n != (256, 128)[st]:
+                        raise MacvoB200Error(f"SepConvGruTC: unexpected filter shape {tuple(w.shape)} for {name}")
+                    self.w[u, o, st] = w.reshape(n, GRU_IN, 5).permute(0, 2, 1).reshape(n, 5 * GRU_IN).to(torch.float16).contiguous()
+                    self.b[u, o, st] = biases[u][name].detach().to(device=device, dtype=torch.float32).contiguous()
+        ptrs = lambda ts: (C.c_void_p * 2)(*[t.data_ptr() for t in ts], *([None] * (2 - len(ts))))
+        self._args = {(o, st): (ptrs(self.h_rows[o] if st == 0 else self.rh_rows[o]), self.x[o].data_ptr(),
+                                ptrs([self.w[u, o, st] for u in range(self.units)]), ptrs([self.b[u, o, st] for u in range(self.units)]),
+                                ptrs(self.h), ptrs(self.z), ptrs(self.rh_rows[o] if st == 0 else self.h_rows[1 - o]))
+                      for o in (0, 1) for st in (0, 1)}
+
+    def _pack(self, src: Tensor, dst: Tensor, offset: int, vertical: int) -> None:
+        B, H, W = self.shape
+        src = _dense(src, GRU_HID, "SepConvGruTC rows")
+        if src.numel() != B * H * W * GRU_HID:
+            raise MacvoB200Error("SepConvGruTC: expected (pixels, 128) rows")
+        _check(load_library().macvo_gru_tc_pack(src.data_ptr(), GRU_HID, GRU_HID, dst.data_ptr(), dst.shape[1], offset, B, H, W,
+                                                vertical, _stream()), "macvo_gru_tc_pack")
+        LAUNCHES[0] += 1
+
+    def set_context(self, inp_rows: Tensor) -> None:
+        """x channels [0, 128) = the context features `inp` (constant over the refinement iterations)"""
+        for o in (0, 1):
+            self._pack(inp_rows, self.x[o], 0, o)
+
+    def set_state(self, unit: int, h_rows: Tensor) -> None:
+        self.h[unit].copy_(_dense(h_rows, GRU_HID, "SepConvGruTC state").view(-1, GRU_HID))
+        self._pack(self.h[unit], self.h_rows[0][unit], 0, 0)
+
+    def step(self, mf: Tensor, agg: Tensor, gamma: Tensor) -> None:
+        """one SepConvGRU update of every unit with x = [inp | mf | mf + gamma * agg]; new state in `self.h[u]`"""
+        B, H, W = self.shape
+        lib = load_library()
+        mf, agg = _dense(mf, GRU_HID, "SepConvGruTC mf"), _dense(agg, GRU_HID, "SepConvGruTC agg")
+        if mf.numel() != B * H * W * GRU_HID or agg.numel() != mf.numel():
+            raise MacvoB200Error("SepConvGruTC.step: expected (pixels, 128) rows")
+        st = _stream()
+        _check(lib.macvo_gru_tc_pack_motion(mf.data_ptr(), agg.data_ptr(), _dev(gamma, torch.float32, "gamma").data_ptr(),
+                                            self.x[0].data_ptr(), self.x[1].data_ptr(), B, H, W, st), "macvo_gru_tc_pack_motion")
+        for o in (0, 1):
+            for stage in (0, 1):
+                a = self._args[o, stage]
+                _check(lib.macvo_gru_tc_stage(stage, o, B, H, W, self.units, a[0], a[1], a[2], a[3], a[4], a[5], a[6], st),
+                       "macvo_gru_tc_stage")
+        LAUNCHES[0] += 5
 
 
 def query_prep(query: Tensor, ln_weight: Tensor, ln_bias: Tensor, coords: Tensor, freq: Tensor, eps: float = 1e-5) -> Tensor:

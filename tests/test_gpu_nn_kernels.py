@@ -129,6 +129,139 @@ def test_gru_fused_kernels(ops):
         ops.gru_gates(zr.t(), hx, z, rhx)
 
 
+@pytest.mark.parametrize("shape", [(1, 60, 80), (1, 12, 16), (2, 13, 17), (1, 90, 160)])
+def test_sepconv_gru_tensor_cores(ops, shape):
+    """csrc/gru_conv_tc.cu (tcgen05 implicit GEMM, fp16 operands, fp32 state) vs SepConvGRU (core/gru.py:22-43) in float64:
+    (a) against the same arithmetic with the convolution inputs / filters rounded to fp16 (what the kernel computes): 1e-3,
+    (b) against the unrounded float64 GRU: 4e-3 (fp16 operand rounding, the TF32-class bound of this mode). Two steps, two units,
+    so the layout ping-pong between the 1x5 and the 5x1 pass and the state hand-over to the next iteration are covered."""
+    B, H, W = shape
+    P = B * H * W
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).to(DEV)
+    names = {"convzr1": (256, 512, 1, 5), "convq1": (128, 512, 1, 5), "convzr2": (256, 512, 5, 1), "convq2": (128, 512, 5, 1)}
+    ws = [{n: rnd(*sh, scale=0.03) for n, sh in names.items()} for _ in range(2)]
+    bs = [{n: rnd(sh[0], scale=0.3) for n, sh in names.items()} for _ in range(2)]
+    gru = ops.SepConvGruTC(ws, bs, B, H, W, DEV)
+    inp = rnd(P, 128).relu()
+    h0 = [torch.tanh(rnd(P, 128)) for _ in range(2)]
+    gamma = torch.tensor([0.6], device=DEV)
+    gru.set_context(inp)
+    for u in range(2):
+        gru.set_state(u, h0[u])
+
+    def to_map(rows):
+        return rows.view(B, H, W, -1).permute(0, 3, 1, 2).double()
+
+    def ref_gru(h, x, w, b, rounded):
+        q16 = (lambda t: t.half().double()) if rounded else (lambda t: t)
+        for o, pad in (("1", (0, 2)), ("2", (2, 0))):
+            hx = torch.cat([q16(h), q16(x)], 1)
+            zr = torch.sigmoid(F.conv2d(hx, q16(w["convzr" + o].double()), b["convzr" + o].double(), padding=pad))
+            z, r = zr[:, :128], zr[:, 128:]
+            q = torch.tanh(F.conv2d(torch.cat([q16(r * h), q16(x)], 1), q16(w["convq" + o].double()), b["convq" + o].double(), padding=pad))
+            h = (1 - z) * h + z * q
+        return h
+
+    ref_r, ref_t = [to_map(h) for h in h0], [to_map(h) for h in h0]
+    for it in range(2):
+        mf, agg = rnd(P, 128).relu(), rnd(P, 128)
+        gru.step(mf, agg, gamma)
+        xs = torch.cat([inp, mf, mf + gamma * agg], 1)
+        for u in range(2):
+            # the fp16 rounding of x happens on the fp32 values the pack kernel forms
+            ref_r[u] = ref_gru(ref_r[u], to_map(xs), ws[u], bs[u], True)
+            ref_t[u] = ref_gru(ref_t[u], to_map(xs), ws[u], bs[u], False)
+            got = to_map(gru.h[u])
+            assert torch.isfinite(got).all()
+            assert (got - ref_r[u]).abs().max().item() <= 1e-3, (it, u)
+            assert (got - ref_t[u]).abs().max().item() <= 4e-3, (it, u)
+    # pad rows of every operand buffer are still zero (the kernels only write pixel rows)
+    for o, (lines, ln) in enumerate(((B * H, W), (B * W, H))):
+        for buf in [gru.x[o]] + gru.h_rows[o] + gru.rh_rows[o]:
+            body = buf[2:2 + lines * (ln + 4)].view(lines, ln + 4, -1)
+            assert not body[:, :2].any() and not body[:, -2:].any() and not buf[:2].any() and not buf[2 + lines * (ln + 4):].any()
+
+
+def _to_rows_u(ops, x_map, shape):
+    """(B, C, H, W) fp32 map -> zero-initialised layout-U fp16 rows via the pack kernel"""
+    B, H, W = shape
+    C = x_map.shape[1]
+    rows = torch.zeros(ops.rows_count(B, H, W), C, dtype=torch.float16, device=DEV)
+    ops.pack_rows(x_map.permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous(), rows, 0, shape)
+    return rows
+
+
+def _from_rows_u(rows, shape):
+    B, H, W = shape
+    body = rows[2:2 + B * (H + 4) * (W + 4)].view(B, H + 4, W + 4, -1)
+    pad = body.clone()
+    pad[:, 2:H + 2, 2:W + 2] = 0
+    assert not pad.any() and not rows[:2].any() and not rows[2 + B * (H + 4) * (W + 4):].any()     # padding untouched
+    return body[:, 2:H + 2, 2:W + 2].permute(0, 3, 1, 2).double()
+
+
+@pytest.mark.parametrize("shape", [(1, 60, 80), (2, 13, 17), (1, 90, 160)])
+@pytest.mark.parametrize("cin,cout,k,relu", [(256, 192, 3, True), (128, 256, 3, True), (256, 2, 3, False), (192, 256, 1, True),
+                                             (128, 126, 3, True), (64, 2, 3, False), (128, 64, 3, True)])
+def test_conv_tc(ops, shape, cin, cout, k, relu):
+    """csrc/conv_tc.cu vs F.conv2d in float64 on the same fp16-rounded operands: 1e-3 of the output scale (fp32 accumulation
+    order; fp16 re-rounding of the fp16 output where one is written)."""
+    B, H, W = shape
+    P = B * H * W
+    g = torch.Generator().manual_seed(cin * 7 + cout + k + H)
+    x = (torch.randn(B, cin, H, W, generator=g)).to(DEV)
+    w = (torch.randn(cout, cin, k, k, generator=g) * (cin * k * k) ** -0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    ref = F.conv2d(x.half().double(), w.half().double(), b.double(), padding=k // 2)
+    if relu:
+        ref = ref.relu()
+    scale = ref.abs().max().item()
+    wp, bp, n = ops.pack_conv_filter(w, b)
+    rows = _to_rows_u(ops, x, shape)
+    out16 = torch.zeros(ops.rows_count(B, H, W), 256, dtype=torch.float16, device=DEV)
+    o32 = 4 if H % 2 == 0 else 1                                # vector-store path | scalar path
+    out32 = torch.full((P, cout + 8), 7.0, device=DEV)
+    ops.conv_tc(rows, wp, bp, n, k, relu, shape, out16=out16, out16_offset=64 if cout <= 192 else 0, out32=out32, out32_offset=o32)
+    got32 = out32[:, o32:o32 + cout].view(B, H, W, cout).permute(0, 3, 1, 2).double()
+    assert (got32 - ref).abs().max().item() <= 1e-3 * scale
+    assert (out32[:, :o32] == 7.0).all() and (out32[:, o32 + cout:] == 7.0).all()                   # neighbours untouched
+    off = 64 if cout <= 192 else 0
+    got16 = _from_rows_u(out16, shape)
+    assert (got16[:, off:off + cout] - ref).abs().max().item() <= 2e-3 * scale
+    assert not got16[:, :off].any() and not got16[:, off + cout:].any()
+    if k == 1:      # dense rows in, dense fp16 rows out (the value projection's shape)
+        dense_in = x.permute(0, 2, 3, 1).reshape(P, cin).half().contiguous()
+        o16 = torch.zeros(P, cout, dtype=torch.float16, device=DEV)
+        ops.conv_tc(dense_in, wp, None, n, 1, False, shape, in_dense=True, out16=o16, out16_dense=True)
+        ref2 = F.conv2d(x.half().double(), w.half().double())
+        assert (o16.view(B, H, W, cout).permute(0, 3, 1, 2).double() - ref2).abs().max().item() <= 2e-3 * ref2.abs().max().item()
+    with pytest.raises(ops.MacvoB200Error):
+        ops.conv_tc(rows[:-1], wp, bp, n, k, relu, shape, out32=out32)
+
+
+def test_flow_im2col(ops):
+    """the 7x7 flow convolution as im2col rows + a 1x1 tensor-core convolution vs F.conv2d(flow, w, padding=3)"""
+    B, H, W = 2, 13, 17
+    P = B * H * W
+    g = torch.Generator().manual_seed(5)
+    c0, c1 = (torch.randn(B, 2, H, W, generator=g) * 20).to(DEV), (torch.randn(B, 2, H, W, generator=g) * 20).to(DEV)
+    w, b = (torch.randn(128, 2, 7, 7, generator=g) * 0.1).to(DEV), torch.randn(128, generator=g).to(DEV)
+    rows = torch.zeros(P, 128, dtype=torch.float16, device=DEV)
+    mf32 = torch.zeros(P, 128, device=DEV)
+    mf16 = torch.zeros(ops.rows_count(B, H, W), 128, dtype=torch.float16, device=DEV)
+    ops.flow_im2col(c1, c0, rows, mf32, mf16)
+    flow = c1 - c0
+    assert torch.equal(mf32[:, 126:], flow.permute(0, 2, 3, 1).reshape(P, 2)) and not mf32[:, :126].any()
+    assert torch.equal(_from_rows_u(mf16, (B, H, W))[:, 126:], flow.half().double())
+    wp, bp, n = ops.pack_conv_filter(w, b, in_channels=128)
+    out = torch.zeros(P, 128, device=DEV)
+    ops.conv_tc(rows, wp, bp, n, 1, True, (B, H, W), in_dense=True, out32=out)
+    ref = F.conv2d(flow.half().double(), w.half().double(), b.double(), padding=3).relu()
+    got = out.view(B, H, W, 128).permute(0, 3, 1, 2).double()
+    assert (got - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
 def test_lookup_rows_equals_lookup_map(ops):
     import sys, os
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
