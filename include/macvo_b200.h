@@ -333,6 +333,11 @@ int macvo_gru_blend(const float* q, const float* bias, const float* z, float* hx
  *   out16     optional fp16 rows [.., out16_offset + n] with row pitch out16_pitch (elements): layout U rows, or dense pixel rows when
  *             out16_dense; out32: optional fp32 dense pixel rows. Only columns n < n_valid are stored. */
 size_t macvo_rows_count(int batch, int height, int width, int vertical);
+/* profiling aid: device buffer of 1 + 3 * capacity uint64 = event count, then (kernel id, start ns, end ns) per launch of the
+ * tensor-core convolution / GRU kernels; NULL (the default) switches it off */
+void macvo_tc_set_timeline(void* buf, int capacity);
+/* profiling aid: 3 x 64 uint64 globaltimer events (producer | MMA steps | epilogue) of block (0,0) of macvo_conv_tc; NULL = off */
+void macvo_conv_tc_set_trace(void* buf);
 int macvo_conv_tc(const void* in_rows, int in_channels, int in_dense, const void* weights, const float* bias, int n_pad,
                   int n_valid, int ksize, int relu, int batch, int height, int width, void* out16, int out16_pitch,
                   int out16_offset, int out16_dense, float* out32, int out32_pitch, int out32_offset, void* stream);
@@ -409,6 +414,10 @@ int macvo_observe_pack(const int64_t* kp0_uv, int k, int capacity, const float* 
 size_t macvo_decoder_token_blob_floats(void);
 int macvo_decoder_token(const float* cost_forward, const float* coords, const float* key, const float* value,
                         const float* weight_blob, float* out, int batch, int n1, float eps, void* stream);
+/* same, writing fp16 "layout U" rows (see macvo_conv_tc; 192 channels per row, [0,160) = [g | cost_forward | 0]) */
+int macvo_decoder_token_rows(const float* cost_forward, const float* coords, const float* key, const float* value,
+                             const float* weight_blob, void* out16_rows, int batch, int height, int width, float eps,
+                             void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (f4) trajectory post-process at terminate(): MotionInterpolate.elaborate_map (Module/MapProcessor.py:52-79) with

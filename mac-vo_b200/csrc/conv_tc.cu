@@ -9,7 +9,9 @@
 // reused by the three dx taps through the UMMA descriptor start (+128 B per pixel; the 128-byte swizzle is address based —
 // profiles/r02_umma_descriptor_shift_probe.log). A 1x1 convolution may also read plain dense pixel rows.
 //
-// One CTA per (128-pixel tile, slice of output channels); warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
+// One CTA PAIR (cta_group::2, M = 256) per (two 128-pixel tiles, slice of output channels): each CTA stages its own A tile and
+// HALF of the filter rows of every step (a first single-CTA version ran at 1/4 of its MMA bound: 10 KB of shared-memory
+// operand reads per 96-cycle MMA on top of the TMA fill traffic); warp 0 = TMA producer, warp 1 = MMA issuer (leader), warps 2..9 = epilogue
 // (TMEM -> registers -> XOR-swizzled smem transpose in the idle operand ring -> bias / ReLU -> row-contiguous global stores
 // as fp16 rows for the next convolution and / or fp32 dense rows). Launched with programmatic stream serialization: the
 // weights of the first ring slots are in flight before `griddepcontrol.wait` lets the input rows be touched.
@@ -20,14 +22,14 @@
 namespace {
 
 constexpr int TILE_M = macvo_rows::TILE_M, BLOCK_K = 64, UMMA_K = 16;
-constexpr int A_ROWS = 136, A_BYTES = A_ROWS * 128, A_SLOTS = 3;
+constexpr int A_ROWS = 136, A_BYTES = A_ROWS * 128;
 constexpr int EPI_WARPS = 8, THREADS = 32 * (2 + EPI_WARPS);
 constexpr int SMEM_MAX = 200 * 1024;
 
 struct ConvArgs {
     int taps, kblocks;            // 1 | 9 ; input channels / 64
-    int n_cta;                    // output channels per CTA (multiple of 32, <= 256); grid.y slices
-    int tmem_cols, b_slots;
+    int n_cta;                    // output channels per CTA pair = UMMA N (multiple of 32, <= 256); grid.y slices
+    int tmem_cols, slots;         // TMEM columns (power of two >= n_cta), ring depth in groups
     int in_dense;                 // A rows are dense pixel rows (1x1 only) instead of layout U
     int batch, height, width, wp; // wp = width + 4
     int m_rows;                   // rows to cover: pixels (dense) or padded pixels (layout U)
@@ -36,102 +38,115 @@ struct ConvArgs {
     __half* out16; int out16_pitch, out16_off, out16_dense;
     float* out32; int out32_pitch, out32_off;
     uint32_t idesc;
+    Timeline tl;                  // profiling aid, buf == NULL in production
+    unsigned long long* trace;    // profiling aid: [role][64] globaltimer events of block (0, 0)
 };
-
-__device__ __forceinline__ void umma_f16_ss1(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
 
 __global__ void __launch_bounds__(THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int b_bytes = a.n_cta * 128;
-    uint8_t* smem_b = smem + A_SLOTS * A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + a.b_slots * b_bytes);
-    const uint32_t bar_afull = smem_u32(bars), bar_aempty = bar_afull + 8 * A_SLOTS;
-    const uint32_t bar_bfull = bar_aempty + 8 * A_SLOTS, bar_bempty = bar_bfull + 8 * a.b_slots;
-    const uint32_t bar_tfull = bar_bempty + 8 * a.b_slots;
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * A_SLOTS + 2 * a.b_slots + 1);
+    // ring of `slots` group slots: [A tile 17 KB | this CTA's half of the filter rows of the group's 1 or 3 taps]
+    const int tpg = a.taps == 9 ? 3 : 1;                       // taps served by one A tile = taps per group
+    const int b_bytes = (a.n_cta / 2) * 128;
+    const int slot_bytes = A_BYTES + tpg * b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.slots * slot_bytes);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * a.slots, bar_tfull = bar_empty + 8 * a.slots;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.slots + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x, slice = blockIdx.y;
-    const int tpg = a.taps == 9 ? 3 : 1;                       // taps served by one A tile
-    const int nsteps = a.kblocks * a.taps;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tile = (int)(blockIdx.x & ~1u) + (int)rank, slice = blockIdx.y;
+    Timeline tl = a.tl;
+    tl.begin(100 + a.taps * 1000 + a.kblocks * 10000 + a.n_cta * 100000);
+    int tr_n = 0;
+    auto TR = [&](int role) {
+        if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tr_n < 64) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            a.trace[role * 64 + tr_n++] = t;
+        }
+    };
+    if (warp == 2 && lane == 0) TR(2);
+    const int ngroups = a.kblocks * (a.taps == 9 ? 3 : 1);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < A_SLOTS; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
-        for (int s = 0; s < a.b_slots; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+        for (int s = 0; s < a.slots; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_tfull, 1);
         fence_barrier_init();
         prefetch_tmap(&map_a); prefetch_tmap(&map_w);
     }
-    if (warp == 1) tmem_alloc_1cta(smem_u32(tmem_base_slot), a.tmem_cols);
+    if (warp == 1) tmem_alloc(smem_u32(tmem_base_slot), a.tmem_cols);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (both CTAs; completion lands on the leader's barriers) =====================
+        // One request per operand and GROUP (a tap row of a 64-channel block): the filter box is the 3-D view (64 channels, rows,
+        // dx) of the (n, tap, c) matrix, so the three dx taps arrive as three consecutive swizzled tiles. All indices are running
+        // counters: a first version issued one request per tap and derived its indices with `/` and `%` by run-time values —
+        // those integer divisions, not the loads or the MMAs, set its pace (0.41 us per step for every N).
         if (elect_one()) {
             const int c_in = a.kblocks * BLOCK_K;
-            auto issue_b = [&](int s) {
-                const int slot = s % a.b_slots, kb = s / a.taps, t = s - kb * a.taps;
-                const uint32_t full = bar_bfull + 8 * slot;
-                mbar_expect_tx(full, b_bytes);
-                tma_load_2d(smem_u32(smem_b + slot * b_bytes), &map_w, full, t * c_in + kb * BLOCK_K, slice * a.n_cta);
+            const int brow = slice * a.n_cta + (int)rank * (a.n_cta / 2);
+            const int base_row = a.in_dense ? tile * TILE_M : macvo_rows::GUARD + tile * TILE_M;
+            int slot = 0, kb = 0, dy = a.taps == 9 ? 0 : 1;
+            uint32_t phase = 0;
+            auto issue_b = [&](int sl, int kb_, int dy_) {                  // filters of one group -> slot sl (after the A tile)
+                const uint32_t full = bar_full + 8 * sl;
+                if (leader) mbar_expect_tx(full, 2 * slot_bytes);          // A + filters, from both CTAs
+                tma_load_3d_2cta(smem_u32(smem + sl * slot_bytes + A_BYTES), &map_w, full,
+                                 (a.taps == 9 ? dy_ * 3 * c_in : 0) + kb_ * BLOCK_K, brow, 0);
             };
-            const int pre = nsteps < a.b_slots ? nsteps : a.b_slots;
-            for (int s = 0; s < pre; ++s) issue_b(s);                       // weights do not depend on the previous kernel
+            auto issue_a = [&](int sl, int kb_, int dy_) {
+                tma_load_2d_2cta(smem_u32(smem + sl * slot_bytes), &map_a, bar_full + 8 * sl, kb_ * BLOCK_K,
+                                 base_row + (a.taps == 9 ? (dy_ - 1) * a.wp - 1 : 0));
+            };
+            auto advance = [&](int& kb_, int& dy_) { if (a.taps == 9) { if (++dy_ == 3) { dy_ = 0; ++kb_; } } else ++kb_; };
+            // the filters of the first `slots` groups do not depend on the previous kernel: in flight before the wait
+            const int pre = ngroups < a.slots ? ngroups : a.slots;
+            { int k2 = kb, d2 = dy; for (int g = 0; g < pre; ++g) { issue_b(g, k2, d2); advance(k2, d2); } }
             asm volatile("griddepcontrol.wait;" ::: "memory");
-            int aslot = 0; uint32_t aphase = 0;
-            for (int s = 0; s < nsteps; ++s) {
-                if (s % tpg == 0) {
-                    const int grp = s / tpg, kb = s / a.taps, dy = a.taps == 9 ? grp % 3 : 1;
-                    mbar_wait(bar_aempty + 8 * aslot, aphase ^ 1);
-                    const uint32_t full = bar_afull + 8 * aslot;
-                    mbar_expect_tx(full, A_BYTES);
-                    const int row0 = a.in_dense ? tile * TILE_M
-                                                : macvo_rows::GUARD + tile * TILE_M + (a.taps == 9 ? (dy - 1) * a.wp - 1 : 0);
-                    tma_load_2d(smem_u32(smem + aslot * A_BYTES), &map_a, full, kb * BLOCK_K, row0);
-                    if (++aslot == A_SLOTS) { aslot = 0; aphase ^= 1; }
+            TR(0);
+            for (int g = 0; g < ngroups; ++g) {
+                if (g >= pre) {
+                    mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+                    issue_b(slot, kb, dy);
                 }
-                if (s >= pre) {
-                    mbar_wait(bar_bempty + 8 * (s % a.b_slots), ((s / a.b_slots) & 1) ^ 1);
-                    issue_b(s);
-                }
+                issue_a(slot, kb, dy);
+                TR(0);
+                advance(kb, dy);
+                if (++slot == a.slots) { slot = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        int aslot = 0; uint32_t aphase = 0;
-        uint32_t sa = 0;
-        for (int s = 0; s < nsteps; ++s) {
-            const int bslot = s % a.b_slots;
-            if (s % tpg == 0) {
-                mbar_wait(bar_afull + 8 * aslot, aphase);
-                sa = smem_u32(smem + aslot * A_BYTES);
-            }
-            mbar_wait(bar_bfull + 8 * bslot, (s / a.b_slots) & 1);
-            tc_fence_after();
-            const bool last_of_group = (s % tpg) == tpg - 1;
-            if (elect_one()) {
-                const uint64_t da = make_kmajor_sw128_desc(sa + (a.taps == 9 ? (s % 3) * 128 : 0));   // dx tap = row shift
-                const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + bslot * b_bytes));
+        // ===================== MMA issuer: leader CTA, cta_group::2 =====================
+        if (leader) {
+            int slot = 0; uint32_t phase = 0;
+            for (int g = 0; g < ngroups; ++g) {
+                mbar_wait(bar_full + 8 * slot, phase);
+                tc_fence_after();
+                if (lane == 0) TR(1);
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + slot * slot_bytes);
+                    for (int j = 0; j < tpg; ++j) {
+                        const uint64_t da = make_kmajor_sw128_desc(sa + j * 128);                   // dx tap = one pixel row further
+                        const uint64_t db = make_kmajor_sw128_desc(sa + A_BYTES + j * b_bytes);
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_f16_ss1(tmem_base, da + 2 * k, db + 2 * k, a.idesc, (s | k) != 0);
-                umma_commit(bar_bempty + 8 * bslot);
-                if (last_of_group) umma_commit(bar_aempty + 8 * aslot);
-                if (s == nsteps - 1) umma_commit(bar_tfull);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_f16_ss2(tmem_base, da + 2 * k, db + 2 * k, a.idesc, (g | j | k) != 0);
+                    }
+                    umma_commit_mc(bar_empty + 8 * slot, 3);
+                    if (g == ngroups - 1) umma_commit_mc(bar_tfull, 3);
+                }
+                __syncwarp();
+                if (++slot == a.slots) { slot = 0; phase ^= 1; }
             }
-            __syncwarp();
-            if (last_of_group && ++aslot == A_SLOTS) { aslot = 0; aphase ^= 1; }
         }
     } else {
         // ===================== epilogue =====================
@@ -160,8 +175,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int pitch = a.n_cta * 4;                            // staging row pitch (bytes), a multiple of 128
         const uint32_t stage_q = smem_u32(smem) + quarter * 32 * pitch;
         asm volatile("griddepcontrol.wait;" ::: "memory");        // nothing of the previous kernel is overwritten before it finished
+        if (warp == 2 && lane == 0) TR(2);
         mbar_wait(bar_tfull, 0);
         tc_fence_after();
+        if (warp == 2 && lane == 0) TR(2);
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int chunks = a.n_cta / 32, c_mid = (chunks + 1) / 2;
         {
@@ -178,12 +195,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");      // both warps of the quarter staged their columns
         // warp `half` finishes rows [16 half, +16) of the quarter: one full row per instruction, 4 columns per lane
+        // (every lane runs every iteration — the shuffles below need the whole warp; lanes past the slice only skip the stores)
         for (int cg = 0; cg * 128 < a.n_cta; ++cg) {
             const int col = cg * 128 + 4 * lane, gcol = slice * a.n_cta + col;
-            if (col >= a.n_cta) continue;
+            const bool lane_on = col < a.n_cta;
             float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.bias) bb = __ldg(reinterpret_cast<const float4*>(a.bias + gcol));
-            const int nv = a.n_valid - gcol;                       // valid columns among this lane's 4
+            if (a.bias && lane_on) bb = __ldg(reinterpret_cast<const float4*>(a.bias + gcol));
+            const int nv = lane_on ? a.n_valid - gcol : 0;       // valid columns among this lane's 4
 #pragma unroll 4
             for (int i = 0; i < 16; ++i) {
                 const int rr = half * 16 + i;
@@ -210,12 +228,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     }
 
+    if (warp == 2 && lane == 0) TR(2);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_relaxed();                   // no CTA exits while its peer may still signal / read its shared memory
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc_1cta(tmem_base, a.tmem_cols);
+        tmem_dealloc(tmem_base, a.tmem_cols);
     }
+    tl.end();
+    if (warp == 2 && lane == 0) TR(2);
 }
 
 // 7x7 neighbourhood of the 2-channel flow as GEMM rows (the motion encoder's convf1, gru.py:50,57, becomes a 1x1 convolution):
@@ -254,6 +276,13 @@ flow_im2col_kernel(const float* __restrict__ coords1, const float* __restrict__ 
 
 }  // namespace
 
+static Timeline g_timeline = {nullptr, 0, -1};
+static unsigned long long* g_conv_trace = nullptr;
+extern "C" void macvo_conv_tc_set_trace(void* buf) { g_conv_trace = static_cast<unsigned long long*>(buf); }
+/* profiling aid (tools/decoder_timeline.py): device buffer of 1 + 3 * capacity uint64; NULL switches it off (the default) */
+extern "C" void macvo_tc_set_timeline(void* buf, int capacity) { g_timeline.buf = static_cast<unsigned long long*>(buf); g_timeline.capacity = capacity; }
+Timeline macvo_tc_timeline() { return g_timeline; }
+
 extern "C" size_t macvo_rows_count(int batch, int height, int width, int vertical) {
     if (batch <= 0 || height <= 0 || width <= 0) return 0;
     return (size_t)macvo_rows::alloc_rows(batch, height, width, vertical);
@@ -272,46 +301,62 @@ extern "C" int macvo_conv_tc(const void* in_rows, int in_channels, int in_dense,
     a.in_dense = in_dense;
     a.batch = batch; a.height = height; a.width = width; a.wp = width + 4;
     a.m_rows = in_dense ? batch * height * width : macvo_rows::padded_pixels(batch, height, width, 0);
-    const int m_tiles = (a.m_rows + TILE_M - 1) / TILE_M;
-    // slices of output channels: as many CTAs as fit one wave of the 148 SMs, every slice a multiple of 32 columns (<= 256)
+    const int pairs = (a.m_rows + 2 * TILE_M - 1) / (2 * TILE_M);
+    // slices of output channels: as many CTA pairs as fit one wave of the 148 SMs, every slice a multiple of 32 columns (<= 256)
     int slices = 1;
     for (int s = 1; s <= 8; ++s)
-        if (n_pad % (32 * s) == 0 && n_pad / s <= 256 && (m_tiles * s <= 148 || n_pad / slices > 256)) slices = s;
+        if (n_pad % (32 * s) == 0 && n_pad / s <= 256 && (2 * pairs * s <= 148 || n_pad / slices > 256)) slices = s;
     a.n_cta = n_pad / slices;
     if (a.n_cta > 256) return MACVO_E_UNSUPPORTED;
     a.tmem_cols = 32;
     while (a.tmem_cols < a.n_cta) a.tmem_cols *= 2;
-    const int b_bytes = a.n_cta * 128;
-    a.b_slots = (SMEM_MAX - A_SLOTS * A_BYTES - 2048) / b_bytes;
-    if (a.b_slots > 12) a.b_slots = 12;
-    if (a.b_slots < 3) return MACVO_E_UNSUPPORTED;
-    const int smem_bytes = A_SLOTS * A_BYTES + a.b_slots * b_bytes + 512 + 1024;
-    if (A_SLOTS * A_BYTES + a.b_slots * b_bytes < TILE_M * a.n_cta * 4) return MACVO_E_UNSUPPORTED;   // epilogue staging reuses the ring
+    const int tpg = a.taps == 9 ? 3 : 1;
+    const int slot_bytes = A_BYTES + tpg * (a.n_cta / 2) * 128;
+    a.slots = (SMEM_MAX - 2048) / slot_bytes;
+    if (a.slots > 8) a.slots = 8;
+    if (a.slots < 2 || a.slots * slot_bytes < TILE_M * a.n_cta * 4) return MACVO_E_UNSUPPORTED;    // epilogue staging reuses the ring
+    const int smem_bytes = a.slots * slot_bytes + 512 + 1024;
     a.relu = relu; a.n_valid = n_valid; a.bias = bias;
     a.out16 = static_cast<__half*>(out16); a.out16_pitch = out16_pitch; a.out16_off = out16_offset; a.out16_dense = out16_dense;
     a.out32 = out32; a.out32_pitch = out32_pitch; a.out32_off = out32_offset;
-    a.idesc = make_idesc_f16(TILE_M, a.n_cta);
+    a.idesc = make_idesc_f16(2 * TILE_M, a.n_cta);
+    a.tl = g_timeline;
+    a.trace = g_conv_trace;
     CUtensorMap map_a, map_w;
     const uint64_t in_rows_total = in_dense ? (uint64_t)a.m_rows : (uint64_t)macvo_rows::alloc_rows(batch, height, width, 0);
     if (!make_map_2d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, in_rows, in_channels, in_rows_total, (uint64_t)in_channels * 2, BLOCK_K, A_ROWS))
         return MACVO_E_DRIVER;
-    const uint64_t kk = (uint64_t)a.taps * in_channels;
-    if (!make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, weights, kk, n_pad, kk * 2, BLOCK_K, a.n_cta)) return MACVO_E_DRIVER;
+    // filters (n_pad, taps * C) as the 3-D view (k within the row, n, dx): box = 64 channels x n_cta / 2 rows x the group's taps
+    {
+        PFN_encodeTiled enc = get_encode_fn();
+        if (!enc) return MACVO_E_DRIVER;
+        const uint64_t kk = (uint64_t)a.taps * in_channels;
+        cuuint64_t dims[3] = {kk, (cuuint64_t)n_pad, (cuuint64_t)tpg};
+        cuuint64_t strides[2] = {kk * 2, (cuuint64_t)in_channels * 2};
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)(a.n_cta / 2), (cuuint32_t)tpg};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(weights), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return MACVO_E_DRIVER;
+    }
     static bool configured = false;
     if (!configured) {
         MACVO_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(m_tiles, slices);
+    cfg.gridDim = dim3(2 * pairs, slices);
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attrs[1];
-    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     MACVO_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_kernel, map_a, map_w, a));
     return MACVO_OK;
 }

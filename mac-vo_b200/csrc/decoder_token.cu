@@ -17,6 +17,8 @@
 // precision modes (the chain it replaces ran TF32 tensor-core GEMMs under allow_tf32): 0.6 GFLOP per call, HBM/L2
 // traffic = the lookup rows (3.1 MB), the keys / values (39 MB) and the output rows (6.1 MB) at 640x480.
 #include "common.cuh"
+#include "rows_layout.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -119,7 +121,7 @@ template <int TP>
 __global__ void __launch_bounds__(4 * TP, 1)
 decoder_token_kernel(const float* __restrict__ cf, const float* __restrict__ coords, const float* __restrict__ key,
                      const float* __restrict__ value, const float* __restrict__ blob, float* __restrict__ out,
-                     long long pixels, int n1, float eps) {
+                     long long pixels, int n1, float eps, __half* __restrict__ out16, int height, int width) {
     extern __shared__ __align__(16) float sm[];
     using L = Lay<TP>;
     constexpr int LD = L::LD, NT = L::NT, S_X0 = L::S_X0, S_CAT = L::S_CAT, S_A = L::S_A;
@@ -267,6 +269,17 @@ decoder_token_kernel(const float* __restrict__ cf, const float* __restrict__ coo
     store_tile<EPI_RESID, LD>(A, sm + V_BFFN3, A, og, pg, acc);
     __syncthreads();
 
+    if (out16 != nullptr) {
+        // fp16 layout-U rows (csrc/rows_layout.cuh, 192 channels per row) for the tensor-core motion encoder: 2 channels per thread
+        for (int e = tid; e < valid * (OUTC / 2); e += NT) {
+            const int r = e / (OUTC / 2), c = 2 * (e - r * (OUTC / 2));
+            auto val = [&](int ch) { return ch < C ? A[ch * LD + r] : (ch < C + CF ? X0[(ch - C) * LD + r] : 0.f); };
+            const long long p = p0 + r;
+            const int x = (int)(p % width), y = (int)((p / width) % height), b = (int)(p / ((long long)width * height));
+            *reinterpret_cast<__half2*>(out16 + macvo_rows::urow(b, y, x, height, width) * 192 + c) = __floats2half2_rn(val(c), val(c + 1));
+        }
+        return;
+    }
     // out rows [g | cost_forward | 0]: coalesced (consecutive threads -> consecutive floats of the (P,160) matrix)
     float* ot = out + p0 * OUTC;
     for (int e = tid; e < valid * OUTC; e += NT) {
@@ -281,10 +294,11 @@ extern "C" size_t macvo_decoder_token_blob_floats(void) { return BLOB; }
 
 template <int TP>
 static int launch_token(const float* cf, const float* coords, const float* key, const float* value, const float* blob,
-                        float* out, long long pixels, int n1, float eps, cudaStream_t st) {
+                        float* out, long long pixels, int n1, float eps, cudaStream_t st, __half* out16 = nullptr, int height = 0,
+                        int width = 0) {
     constexpr int smem = Lay<TP>::S_END * 4;
     MACVO_CUDA_TRY(cudaFuncSetAttribute(decoder_token_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    decoder_token_kernel<TP><<<(unsigned)((pixels + TP - 1) / TP), 4 * TP, smem, st>>>(cf, coords, key, value, blob, out, pixels, n1, eps);
+    decoder_token_kernel<TP><<<(unsigned)((pixels + TP - 1) / TP), 4 * TP, smem, st>>>(cf, coords, key, value, blob, out, pixels, n1, eps, out16, height, width);
     MACVO_LAUNCH_CHECK();
     return MACVO_OK;
 }
@@ -301,4 +315,21 @@ extern "C" int macvo_decoder_token(const float* cost_forward, const float* coord
     cudaStream_t st = as_stream(stream);
     return cost(72) < cost(64) ? launch_token<72>(cost_forward, coords, key, value, weight_blob, out, pixels, n1, eps, st)
                                : launch_token<64>(cost_forward, coords, key, value, weight_blob, out, pixels, n1, eps, st);
+}
+
+/* same, writing fp16 layout-U rows (rows, 192): channels [0,160) = [g | cost_forward | 0], the tcgen05 motion encoder's input */
+extern "C" int macvo_decoder_token_rows(const float* cost_forward, const float* coords, const float* key, const float* value,
+                                        const float* weight_blob, void* out16_rows, int batch, int height, int width, float eps,
+                                        void* stream) {
+    if (!cost_forward || !coords || !key || !value || !weight_blob || !out16_rows || batch <= 0 || height <= 0 || width <= 0) return MACVO_E_ARG;
+    const int n1 = height * width;
+    const long long pixels = (long long)batch * n1;
+    int dev = 0, sms = 148;
+    MACVO_CUDA_TRY(cudaGetDevice(&dev));
+    MACVO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    auto cost = [&](int tp) { const long long tiles = (pixels + tp - 1) / tp; return ((tiles + sms - 1) / sms) * tp; };
+    cudaStream_t st = as_stream(stream);
+    __half* o = static_cast<__half*>(out16_rows);
+    return cost(72) < cost(64) ? launch_token<72>(cost_forward, coords, key, value, weight_blob, nullptr, pixels, n1, eps, st, o, height, width)
+                               : launch_token<64>(cost_forward, coords, key, value, weight_blob, nullptr, pixels, n1, eps, st, o, height, width);
 }

@@ -40,18 +40,6 @@ template <int N> struct Cfg {
     static constexpr int SMEM = A_SLOTS * A_BYTES + B_SLOTS * B_BYTES + 512 + 1024;
 };
 
-__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void umma_f16_ss2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
 // MUFU-based gate functions (ex2 + rcp): absolute error ~1e-7, far below the fp16 rounding of the convolution operands
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
@@ -67,6 +55,7 @@ struct Geometry {
     int lines, len, lp;          // lines of `len` pixels, padded pitch lp = len + 4
     int m_pad, pairs;            // padded pixels, CTA pairs per unit
     unsigned long long* trace;   // profiling aid (NULL in production): globaltimer events of cluster 0's leader, [role][event]
+    Timeline tl;                 // profiling aid: in-stream timeline shared with csrc/conv_tc.cu
 };
 
 // STAGE 0: N = 256 (z | r)   STAGE 1: N = 128 (q, then the blend)
@@ -95,6 +84,7 @@ gru_conv_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
     const Unit u = unit == 0 ? u0 : u1;
     const CUtensorMap* map_h = unit == 0 ? &map_h0 : &map_h1;
     const CUtensorMap* map_w = unit == 0 ? &map_w0 : &map_w1;
+    g.tl.begin(STAGE + 2 * g.vertical);
     int tr_n = 0;
     auto TR = [&](int role) {
         if (g.trace != nullptr && blockIdx.x == 0 && tr_n < 64) {
@@ -283,12 +273,13 @@ gru_conv_tc_kernel(const __grid_constant__ CUtensorMap map_h0, const __grid_cons
     if (warp == 2 && lane == 0) TR(2);
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                       // no CTA exits while its peer may still signal / copy into it
+    cluster_sync_relaxed();                   // no CTA exits while its peer may still signal / read its shared memory
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, N);
     }
     if (warp == 2 && lane == 0) TR(2);
+    g.tl.end();
 }
 
 // fp32 pixel rows (dense order) -> fp16 operand rows of one layout (pad rows are never written: they stay zero)
@@ -339,6 +330,7 @@ Geometry make_geometry(int batch, int height, int width, int vertical) {
     g.m_pad = g.lines * g.lp;
     g.pairs = (g.m_pad + 2 * TILE_M - 1) / (2 * TILE_M);
     g.trace = nullptr;
+    g.tl = Timeline{nullptr, 0, -1};
     return g;
 }
 size_t operand_rows(const Geometry& g) { return (size_t)macvo_rows::alloc_rows(g.batch, g.height, g.width, g.vertical); }
@@ -375,6 +367,7 @@ int launch_stage(const CUtensorMap* maps, Unit u0, Unit u1, const Geometry& g, i
 
 }  // namespace
 
+Timeline macvo_tc_timeline();          // csrc/conv_tc.cu
 static unsigned long long* g_trace = nullptr;
 /* profiling aid (tools/gru_probe.py): device buffer of 3 x 64 u64 that cluster 0's leader fills with globaltimer events */
 extern "C" void macvo_gru_tc_set_trace(void* buf) { g_trace = static_cast<unsigned long long*>(buf); }
@@ -418,6 +411,7 @@ extern "C" int macvo_gru_tc_stage(int stage, int vertical, int batch, int height
         if (!h_rows[i] || !weights[i] || !bias[i] || !h_master[i] || !z[i] || !out_rows[i]) return MACVO_E_ARG;
     Geometry g = make_geometry(batch, height, width, vertical);
     g.trace = g_trace;
+    g.tl = macvo_tc_timeline();
     const int n = stage == 0 ? 256 : 128;
     CUtensorMap maps[5];
     for (int i = 0; i < 2; ++i) {

@@ -51,6 +51,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// execution-only rendezvous of the cluster (no memory ordering): used before exit, where the default .release arrive would first
+// wait for every in-flight global store of the epilogue to be acknowledged (2-4 us on the event traces of the decoder kernels)
+__device__ __forceinline__ void cluster_sync_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;    // shared-window address with the CTA-pair rank bit cleared -> CTA 0
 // 2-CTA TMA load: data lands in THIS CTA's smem, the complete_tx goes to the LEADER CTA's mbarrier
 __device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -182,6 +187,46 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+
+// ---- CTA-pair variants with both operands in shared memory (csrc/gru_conv_tc.cu, csrc/conv_tc.cu) ----------------------------
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// ---- profiling aid: in-stream timeline (globaltimer) of the tensor-core kernels --------------------------------------------
+// buf[0] = event counter, then (kernel id, start ns, end ns) triples written by thread 0 of block 0 of every launch.
+struct Timeline {
+    unsigned long long* buf; int capacity, slot;
+    __device__ __forceinline__ void begin(int id) {
+        slot = -1;
+        if (buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+            const int i = (int)atomicAdd(buf, 1ULL);
+            if (i < capacity) {
+                slot = i;
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                buf[1 + 3 * i] = (unsigned long long)id;
+                buf[2 + 3 * i] = t;
+            }
+        }
+    }
+    __device__ __forceinline__ void end() {
+        if (slot >= 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            buf[3 + 3 * slot] = t;
+        }
+    }
+};
 
 // ---- host side: tensor maps ------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -249,6 +249,7 @@ class FlowFormerCovNet:
         self.enc_dtype, self.dec_dtype, self.depth = enc_dtype, dec_dtype, decoder_depth
         # TF32 mode only: SepConvGRU on the tcgen05 kernel (False / MACVO_B200_GRU_TC=0: cuDNN convolutions + glue kernels)
         self.gru_tensor_cores = os.environ.get("MACVO_B200_GRU_TC", "1") != "0"
+        self.conv_tensor_cores = os.environ.get("MACVO_B200_CONV_TC", "1") != "0"      # same, the decoder's 3x3 / 1x1 convolutions
         self._ops = None
         self._fused_conv_relu = True
         if corr_fn is None or lookup_fn is None or self.device.type == "cuda":
@@ -646,6 +647,31 @@ class FlowFormerCovNet:
             q = F.conv2d(rhx_map, self.W[p + f"convq{o}.weight"], None, padding=pad)
             self._ops.gru_blend(q.permute(0, 2, 3, 1), z, hx, h_dense if o == "2" else None, self.W[p + f"convq{o}.bias"])
 
+    def _make_decoder_tc(self, B: int, H: int, W: int, device):
+        """Buffers (fp16 padded pixel rows, csrc/rows_layout.cuh) and packed filters of the tensor-core decoder iteration
+        (csrc/conv_tc.cu): motion encoder, value projection, flow head, covariance head."""
+        from types import SimpleNamespace
+        ops, m = self._ops, "memory_decoder."
+        e, ub, cu = m + "update_block.encoder.", m + "update_block.", m + "cov_update."
+        rows, P = ops.rows_count(B, H, W), B * H * W
+        u16 = lambda c: torch.zeros(rows, c, dtype=torch.float16, device=device)
+        t = SimpleNamespace(shape=(B, H, W))
+        t.tok16, t.c1, t.cp, t.f1, t.mf16 = u16(192), u16(256), u16(256), u16(128), u16(128)
+        t.fh, t.ch1, t.ch2, t.ch3 = u16(256), u16(256), u16(128), u16(64)
+        t.f0 = torch.zeros(P, 128, dtype=torch.float16, device=device)            # im2col rows of the flow (dense)
+        t.v16 = torch.zeros(P, 128, dtype=torch.float16, device=device)
+        t.mf32 = torch.zeros(P, 128, dtype=torch.float32, device=device)
+        t.d_flow, t.d_cov = (torch.zeros(P, 2, dtype=torch.float32, device=device) for _ in range(2))
+        pk = lambda name, cin=None: ops.pack_conv_filter(self.W[name + ".weight"], self.W.get(name + ".bias"), cin, device)
+        t.convc1 = pk(e + "convc1p", 192)
+        t.convc2, t.convf2, t.conv = pk(e + "convc2"), pk(e + "convf2"), pk(e + "conv")
+        wf1 = self.W[e + "convf1.weight"]                                          # (128, 2, 7, 7) -> 1x1 over the 98 im2col columns
+        t.convf1 = ops.pack_conv_filter(wf1.permute(0, 2, 3, 1).reshape(wf1.shape[0], 98, 1, 1), self.W[e + "convf1.bias"], 128, device)
+        t.to_v = pk(ub + "aggregator.to_v")
+        t.fh1, t.fh2 = pk(ub + "flow_head.conv1"), pk(ub + "flow_head.conv2")
+        t.chw = [pk(cu + f"cov_head.conv{i}") for i in (1, 2, 3, 4)]
+        return t
+
     @staticmethod
     def convex_upsample(flow: Tensor, mask: Tensor) -> Tensor:
         """`upsample_flow` (decoder.py:131-139): softmax over the 9 neighbours, 8x."""
@@ -679,7 +705,7 @@ class FlowFormerCovNet:
         native = self._native(ctx) and dd == torch.float32
         # TF32 mode: both SepConvGRU units run on the tcgen05 kernel (fp16 operands, fp32 state; csrc/gru_conv_tc.cu);
         # strict mode keeps cuDNN's fp32 convolutions + the fused glue kernels
-        gru_tc = None
+        gru_tc = dec_tc = None
         if native:
             side = self._memo(("side_stream", ctx.device), lambda: torch.cuda.Stream(ctx.device))
             as_map = lambda t: t.view(B, H1, W1, -1).permute(0, 3, 1, 2)                   # channels_last logical map
@@ -692,6 +718,7 @@ class FlowFormerCovNet:
                 bs = [{n: self.W[pre + "gru." + n + ".bias"] for n in names} for pre in (ub, cu)]
                 return self._ops.SepConvGruTC(ws, bs, B, H1, W1, ctx.device)
             gru_tc = self._memo(("gru_tc", B, H1, W1, ctx.device), make_gru)
+            dec_tc = self._memo(("decoder_tc", B, H1, W1, ctx.device), lambda: self._make_decoder_tc(B, H1, W1, ctx.device))
             gru_tc.set_context(inp_rows)
             gru_tc.set_state(0, net_rows)
             gru_tc.set_state(1, net_rows)
@@ -712,7 +739,61 @@ class FlowFormerCovNet:
         if fast_tokens:
             token_blob = self._memo(("token_blob", ctx.device), lambda: self._ops.decoder_token_blob(self.W, m))
             key, value = key.contiguous(), value.contiguous()
+        use_tc = dec_tc is not None and fast_tokens and attention_h is not None and self.conv_tensor_cores
+        cov_done = None
+        if use_tc:
+            side2 = self._memo(("side_stream2", ctx.device), lambda: torch.cuda.Stream(ctx.device))
         for _ in range(self.depth):
+            if use_tc:
+                # TF32 mode: the whole iteration on our kernels — lookup, token kernel, motion encoder / value projection / heads
+                # on the tcgen05 convolution kernel (fp16 rows between the layers), SepConvGRU on its tcgen05 kernel; the one
+                # library call left is the GMA aggregation GEMM
+                ops, t, shp = self._ops, dec_tc, (B, H1, W1)
+                main = torch.cuda.current_stream()
+                fork = torch.cuda.Event()
+                fork.record(main)
+                with torch.cuda.stream(side):                                                # flow branch of the motion encoder
+                    side.wait_event(fork)
+                    ops.flow_im2col(coords1, coords0, t.f0, t.mf32, t.mf16)
+                    ops.conv_tc(t.f0, t.convf1[0], t.convf1[1], 128, 1, True, shp, in_dense=True, out16=t.f1)
+                    ops.conv_tc(t.f1, t.convf2[0], t.convf2[1], 64, 3, True, shp, out16=t.cp, out16_offset=192)
+                    joinf = torch.cuda.Event()
+                    joinf.record(side)
+                cf = ops.corr_lookup(cost_maps, coords1, rows=True)                          # (P, 81)
+                ops.decoder_token(cf, coords1, key, value, token_blob, out16_rows=t.tok16)   # rows [global | forward | 0] in fp16
+                ops.conv_tc(t.tok16, t.convc1[0], t.convc1[1], 256, 1, True, shp, out16=t.c1)
+                ops.conv_tc(t.c1, t.convc2[0], t.convc2[1], 192, 3, True, shp, out16=t.cp)
+                main.wait_event(joinf)
+                ops.conv_tc(t.cp, t.conv[0], t.conv[1], 126, 3, True, shp, out16=t.mf16, out32=t.mf32)   # + flow in channels 126, 127
+                ops.conv_tc(t.mf16, t.to_v[0], None, 128, 1, False, shp, out16=t.v16, out16_dense=True)
+                agg = torch.bmm(attention_h, t.v16.view(B, N, 128), out_dtype=torch.float32)  # GMA aggregation (gma.py:84-130)
+                if cov_done is not None:            # the previous iteration's covariance head still reads the covariance unit's state rows
+                    main.wait_event(cov_done)
+                gru_tc.step(t.mf32, agg.view(P, 128), gamma)
+                fork2 = torch.cuda.Event()
+                fork2.record(main)
+                # The covariance head (4 chained convolutions, covhead.py:20-58) feeds only the covariance coordinates: it runs on
+                # its own stream and is joined right before the NEXT iteration's GRU update, so it overlaps the next lookup / token
+                # kernel / motion encoder instead of extending this iteration (they depend on the flow head only).
+                with torch.cuda.stream(side2):
+                    side2.wait_event(fork2)
+                    ops.conv_tc(gru_tc.h_rows[0][1], t.chw[0][0], t.chw[0][1], 256, 3, True, shp, out16=t.ch1)
+                    ops.conv_tc(t.ch1, t.chw[1][0], t.chw[1][1], 128, 3, False, shp, out16=t.ch2)
+                    ops.conv_tc(t.ch2, t.chw[2][0], t.chw[2][1], 64, 3, True, shp, out16=t.ch3)
+                    ops.conv_tc(t.ch3, t.chw[3][0], t.chw[3][1], 2, 3, False, shp, out32=t.d_cov)
+                    ccoords1 = ccoords1 + t.d_cov.view(B, H1, W1, 2).permute(0, 3, 1, 2)
+                    cov_done = torch.cuda.Event()
+                    cov_done.record(side2)
+                ccoords1.record_stream(main)
+                ops.conv_tc(gru_tc.h_rows[0][0], t.fh1[0], t.fh1[1], 256, 3, True, shp, out16=t.fh)
+                ops.conv_tc(t.fh, t.fh2[0], t.fh2[1], 2, 3, False, shp, out32=t.d_flow)
+                coords1 = coords1 + t.d_flow.view(B, H1, W1, 2).permute(0, 3, 1, 2)
+                if self.taps is not None:
+                    main.wait_event(cov_done)
+                net, cnet = as_map(net_d), as_map(cnet_d)
+                self._tap("flow_iter", coords1 - coords0)
+                self._tap("cov_iter", ccoords1 - coords0)
+                continue
             flow = (coords1 - coords0).to(dd)
             if native and fast_tokens:
                 # pixels-major rows end to end: lookup kernel -> ONE token kernel (token MLP, LayerNorm + sine embedding, q
@@ -801,6 +882,8 @@ class FlowFormerCovNet:
             ccoords1 = ccoords1 + _f32(d_cov)
             self._tap("flow_iter", coords1 - coords0)
             self._tap("cov_iter", ccoords1 - coords0)
+        if cov_done is not None:
+            torch.cuda.current_stream().wait_event(cov_done)
         # the reference evaluates both mask heads + upsampling every iteration but (eval mode) returns
         # only the last one (covhead.py:137-140) -> evaluate once
         up_mask = _f32(0.25 * self._conv(F.relu(self._conv(net, ub + "mask.0", padding=1)), ub + "mask.2"))

@@ -95,10 +95,13 @@ EXPORTS = {
     "macvo_latent_pool": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_void_p]),
     "macvo_decoder_token_blob_floats": (C.c_size_t, []),
     "macvo_decoder_token": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "macvo_decoder_token_rows": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_float, C.c_void_p]),
     "macvo_gru_input": (C.c_int, [C.c_void_p] * 7 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_gates": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_blend": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "macvo_rows_count": (C.c_size_t, [C.c_int] * 4),
+    "macvo_tc_set_timeline": (None, [C.c_void_p, C.c_int]),
+    "macvo_conv_tc_set_trace": (None, [C.c_void_p]),
     "macvo_conv_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 7
                       + [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p] + [C.c_int] * 2 + [C.c_void_p]),
     "macvo_flow_im2col": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p]),
@@ -1044,9 +1047,11 @@ def decoder_token_blob(w: dict, prefix: str = "memory_decoder.") -> Tensor:
     return blob.contiguous()
 
 
-def decoder_token(cost_forward: Tensor, coords: Tensor, key: Tensor, value: Tensor, blob: Tensor, eps: float = 1e-5) -> Tensor:
+def decoder_token(cost_forward: Tensor, coords: Tensor, key: Tensor, value: Tensor, blob: Tensor, eps: float = 1e-5,
+                  out16_rows: Tensor | None = None) -> Tensor:
     """one refinement iteration's token path: lookup rows (P,81) + coords (B,2,H,W) + per-pixel keys / values (P,8,64)
-    -> (P,160) rows [cost_global | cost_forward | 0] (decoder.py:20-76,112-116; csrc/decoder_token.cu)"""
+    -> (P,160) rows [cost_global | cost_forward | 0] (decoder.py:20-76,112-116; csrc/decoder_token.cu); with `out16_rows` (a
+    layout-U fp16 buffer of 192 channels, csrc/rows_layout.cuh) the rows are written there instead (and returned)"""
     cf = _dense(cost_forward, 81, "decoder_token cost_forward")
     co = _dev(coords, torch.float32, "decoder_token coords")
     B, _, H, W = co.shape
@@ -1054,6 +1059,16 @@ def decoder_token(cost_forward: Tensor, coords: Tensor, key: Tensor, value: Tens
     k, v = _dense(key, 64, "decoder_token key"), _dense(value, 64, "decoder_token value")
     if cf.numel() != P * 81 or k.numel() != P * 512 or v.numel() != P * 512:
         raise MacvoB200Error("decoder_token: expects cost_forward (P,81), key / value (P,8,64) with P = B*H*W")
+    if out16_rows is not None:
+        if not (out16_rows.is_cuda and out16_rows.dtype == torch.float16 and out16_rows.is_contiguous()
+                and tuple(out16_rows.shape) == (rows_count(B, H, W), 192)):
+            raise MacvoB200Error("decoder_token: out16_rows must be a contiguous fp16 (rows_count(B, H, W), 192) CUDA tensor")
+        rc = load_library().macvo_decoder_token_rows(cf.data_ptr(), co.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                                     _dense(blob, 1, "decoder_token blob").data_ptr(), out16_rows.data_ptr(), B, H, W,
+                                                     float(eps), _stream())
+        _check(rc, "macvo_decoder_token_rows")
+        LAUNCHES[0] += 1
+        return out16_rows
     out = torch.empty((P, 160), dtype=torch.float32, device=cf.device)
     rc = load_library().macvo_decoder_token(cf.data_ptr(), co.data_ptr(), k.data_ptr(), v.data_ptr(),
                                             _dense(blob, 1, "decoder_token blob").data_ptr(), out.data_ptr(), B, H * W,

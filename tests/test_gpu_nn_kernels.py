@@ -176,11 +176,16 @@ def test_sepconv_gru_tensor_cores(ops, shape):
             assert torch.isfinite(got).all()
             assert (got - ref_r[u]).abs().max().item() <= 1e-3, (it, u)
             assert (got - ref_t[u]).abs().max().item() <= 4e-3, (it, u)
-    # pad rows of every operand buffer are still zero (the kernels only write pixel rows)
-    for o, (lines, ln) in enumerate(((B * H, W), (B * W, H))):
-        for buf in [gru.x[o]] + gru.h_rows[o] + gru.rh_rows[o]:
-            body = buf[2:2 + lines * (ln + 4)].view(lines, ln + 4, -1)
-            assert not body[:, :2].any() and not body[:, -2:].any() and not buf[:2].any() and not buf[2 + lines * (ln + 4):].any()
+    # pad rows of every operand buffer are still zero (the kernels only write pixel rows): layout U for the 1x5 pass, V for 5x1
+    for buf in [gru.x[0]] + gru.h_rows[0] + gru.rh_rows[0]:
+        n = B * (H + 4) * (W + 4)
+        body = buf[2:2 + n].view(B, H + 4, W + 4, -1).clone()
+        body[:, 2:H + 2, 2:W + 2] = 0
+        assert not body.any() and not buf[:2].any() and not buf[2 + n:].any()
+    for buf in [gru.x[1]] + gru.h_rows[1] + gru.rh_rows[1]:
+        n = B * W * (H + 4)
+        body = buf[2:2 + n].view(B * W, H + 4, -1)
+        assert not body[:, :2].any() and not body[:, -2:].any() and not buf[:2].any() and not buf[2 + n:].any()
 
 
 def _to_rows_u(ops, x_map, shape):
@@ -254,7 +259,7 @@ def test_flow_im2col(ops):
     flow = c1 - c0
     assert torch.equal(mf32[:, 126:], flow.permute(0, 2, 3, 1).reshape(P, 2)) and not mf32[:, :126].any()
     assert torch.equal(_from_rows_u(mf16, (B, H, W))[:, 126:], flow.half().double())
-    wp, bp, n = ops.pack_conv_filter(w, b, in_channels=128)
+    wp, bp, n = ops.pack_conv_filter(w.permute(0, 2, 3, 1).reshape(128, 98, 1, 1), b, in_channels=128)   # 1x1 over the im2col columns
     out = torch.zeros(P, 128, device=DEV)
     ops.conv_tc(rows, wp, bp, n, 1, True, (B, H, W), in_dense=True, out32=out)
     ref = F.conv2d(flow.half().double(), w.half().double(), b.double(), padding=3).relu()
@@ -340,6 +345,11 @@ def test_decoder_token_kernel(ops, b, h, w):
     blob = ops.decoder_token_blob(sd)
     got = ops.decoder_token(cf, coords, key, value, blob)
     assert got.shape == (P, 160) and torch.equal(got[:, 64:145], cf) and not got[:, 145:].any()
+    # the fp16 layout-U variant (the tensor-core motion encoder's input) holds the same rows, rounded once
+    rows16 = torch.zeros(ops.rows_count(b, h, w), 192, dtype=torch.float16, device=DEV)
+    assert ops.decoder_token(cf, coords, key, value, blob, out16_rows=rows16) is rows16
+    body = _from_rows_u(rows16, (b, h, w))                                      # (B, 192, H, W); asserts the padding stayed zero
+    assert torch.equal(body[:, :160].permute(0, 2, 3, 1).reshape(P, 160), got.half().double()) and not body[:, 160:].any()
 
     m, ca = "memory_decoder.", "memory_decoder.decoder_layer.cross_attend."
     W = {k: v.double() for k, v in sd.items()}

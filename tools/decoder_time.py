@@ -1,4 +1,4 @@
-"""Device time of the 12-iteration decoder alone (captured into a CUDA graph), SepConvGRU on tcgen05 vs cuDNN + glue kernels."""
+"""Device time of the 12-iteration decoder alone (captured into a CUDA graph): tcgen05 convolutions + GRU vs GRU only vs cuDNN."""
 import json
 import os
 import sys
@@ -23,8 +23,9 @@ with torch.inference_mode():
     cm, cmaps = net.cost_perceiver(cv, ctx)
     ctx, cmaps = ctx.float(), cmaps.float()
     ref = None
-    for mode in (True, False):
-        net.gru_tensor_cores = mode
+    modes = sys.argv[1].split(",") if len(sys.argv) > 1 else ("conv_tc+gru_tc", "gru_tc", "cudnn")
+    for mode in modes:
+        net.gru_tensor_cores, net.conv_tensor_cores = mode != "cudnn", mode == "conv_tc+gru_tc"
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
             for _ in range(2):
@@ -40,10 +41,10 @@ with torch.inference_mode():
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
         ts.sort()
-        out["decoder_ms_gru_tc" if mode else "decoder_ms_cudnn_gru"] = ts[len(ts) // 2]
+        out["decoder_ms_" + mode] = ts[len(ts) // 2]
         if ref is None:
             ref = [r.clone() for r in res]
         else:
-            out["flow_diff_rel"] = ((res[0] - ref[0]).abs().max() / ref[0].abs().max()).item()
-            out["logcov_diff_abs"] = (res[1] - ref[1]).abs().max().item()
+            out["flow_diff_rel_vs_" + mode] = ((res[0] - ref[0]).abs().max() / ref[0].abs().max()).item()
+            out["logcov_diff_abs_vs_" + mode] = (res[1] - ref[1]).abs().max().item()
 print(json.dumps(out))
