@@ -331,7 +331,9 @@ int macvo_gru_blend(const float* q, const float* bias, const float* z, float* hx
  *   weights   (n_pad, ksize^2 * in_channels) fp16, K index = (ky * ksize + kx) * in_channels + c; n_pad % 32 == 0, rows >= n_valid
  *             zero; bias (n_pad) fp32 or NULL; relu != 0 applies max(., 0)
  *   out16     optional fp16 rows [.., out16_offset + n] with row pitch out16_pitch (elements): layout U rows, or dense pixel rows when
- *             out16_dense; out32: optional fp32 dense pixel rows. Only columns n < n_valid are stored. */
+ *             out16_dense; out32: optional fp32 dense pixel rows, or — out32_planes != 0 — a (batch, n_valid, H, W) fp32 map to
+ *             which the result is ADDED in place (the decoder's `coords1 = coords1 + delta_flow`, covhead.py:133-134).
+ *             Only columns n < n_valid are stored. */
 size_t macvo_rows_count(int batch, int height, int width, int vertical);
 /* profiling aid: device buffer of 1 + 3 * capacity uint64 = event count, then (kernel id, start ns, end ns) per launch of the
  * tensor-core convolution / GRU kernels; NULL (the default) switches it off */
@@ -340,7 +342,8 @@ void macvo_tc_set_timeline(void* buf, int capacity);
 void macvo_conv_tc_set_trace(void* buf);
 int macvo_conv_tc(const void* in_rows, int in_channels, int in_dense, const void* weights, const float* bias, int n_pad,
                   int n_valid, int ksize, int relu, int batch, int height, int width, void* out16, int out16_pitch,
-                  int out16_offset, int out16_dense, float* out32, int out32_pitch, int out32_offset, void* stream);
+                  int out16_offset, int out16_dense, float* out32, int out32_pitch, int out32_offset, int out32_planes,
+                  void* stream);
 /* the motion encoder's 7x7 convolution of the 2-channel flow as a GEMM operand (gru.py:50,57): rows (pixels, 128) fp16 dense,
  * column (ky * 7 + kx) * 2 + c = (coords1 - coords0)[c, y + ky - 3, x + kx - 3], zero outside / beyond column 98; also writes the
  * flow into channels 126, 127 of the motion-feature rows (mf32: (pixels, 128) fp32 dense, mf16_rows: layout U, 128 ch; may be NULL) */

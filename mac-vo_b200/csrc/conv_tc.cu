@@ -37,6 +37,7 @@ struct ConvArgs {
     const float* bias;            // (grid.y * n_cta) or NULL
     __half* out16; int out16_pitch, out16_off, out16_dense;
     float* out32; int out32_pitch, out32_off;
+    int out32_planes;             // 1: out32 is a (batch, n_valid, H, W) map and the result is ADDED to it (coords += delta)
     uint32_t idesc;
     Timeline tl;                  // profiling aid, buf == NULL in production
     unsigned long long* trace;    // profiling aid: [role][64] globaltimer events of block (0, 0)
@@ -210,7 +211,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 float4 v = lds128(stage_q + rr * pitch + (((col >> 2) ^ (rr & 7)) << 4));
                 v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
                 if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                if (a.out32) {
+                if (a.out32 && a.out32_planes) {
+                    const long long hw = (long long)a.height * a.width, img = d / hw;
+                    float* o = a.out32 + (img * a.n_valid + gcol) * hw + (d - img * hw);
+                    o[0] += v.x; if (nv > 1) o[hw] += v.y; if (nv > 2) o[2 * hw] += v.z; if (nv > 3) o[3 * hw] += v.w;
+                } else if (a.out32) {
                     float* o = a.out32 + d * a.out32_pitch + a.out32_off + gcol;
                     if (nv >= 4 && ((a.out32_pitch | a.out32_off) & 3) == 0) *reinterpret_cast<float4*>(o) = v;
                     else { o[0] = v.x; if (nv > 1) o[1] = v.y; if (nv > 2) o[2] = v.z; if (nv > 3) o[3] = v.w; }
@@ -290,7 +295,8 @@ extern "C" size_t macvo_rows_count(int batch, int height, int width, int vertica
 
 extern "C" int macvo_conv_tc(const void* in_rows, int in_channels, int in_dense, const void* weights, const float* bias, int n_pad,
                              int n_valid, int ksize, int relu, int batch, int height, int width, void* out16, int out16_pitch,
-                             int out16_offset, int out16_dense, float* out32, int out32_pitch, int out32_offset, void* stream) {
+                             int out16_offset, int out16_dense, float* out32, int out32_pitch, int out32_offset, int out32_planes,
+                             void* stream) {
     if (!in_rows || !weights || batch <= 0 || height <= 0 || width <= 0 || in_channels <= 0 || in_channels % BLOCK_K ||
         n_pad <= 0 || n_pad % 32 || n_valid <= 0 || n_valid > n_pad || (ksize != 1 && ksize != 3) || (in_dense && ksize != 1) ||
         (!out16 && !out32) || (out16 && (out16_pitch % 4 || out16_offset % 4)))
@@ -318,7 +324,7 @@ extern "C" int macvo_conv_tc(const void* in_rows, int in_channels, int in_dense,
     const int smem_bytes = a.slots * slot_bytes + 512 + 1024;
     a.relu = relu; a.n_valid = n_valid; a.bias = bias;
     a.out16 = static_cast<__half*>(out16); a.out16_pitch = out16_pitch; a.out16_off = out16_offset; a.out16_dense = out16_dense;
-    a.out32 = out32; a.out32_pitch = out32_pitch; a.out32_off = out32_offset;
+    a.out32 = out32; a.out32_pitch = out32_pitch; a.out32_off = out32_offset; a.out32_planes = out32_planes;
     a.idesc = make_idesc_f16(2 * TILE_M, a.n_cta);
     a.tl = g_timeline;
     a.trace = g_conv_trace;

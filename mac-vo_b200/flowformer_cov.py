@@ -780,14 +780,11 @@ class FlowFormerCovNet:
                     ops.conv_tc(gru_tc.h_rows[0][1], t.chw[0][0], t.chw[0][1], 256, 3, True, shp, out16=t.ch1)
                     ops.conv_tc(t.ch1, t.chw[1][0], t.chw[1][1], 128, 3, False, shp, out16=t.ch2)
                     ops.conv_tc(t.ch2, t.chw[2][0], t.chw[2][1], 64, 3, True, shp, out16=t.ch3)
-                    ops.conv_tc(t.ch3, t.chw[3][0], t.chw[3][1], 2, 3, False, shp, out32=t.d_cov)
-                    ccoords1 = ccoords1 + t.d_cov.view(B, H1, W1, 2).permute(0, 3, 1, 2)
+                    ops.conv_tc(t.ch3, t.chw[3][0], t.chw[3][1], 2, 3, False, shp, add_to_map=ccoords1)   # ccoords1 += delta (in the epilogue)
                     cov_done = torch.cuda.Event()
                     cov_done.record(side2)
-                ccoords1.record_stream(main)
                 ops.conv_tc(gru_tc.h_rows[0][0], t.fh1[0], t.fh1[1], 256, 3, True, shp, out16=t.fh)
-                ops.conv_tc(t.fh, t.fh2[0], t.fh2[1], 2, 3, False, shp, out32=t.d_flow)
-                coords1 = coords1 + t.d_flow.view(B, H1, W1, 2).permute(0, 3, 1, 2)
+                ops.conv_tc(t.fh, t.fh2[0], t.fh2[1], 2, 3, False, shp, add_to_map=coords1)               # coords1 += delta_flow
                 if self.taps is not None:
                     main.wait_event(cov_done)
                 net, cnet = as_map(net_d), as_map(cnet_d)

@@ -103,7 +103,7 @@ EXPORTS = {
     "macvo_tc_set_timeline": (None, [C.c_void_p, C.c_int]),
     "macvo_conv_tc_set_trace": (None, [C.c_void_p]),
     "macvo_conv_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 7
-                      + [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p] + [C.c_int] * 2 + [C.c_void_p]),
+                      + [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p] + [C.c_int] * 3 + [C.c_void_p]),
     "macvo_flow_im2col": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p]),
     "macvo_gru_tc_operand_rows": (C.c_size_t, [C.c_int] * 4),
     "macvo_gru_tc_set_trace": (None, [C.c_void_p]),
@@ -897,8 +897,9 @@ def pack_conv_filter(weight: Tensor, bias: Tensor | None, in_channels: int | Non
 
 def conv_tc(in_rows: Tensor, weights: Tensor, bias: Tensor | None, n_valid: int, ksize: int, relu: bool, shape: tuple[int, int, int],
             in_dense: bool = False, out16: Tensor | None = None, out16_offset: int = 0, out16_dense: bool = False,
-            out32: Tensor | None = None, out32_offset: int = 0) -> None:
-    """3x3 / 1x1 convolution on the tcgen05 path (csrc/conv_tc.cu): fp16 pixel rows in, fp16 rows and / or fp32 dense rows out"""
+            out32: Tensor | None = None, out32_offset: int = 0, add_to_map: Tensor | None = None) -> None:
+    """3x3 / 1x1 convolution on the tcgen05 path (csrc/conv_tc.cu): fp16 pixel rows in, fp16 rows and / or fp32 dense rows out;
+    `add_to_map` (B, n_valid, H, W) fp32 instead of out32: the result is added to that map in place"""
     B, H, W = shape
     for t, dt, what in ((in_rows, torch.float16, "in_rows"), (weights, torch.float16, "weights"), (out16, torch.float16, "out16"),
                         (out32, torch.float32, "out32"), (bias, torch.float32, "bias")):
@@ -910,14 +911,20 @@ def conv_tc(in_rows: Tensor, weights: Tensor, bias: Tensor | None, n_valid: int,
     need = B * H * W if in_dense else rows_count(B, H, W)
     if in_rows.shape[0] != need:
         raise MacvoB200Error(f"conv_tc: expected {need} input rows, got {in_rows.shape[0]}")
-    for t, dense, off in ((out16, out16_dense, out16_offset), (out32, True, out32_offset)):
+    planes = add_to_map is not None
+    if planes:
+        if out32 is not None or not (add_to_map.is_cuda and add_to_map.dtype == torch.float32 and add_to_map.is_contiguous()
+                                     and tuple(add_to_map.shape) == (B, n_valid, H, W)):
+            raise MacvoB200Error("conv_tc: add_to_map must be a contiguous fp32 (B, n_valid, H, W) CUDA tensor (and excludes out32)")
+        out32 = add_to_map
+    for t, dense, off in ((out16, out16_dense, out16_offset), (None if planes else out32, True, out32_offset)):
         if t is not None and (t.shape[0] != (B * H * W if dense else rows_count(B, H, W)) or off + n_valid > t.shape[1]):
             raise MacvoB200Error("conv_tc: output rows / channel range do not fit")
     rc = load_library().macvo_conv_tc(in_rows.data_ptr(), c_in, int(in_dense), weights.data_ptr(), None if bias is None else bias.data_ptr(),
                                       weights.shape[0], n_valid, ksize, int(relu), B, H, W,
                                       None if out16 is None else out16.data_ptr(), 0 if out16 is None else out16.shape[1], out16_offset,
                                       int(out16_dense), None if out32 is None else out32.data_ptr(),
-                                      0 if out32 is None else out32.shape[1], out32_offset, _stream())
+                                      0 if out32 is None else out32.shape[1], out32_offset, int(planes), _stream())
     _check(rc, "macvo_conv_tc")
     LAUNCHES[0] += 1
 

@@ -235,6 +235,11 @@ def test_conv_tc(ops, shape, cin, cout, k, relu):
     got16 = _from_rows_u(out16, shape)
     assert (got16[:, off:off + cout] - ref).abs().max().item() <= 2e-3 * scale
     assert not got16[:, :off].any() and not got16[:, off + cout:].any()
+    if cout == 2:   # the heads' form: the result is added in place to a (B, 2, H, W) coordinate map
+        cmap = torch.randn(B, 2, H, W, generator=g).to(DEV) * 30
+        want = cmap.double() + ref
+        ops.conv_tc(rows, wp, bp, n, k, relu, shape, add_to_map=cmap)
+        assert (cmap.double() - want).abs().max().item() <= 1e-3 * scale + 1e-5 * 30
     if k == 1:      # dense rows in, dense fp16 rows out (the value projection's shape)
         dense_in = x.permute(0, 2, 3, 1).reshape(P, cin).half().contiguous()
         o16 = torch.zeros(P, cout, dtype=torch.float16, device=DEV)
