@@ -273,7 +273,9 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
                    "l2": "per-frame working set (184 MB correlation volume + >1 GB activations) exceeds the 126 MB L2; "
                          "the corr roofline loop flushes L2 with a 256 MB write between launches",
                    "matmul_precision": "TF32 like the reference GPU frontend (Frontend.py:275-277): cuDNN / cuBLAS layers, our attention / "
-                                       "PatchEmbed kernels and the correlation volume (kind::tf32); token path, LayerNorm, lookup, "
+                                       "PatchEmbed kernels and the correlation volume (kind::tf32); the decoder's SepConvGRU units and 3x3 / 1x1 "
+                                       "convolutions on our tcgen05 kernels with fp16 operands (11-bit significand), fp32 accumulation "
+                                       "and fp32 recurrent state; token path, LayerNorm, lookup, "
                                        "post-processing, covariance fp32; LM fp64. Parity of this mode at this shape: "
                                        "tests/test_gpu_parity_ladder.py (flow 9e-4 of its scale vs float64 truth; strict-fp32 mode 2.5e-6)"},
         # e2e: pinned HOST images in, optimised pose + the frame's packed observations / mapping points out, through the

@@ -250,6 +250,7 @@ class FlowFormerCovNet:
         # TF32 mode only: SepConvGRU on the tcgen05 kernel (False / MACVO_B200_GRU_TC=0: cuDNN convolutions + glue kernels)
         self.gru_tensor_cores = os.environ.get("MACVO_B200_GRU_TC", "1") != "0"
         self.conv_tensor_cores = os.environ.get("MACVO_B200_CONV_TC", "1") != "0"      # same, the decoder's 3x3 / 1x1 convolutions
+        self.gru_split_units = os.environ.get("MACVO_B200_GRU_SPLIT", "1") != "0"      # one launch chain per GRU unit on two streams
         self._ops = None
         self._fused_conv_relu = True
         if corr_fn is None or lookup_fn is None or self.device.type == "cuda":
@@ -769,14 +770,17 @@ class FlowFormerCovNet:
                 agg = torch.bmm(attention_h, t.v16.view(B, N, 128), out_dtype=torch.float32)  # GMA aggregation (gma.py:84-130)
                 if cov_done is not None:            # the previous iteration's covariance head still reads the covariance unit's state rows
                     main.wait_event(cov_done)
-                gru_tc.step(t.mf32, agg.view(P, 128), gamma)
-                fork2 = torch.cuda.Event()
-                fork2.record(main)
+                # one launch chain per GRU unit on two streams (a joint launch is 168 CTAs = two waves per stage); the covariance
+                # unit's chain ends in `unit1_done`, which only the covariance head waits for
+                unit1_done = gru_tc.step(t.mf32, agg.view(P, 128), gamma, split_units=self.gru_split_units, join=False)
+                if unit1_done is None:
+                    unit1_done = torch.cuda.Event()
+                    unit1_done.record(main)
                 # The covariance head (4 chained convolutions, covhead.py:20-58) feeds only the covariance coordinates: it runs on
                 # its own stream and is joined right before the NEXT iteration's GRU update, so it overlaps the next lookup / token
                 # kernel / motion encoder instead of extending this iteration (they depend on the flow head only).
                 with torch.cuda.stream(side2):
-                    side2.wait_event(fork2)
+                    side2.wait_event(unit1_done)
                     ops.conv_tc(gru_tc.h_rows[0][1], t.chw[0][0], t.chw[0][1], 256, 3, True, shp, out16=t.ch1)
                     ops.conv_tc(t.ch1, t.chw[1][0], t.chw[1][1], 128, 3, False, shp, out16=t.ch2)
                     ops.conv_tc(t.ch2, t.chw[2][0], t.chw[2][1], 64, 3, True, shp, out16=t.ch3)

@@ -985,6 +985,12 @@ class SepConvGruTC:
                                 ptrs([self.w[u, o, st] for u in range(self.units)]), ptrs([self.b[u, o, st] for u in range(self.units)]),
                                 ptrs(self.h), ptrs(self.z), ptrs(self.rh_rows[o] if st == 0 else self.h_rows[1 - o]))
                       for o in (0, 1) for st in (0, 1)}
+        one = lambda t: (C.c_void_p * 2)(t.data_ptr(), None)
+        self._unit_args = {(u, o, st): (one((self.h_rows[o] if st == 0 else self.rh_rows[o])[u]), self.x[o].data_ptr(),
+                                        one(self.w[u, o, st]), one(self.b[u, o, st]), one(self.h[u]), one(self.z[u]),
+                                        one((self.rh_rows[o] if st == 0 else self.h_rows[1 - o])[u]))
+                           for u in range(self.units) for o in (0, 1) for st in (0, 1)}
+        self._side = torch.cuda.Stream(device) if self.units == 2 else None
 
     def _pack(self, src: Tensor, dst: Tensor, offset: int, vertical: int) -> None:
         B, H, W = self.shape
@@ -1004,8 +1010,12 @@ class SepConvGruTC:
         self.h[unit].copy_(_dense(h_rows, GRU_HID, "SepConvGruTC state").view(-1, GRU_HID))
         self._pack(self.h[unit], self.h_rows[0][unit], 0, 0)
 
-    def step(self, mf: Tensor, agg: Tensor, gamma: Tensor) -> None:
-        """one SepConvGRU update of every unit with x = [inp | mf | mf + gamma * agg]; new state in `self.h[u]`"""
+    def step(self, mf: Tensor, agg: Tensor, gamma: Tensor, split_units: bool = False, join: bool = True):
+        """one SepConvGRU update of every unit with x = [inp | mf | mf + gamma * agg]; new state in `self.h[u]`.
+        split_units: one 4-launch chain per unit on two streams instead of 4 launches covering both units — with 84 CTA tiles per
+        unit (640x480: two 60x80 maps) a joint launch is 168 CTAs = two waves on 148 SMs per stage, two independent chains of
+        84-CTA launches keep the SMs filled across the stage boundaries. With join=False the current stream only carries
+        unit 0's chain and the returned event marks the end of unit 1's (the caller orders unit 1's consumers after it)."""
         B, H, W = self.shape
         lib = load_library()
         mf, agg = _dense(mf, GRU_HID, "SepConvGruTC mf"), _dense(agg, GRU_HID, "SepConvGruTC agg")
@@ -1014,12 +1024,34 @@ class SepConvGruTC:
         st = _stream()
         _check(lib.macvo_gru_tc_pack_motion(mf.data_ptr(), agg.data_ptr(), _dev(gamma, torch.float32, "gamma").data_ptr(),
                                             self.x[0].data_ptr(), self.x[1].data_ptr(), B, H, W, st), "macvo_gru_tc_pack_motion")
+        if split_units and self.units == 2:
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for u, stream in ((1, self._side), (0, main)):
+                with torch.cuda.stream(stream):
+                    if u == 1:
+                        stream.wait_event(fork)
+                    for o in (0, 1):
+                        for stage in (0, 1):
+                            a = self._unit_args[u, o, stage]
+                            _check(lib.macvo_gru_tc_stage(stage, o, B, H, W, 1, a[0], a[1], a[2], a[3], a[4], a[5], a[6],
+                                                          stream.cuda_stream), "macvo_gru_tc_stage")
+                    if u == 1:
+                        join_ev = torch.cuda.Event()
+                        join_ev.record(stream)
+            LAUNCHES[0] += 9
+            if not join:
+                return join_ev
+            main.wait_event(join_ev)
+            return None
         for o in (0, 1):
             for stage in (0, 1):
                 a = self._args[o, stage]
                 _check(lib.macvo_gru_tc_stage(stage, o, B, H, W, self.units, a[0], a[1], a[2], a[3], a[4], a[5], a[6], st),
                        "macvo_gru_tc_stage")
         LAUNCHES[0] += 5
+        return None
 
 
 def query_prep(query: Tensor, ln_weight: Tensor, ln_bias: Tensor, coords: Tensor, freq: Tensor, eps: float = 1e-5) -> Tensor:

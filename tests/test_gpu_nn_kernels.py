@@ -166,7 +166,7 @@ def test_sepconv_gru_tensor_cores(ops, shape):
     ref_r, ref_t = [to_map(h) for h in h0], [to_map(h) for h in h0]
     for it in range(2):
         mf, agg = rnd(P, 128).relu(), rnd(P, 128)
-        gru.step(mf, agg, gamma)
+        gru.step(mf, agg, gamma, split_units=(it == 1))         # second step: one launch chain per unit on two streams
         xs = torch.cat([inp, mf, mf + gamma * agg], 1)
         for u in range(2):
             # the fp16 rounding of x happens on the fp32 values the pack kernel forms

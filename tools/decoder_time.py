@@ -25,7 +25,8 @@ with torch.inference_mode():
     ref = None
     modes = sys.argv[1].split(",") if len(sys.argv) > 1 else ("conv_tc+gru_tc", "gru_tc", "cudnn")
     for mode in modes:
-        net.gru_tensor_cores, net.conv_tensor_cores = mode != "cudnn", mode == "conv_tc+gru_tc"
+        net.gru_tensor_cores, net.conv_tensor_cores = mode != "cudnn", mode.startswith("conv_tc+gru_tc")
+        net.gru_split_units = mode.endswith("+split")
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
             for _ in range(2):
