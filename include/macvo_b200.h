@@ -373,6 +373,15 @@ int macvo_gru_tc_pack(const float* src, int src_pitch, int channels, void* dst, 
 /* per iteration: x channels [128, 384) = [mf | mf + gamma * agg] of both layouts (gma.py:84-130) */
 int macvo_gru_tc_pack_motion(const float* mf, const float* agg, const float* gamma, void* x_rows_h, void* x_rows_v, int batch,
                              int height, int width, void* stream);
+/* GMA attention matrix (gma.py:39-82): out (rows, cols) fp16 = softmax over each row of the fp32 scores; cols % 4 == 0, <= 8192.
+ * Replaces softmax (fp32 read + write) + cast to fp16: the row is read once. Used when TF32 matmuls are allowed (the matrix is
+ * then kept in fp16 for the per-iteration aggregation GEMM). */
+int macvo_softmax_rows_f16(const float* scores, void* out, long long rows, int cols, void* stream);
+/* convex 8x upsampling (core/decoder.py:131-139): flow (batch, 2, H, W) fp32 planes, mask_nhwc (batch, H, W, 576) fp32 logits
+ * (channel k*64 + i*8 + j; a channels_last convolution output), out (batch, 2, 8H, 8W):
+ * out[n, c, 8y+i, 8x+j] = sum_k softmax_k(scale * mask[.., k*64 + i*8 + j]) * 8 * flow[n, c, y + k/3 - 1, x + k%3 - 1] (zero outside) */
+int macvo_convex_upsample(const float* flow, const float* mask_nhwc, float* out, float scale, int batch, int height, int width,
+                          void* stream);
 /* out (pixels,64) = LayerNorm_64(query) + LinearPositionEmbeddingSine(coords)  (decoder.py:56-66, attention.py:71-101);
  * coords (batch, 2, n1) [x, y]; freq: the 16 fp32 frequencies k*pi/200. */
 int macvo_query_prep(const float* query, const float* ln_weight, const float* ln_bias, const float* coords,

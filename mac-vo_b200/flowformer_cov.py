@@ -696,7 +696,10 @@ class FlowFormerCovNet:
         # GMA attention, once per frame (gma.py:39-82): softmax over the N x N similarity
         qk = self._conv(inp, m + "att.to_qk")
         qv = (qk[:, :128] * (128 ** -0.5)).flatten(2).transpose(1, 2)            # (B, N, 128)
-        attention = torch.matmul(qv, qk[:, 128:].flatten(2)).softmax(dim=-1)     # (B, N, N)
+        scores = torch.matmul(qv, qk[:, 128:].flatten(2))                        # (B, N, N)
+        fuse_att = (self._native(ctx) and dd == torch.float32 and torch.backends.cuda.matmul.allow_tf32
+                    and scores.shape[-1] % 4 == 0 and scores.shape[-1] <= 8192)
+        attention = None if fuse_att else scores.softmax(dim=-1)
         ca = m + "decoder_layer.cross_attend."
         key = self._lin(cost_memory, ca + "k")
         value = self._lin(cost_memory, ca + "v")
@@ -735,7 +738,10 @@ class FlowFormerCovNet:
             net_d, cnet_d = torch.empty(P, 128, dtype=dd, device=ctx.device), torch.empty(P, 128, dtype=dd, device=ctx.device)
         # the N x N GMA attention matrix (184 MB at 640x480) is re-read by every iteration's aggregation GEMM, which is
         # bound by that read: when TF32 matmuls are allowed it is kept in fp16 (values in [0, 1]; no precision below TF32's)
-        attention_h = attention.to(torch.float16) if native and torch.backends.cuda.matmul.allow_tf32 else None
+        if fuse_att:
+            attention_h = self._ops.softmax_rows_f16(scores)       # softmax + fp16 in one pass over the scores
+        else:
+            attention_h = attention.to(torch.float16) if native and torch.backends.cuda.matmul.allow_tf32 else None
         fast_tokens = native and QUERY_DIM == 64 and self.lookup_fn is self._ops.corr_lookup
         if fast_tokens:
             token_blob = self._memo(("token_blob", ctx.device), lambda: self._ops.decoder_token_blob(self.W, m))
@@ -887,6 +893,11 @@ class FlowFormerCovNet:
             torch.cuda.current_stream().wait_event(cov_done)
         # the reference evaluates both mask heads + upsampling every iteration but (eval mode) returns
         # only the last one (covhead.py:137-140) -> evaluate once
+        if native:      # scale + softmax + unfold + weighted sum + pixel shuffle in one kernel per map
+            up_logits = self._conv(self._conv_relu(net, ub + "mask.0", padding=1), ub + "mask.2")
+            cov_logits = self._conv(self._conv_relu(cnet, cu + "mask.0", padding=1), cu + "mask.2")
+            return (self._ops.convex_upsample(coords1 - coords0, up_logits, 0.25),
+                    self._ops.convex_upsample(ccoords1 - coords0, cov_logits, 0.25))
         up_mask = _f32(0.25 * self._conv(F.relu(self._conv(net, ub + "mask.0", padding=1)), ub + "mask.2"))
         cov_mask = _f32(0.25 * self._conv(F.relu(self._conv(cnet, cu + "mask.0", padding=1)), cu + "mask.2"))
         return self.convex_upsample(coords1 - coords0, up_mask), self.convex_upsample(ccoords1 - coords0, cov_mask)

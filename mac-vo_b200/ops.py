@@ -99,6 +99,8 @@ EXPORTS = {
     "macvo_gru_input": (C.c_int, [C.c_void_p] * 7 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_gates": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
     "macvo_gru_blend": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]),
+    "macvo_softmax_rows_f16": (C.c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_int, C.c_void_p]),
+    "macvo_convex_upsample": (C.c_int, [C.c_void_p] * 3 + [C.c_float] + [C.c_int] * 3 + [C.c_void_p]),
     "macvo_rows_count": (C.c_size_t, [C.c_int] * 4),
     "macvo_tc_set_timeline": (None, [C.c_void_p, C.c_int]),
     "macvo_conv_tc_set_trace": (None, [C.c_void_p]),
@@ -1052,6 +1054,34 @@ class SepConvGruTC:
                        "macvo_gru_tc_stage")
         LAUNCHES[0] += 5
         return None
+
+
+def convex_upsample(flow: Tensor, mask_logits: Tensor, scale: float = 1.0) -> Tensor:
+    """`upsample_flow` (core/decoder.py:131-139) in one kernel: flow (B,2,H,W), mask_logits (B,576,H,W) -> (B,2,8H,8W); the
+    softmax runs over scale * mask_logits"""
+    f = _dev(flow, torch.float32, "convex_upsample flow")
+    B, c, H, W = f.shape
+    if c != 2 or tuple(mask_logits.shape) != (B, 576, H, W) or not mask_logits.is_cuda or mask_logits.dtype != torch.float32:
+        raise MacvoB200Error("convex_upsample: expects flow (B,2,H,W) and fp32 CUDA mask logits (B,576,H,W)")
+    m = mask_logits.permute(0, 2, 3, 1)
+    if not m.is_contiguous():
+        m = m.contiguous()
+    out = torch.empty((B, 2, 8 * H, 8 * W), dtype=torch.float32, device=f.device)
+    rc = load_library().macvo_convex_upsample(f.data_ptr(), m.data_ptr(), out.data_ptr(), float(scale), B, H, W, _stream())
+    _check(rc, "macvo_convex_upsample")
+    LAUNCHES[0] += 1
+    return out
+
+
+def softmax_rows_f16(scores: Tensor) -> Tensor:
+    """softmax over the last dimension of fp32 scores, written as fp16 (the GMA attention matrix under TF32; gma.py:39-82)"""
+    x = _dev(scores, torch.float32, "softmax_rows_f16 scores")
+    cols = x.shape[-1]
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    rc = load_library().macvo_softmax_rows_f16(x.data_ptr(), out.data_ptr(), x.numel() // cols, cols, _stream())
+    _check(rc, "macvo_softmax_rows_f16")
+    LAUNCHES[0] += 1
+    return out
 
 
 def query_prep(query: Tensor, ln_weight: Tensor, ln_bias: Tensor, coords: Tensor, freq: Tensor, eps: float = 1e-5) -> Tensor:

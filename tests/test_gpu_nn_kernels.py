@@ -188,6 +188,35 @@ def test_sepconv_gru_tensor_cores(ops, shape):
         assert not body[:, :2].any() and not body[:, -2:].any() and not buf[:2].any() and not buf[2 + n:].any()
 
 
+@pytest.mark.parametrize("rows,cols", [(3, 4), (17, 4800), (9, 8192), (5, 1236)])
+def test_softmax_rows_f16(ops, rows, cols):
+    """fused row softmax -> fp16 (the GMA attention matrix, gma.py:39-82) vs float64 softmax: half an fp16 ulp of the result + 1e-7"""
+    g = torch.Generator().manual_seed(rows * cols)
+    x = (torch.randn(2, rows, cols, generator=g) * 6).to(DEV)
+    x[0, 0, : min(cols, 7)] = 40.0                                  # a dominant block: exp of the rest underflows gracefully
+    got = ops.softmax_rows_f16(x)
+    ref = torch.softmax(x.double(), dim=-1)
+    assert got.dtype == torch.float16 and got.shape == x.shape
+    assert ((got.double() - ref).abs() <= ref * 2.0 ** -10 + 1e-7).all()
+    assert (got.double().sum(-1) - 1).abs().max().item() <= 2e-3
+    with pytest.raises(ops.MacvoB200Error):
+        ops.softmax_rows_f16(x.cpu())
+
+
+@pytest.mark.parametrize("b,h,w", [(1, 5, 7), (2, 60, 80), (1, 13, 17)])
+def test_convex_upsample(ops, b, h, w):
+    """csrc/decoder_fused.cu convex_upsample_kernel vs `upsample_flow` (core/decoder.py:131-139) in float64"""
+    from macvo_b200.flowformer_cov import FlowFormerCovNet
+    g = torch.Generator().manual_seed(h * w)
+    flow = (torch.randn(b, 2, h, w, generator=g) * 10).to(DEV)
+    logits = (torch.randn(b, 576, h, w, generator=g) * 8).to(DEV).contiguous(memory_format=torch.channels_last)
+    ref = FlowFormerCovNet.convex_upsample(flow.double(), 0.25 * logits.double())
+    for m in (logits, logits.contiguous()):                     # channels_last (a conv output) and NCHW (copied once) inputs
+        got = ops.convex_upsample(flow, m, 0.25)
+        assert got.shape == (b, 2, 8 * h, 8 * w)
+        assert (got.double() - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
+
+
 def _to_rows_u(ops, x_map, shape):
     """(B, C, H, W) fp32 map -> zero-initialised layout-U fp16 rows via the pack kernel"""
     B, H, W = shape
