@@ -217,16 +217,21 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
         period = 2 * SEQ_LEN - 2                                          # ping-pong 0,1,..,7,6,..,1,0,1,...
         pp = lambda i: (i % period) if (i % period) < SEQ_LEN else period - (i % period)
         seq = [frames[pp(i)] for i in range(1, warmup + steps + 1)]
-        for f in seq[:warmup]:
-            odo.run_pair(f)
+        # fused driver: the next frame is announced so its frontend is launched ahead of this frame's tail (software pipelining
+        # across frames: pipeline.FusedTwoFrameOdometry.run_pair); every frame of the timed region is still uploaded, run through
+        # the whole path and finished inside it (odo.finish() drains the last tail)
+        step = (lambda i: odo.run_pair(seq[i], next_frame=seq[i + 1] if i + 1 < len(seq) else None)) if fused \
+            else (lambda i: odo.run_pair(seq[i]))
+        for i in range(warmup):
+            step(i)
         barrier()
         ops.LAUNCHES[0] = 0
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         torch.cuda.nvtx.range_push("macvo_timed")     # lets `ncu --nvtx --nvtx-include macvo_timed/` list exactly these launches
         last = None
-        for f in seq[warmup:]:
-            odo.run_pair(f)
+        for i in range(warmup, len(seq)):
+            step(i)
             if read_pose and fused:
                 last = odo.latest_pose()                                  # D2H of the step's result (waits for this frame)
             elif read_pose and odo.optimizer.get_result() is not None:

@@ -396,15 +396,21 @@ def sample_candidates(cand: CandidateList, num_point: int) -> Tensor:
     return sample_candidates_many([(cand, num_point)])[0]
 
 
-def sample_candidates_many(requests: list[tuple[CandidateList, int]]) -> list[Tensor]:
-    """Sampling for several candidate lists behind ONE host synchronisation: the counts of all lists are fetched
-    together, then `torch.randperm(n)[:numPoint]` is drawn per list IN THE GIVEN ORDER from the CPU default generator
-    (the order MAC-VO consumes it: keypoints, then mapping points — Odometry/MACVO.py:197,315)."""
-    lib = load_library()
+def request_candidate_counts(requests: list[tuple[CandidateList, int]]) -> torch.cuda.Event:
+    """enqueue the device->host copies of every list's count / status; the returned event fires when they have landed"""
     for cand, _ in requests:
         cand.host[0:1].copy_(cand.n, non_blocking=True)
         cand.host[1:2].copy_(cand.status, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    ev = torch.cuda.Event()
+    ev.record()
+    return ev
+
+
+def sample_from_counts(requests: list[tuple[CandidateList, int]]) -> list[Tensor]:
+    """after the event of `request_candidate_counts` fired: `torch.randperm(n)[:numPoint]` per list IN THE GIVEN ORDER from the
+    CPU default generator (the order MAC-VO consumes it: keypoints, then mapping points — Odometry/MACVO.py:197,315) and the
+    gathers of the drawn candidates on the current stream"""
+    lib = load_library()
     outs = []
     for cand, num_point in requests:
         dev = cand.idx.device
@@ -422,6 +428,13 @@ def sample_candidates_many(requests: list[tuple[CandidateList, int]]) -> list[Te
             LAUNCHES[0] += 1
         outs.append(out)
     return outs
+
+
+def sample_candidates_many(requests: list[tuple[CandidateList, int]]) -> list[Tensor]:
+    """Sampling for several candidate lists behind ONE host synchronisation: the counts of all lists are fetched
+    together, then drawn per list in the given order (see `sample_from_counts`)."""
+    request_candidate_counts(requests).synchronize()
+    return sample_from_counts(requests)
 
 
 # ------------------------------------------------------------------------------------------------

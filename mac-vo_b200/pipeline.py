@@ -188,6 +188,9 @@ class FusedTwoFrameOdometry:
         self.frame_no = 0
         self.prev = None
         self.last: FrameResult | None = None
+        self._prefetched = None         # (frame, depth, match) of a frontend launched ahead by run_pair(..., next_frame=)
+        self._tail_stream = None
+        self._tail_done = None
 
     def initialize(self, frame0) -> None:
         depth0 = self.frontend.estimate_depth(frame0)
@@ -200,16 +203,49 @@ class FusedTwoFrameOdometry:
         return float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
 
     @torch.inference_mode()
-    def run_pair(self, frame1) -> FrameResult:
+    def run_pair(self, frame1, next_frame=None) -> FrameResult:
+        """One frame. With `next_frame` (the frame the NEXT call will pass) the frames are software-pipelined: its frontend —
+        which depends on images only, not on this frame's pose — is enqueued before the host waits for this frame's candidate
+        counts, and this frame's tail (sampling gathers, observation building, LM, mapping covariances, result copies) runs on
+        a second stream next to it, so neither the tail nor the host round trip of the one synchronisation leaves the GPU idle.
+        Results are identical (same kernels, same `randperm` order)."""
         ops = self.ops
         frame0, depth0 = self.prev
         slot = self.frame_no & 1
-        depth1, match01 = self.frontend.estimate_pair(frame0, frame1)
+        if self._prefetched is not None and self._prefetched[0] is frame1:
+            depth1, match01 = self._prefetched[1:]
+        else:
+            depth1, match01 = self.frontend.estimate_pair(frame0, frame1)
+        self._prefetched = None
+        main = torch.cuda.current_stream()
+        if self._tail_done is not None:            # the previous frame's tail read the candidate lists the selectors now overwrite
+            main.wait_event(self._tail_done)
         # selection kernels for keypoints AND mapping points first, then a single synchronisation for both counts
         reqs = [(self.kp_selector.enqueue_candidates(match01), self.num_point)]
         if self.mapping:
             reqs.append((self.map_selector.enqueue_candidates(depth0), self.num_map_point))
-        picks = ops.sample_candidates_many(reqs)
+        counts = ops.request_candidate_counts(reqs)
+        if next_frame is None:
+            counts.synchronize()
+            return self._tail(frame0, frame1, depth0, depth1, match01, reqs, slot)
+        self._prefetched = (next_frame, *self.frontend.estimate_pair(frame1, next_frame))
+        counts.synchronize()
+        if self._tail_stream is None:
+            self._tail_stream = torch.cuda.Stream(self.device)
+        tail = self._tail_stream
+        tail.wait_event(counts)
+        for t in (match01.flow, match01.cov, depth0.depth, depth1.depth, depth1.disparity, depth1.disparity_uncertainty):
+            t.record_stream(tail)              # allocated on the main stream, consumed on the tail stream
+        with torch.cuda.stream(tail):
+            res = self._tail(frame0, frame1, depth0, depth1, match01, reqs, slot)
+            self._tail_done = torch.cuda.Event()
+            self._tail_done.record(tail)
+        return res
+
+    def _tail(self, frame0, frame1, depth0, depth1, match01, reqs, slot) -> FrameResult:
+        """everything after the candidate counts reached the host, on the current stream"""
+        ops = self.ops
+        picks = ops.sample_from_counts(reqs)
         kp0_uv = picks[0]
         obs, stats = self.obs[slot], self.stats[slot]
         next_pose = torch.empty((7,), dtype=torch.float64, device=self.device)
@@ -276,5 +312,7 @@ class FusedTwoFrameOdometry:
 
     def finish(self) -> torch.Tensor:
         """All poses (F, 7) float32 like `TwoFrameOdometry.finish` (the map stores fp32 poses)."""
+        if self._tail_done is not None:
+            self._tail_done.synchronize()
         torch.cuda.current_stream().synchronize()
         return torch.stack([p.cpu().float() for p in self.pose_dev])

@@ -261,11 +261,50 @@ def test_fused_tail_equals_plugin_api_path(plugins):
     np.testing.assert_allclose(pb.numpy(), pa.numpy(), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_software_pipelined_frames_equal_sequential(plugins, graph):
+    """`run_pair(frame, next_frame=...)` (next frontend launched ahead, this frame's tail on a second stream) returns exactly what
+    the sequential driver returns: keypoints, observation buffers and poses bit-identical over 7 frames, eager and CUDA-graph
+    frontend (the graph's static buffers are overwritten by the prefetched frame while the tail still runs)."""
+    from macvo_b200 import synthetic
+    from macvo_b200.pipeline import FusedTwoFrameOdometry
+    P = plugins
+    frames = synthetic.make_sequence(8, 192, 256, pin=True)
+
+    def build():
+        return FusedTwoFrameOdometry(
+            _frontend(P, graph, 4),
+            P.B200_CovAwareSelector_NoDepth(NS(device=DEV, kernel_size=7, mask_width=32, max_match_cov=100.0)),
+            P.B200_MatchCovariance(NS(device=DEV, kernel_size=31, match_cov_default=0.25, min_depth_cov=0.05, min_flow_cov=0.25)),
+            P.B200_TwoFrame_PGO(NS(graph_type="disp", device=DEV, vectorize=True, parallel=False, autodiff=False)),
+            num_point=64, map_selector=P.B200_MappingPointSelector(NS(max_depth=5.0, max_depth_cov=0.005, mask_width=32)))
+
+    runs = []
+    for pipelined in (False, True):
+        odo = build()
+        torch.manual_seed(5)
+        odo.initialize(frames[0])
+        obs = []
+        for i in range(1, len(frames)):
+            nxt = frames[i + 1] if pipelined and i + 1 < len(frames) and i != 4 else None      # one sequential frame in between
+            odo.run_pair(frames[i], next_frame=nxt)
+            obs.append(odo.observations())
+        runs.append((obs, odo.finish()))
+    _strict_fp32()
+    (oa, pa), (ob, pb) = runs
+    assert torch.equal(pa, pb)
+    for x, y in zip(oa, ob):
+        assert x["num_obs"] == y["num_obs"] and x["num_kp"] == y["num_kp"]
+        for k in ("pixel1_uv", "pixel2_uv", "pos_Tw", "obs1_covTc", "obs2_covTc", "map_cov", "map_pos_Tc"):
+            assert torch.equal(x[k], y[k]), k
+
+
 def test_match_covariance_accepts_macvo_transposed_view(plugins):
     """Odometry/MACVO.py:231-243 passes `retrieve_pixels(kp0_uv, match01.cov).T` — a NON-contiguous (K,3) view — and
     relies on the in-place clamp reaching that storage (it later becomes pixel2_uv_cov)."""
     from oracle import covariance as ocov
     P = plugins
+    _strict_fp32()     # a frontend built by an earlier test leaves float32 matmul precision "medium", which also lowers the CPU oracle's
     H, W, K = 160, 224, 96
     kp, depth, flow_cov = cases.cov_inputs(H, W, K, "float_cov")
     frame = NS(fx=320.0, fy=320.0, cx=112.0, cy=80.0)
