@@ -617,12 +617,30 @@ class FlowFormerCovNet:
             x = x.view(B, LATENT_TOKENS, N, -1).permute(0, 2, 1, 3).reshape(B * N, LATENT_TOKENS, -1)
         return x + short_cut, cost_maps
 
-    def memory_encoder(self, img1: Tensor, img2: Tensor, context: Tensor) -> tuple[Tensor, Tensor]:
-        feats = self.svt(torch.cat([img1, img2], dim=0), "memory_encoder.feat_encoder")
-        feats = self._conv(feats, "memory_encoder.channel_convertor")
-        B = feats.shape[0] // 2
+    def memory_encoder(self, img1: Tensor, img2: Tensor, context: Tensor, shared: tuple[int, int] | None = None) -> tuple[Tensor, Tensor]:
+        """shared = (i, j): image2[j] IS image1[i] (the frontend batches [t2.L, t1.L] against [t2.R, t2.L], Frontend.py:284-285,
+        so t2.L would be encoded twice in the same call): that image goes through the feature encoder once."""
+        B = img1.shape[0]
+        if shared is None:
+            feats = self.svt(torch.cat([img1, img2], dim=0), "memory_encoder.feat_encoder")
+            feats = self._conv(feats, "memory_encoder.channel_convertor")
+            f1, f2 = feats[:B], feats[B:]
+        else:
+            i, j = shared
+            if not (0 <= i < B and 0 <= j < B):
+                raise ValueError(f"shared={shared}: image indices must lie in [0, {B})")
+            keep = [k for k in range(B) if k != j]
+            feats = self.svt(torch.cat([img1] + [img2[k:k + 1] for k in keep], dim=0), "memory_encoder.feat_encoder")
+            feats = self._conv(feats, "memory_encoder.channel_convertor")
+            f1 = feats[:B]
+            f2 = torch.empty_like(f1)                                       # same (channels_last) layout as f1
+            for pos, k in enumerate(keep):
+                f2[k:k + 1].copy_(feats[B + pos:B + pos + 1])
+            f2[j:j + 1].copy_(feats[i:i + 1])
+            if self.taps is not None:
+                feats = torch.cat([f1, f2], dim=0)
         self._tap("feats", feats)
-        cost_volume = self.corr_fn(feats[:B], feats[B:]).to(feats.dtype)   # encoder.py:289-290
+        cost_volume = self.corr_fn(f1, f2).to(feats.dtype)                 # encoder.py:289-290
         self._tap("corr_rows", cost_volume.reshape(B, -1, cost_volume.shape[-2] * cost_volume.shape[-1])[:, ::97])
         out = self.cost_perceiver(cost_volume, context)
         self._tap("cost_memory", out[0])
@@ -904,7 +922,7 @@ class FlowFormerCovNet:
 
     # ---- top level (flownet.py:18-44) -----------------------------------------------------------
     @torch.inference_mode()
-    def forward(self, image1: Tensor, image2: Tensor) -> tuple[Tensor, Tensor]:
+    def forward(self, image1: Tensor, image2: Tensor, shared: tuple[int, int] | None = None) -> tuple[Tensor, Tensor]:
         image1 = ((2 * image1) - 1.0).to(self.enc_dtype)
         image2 = ((2 * image2) - 1.0).to(self.enc_dtype)
         self._ctx_join = None
@@ -927,7 +945,7 @@ class FlowFormerCovNet:
         if self.taps is not None:
             self._join_context()
             self._tap("context", context)
-        cost_memory, cost_maps = self.memory_encoder(image1, image2, context)
+        cost_memory, cost_maps = self.memory_encoder(image1, image2, context, shared)
         self._join_context()
         return self.memory_decoder(cost_memory, _f32(context), _f32(cost_maps))
 
@@ -937,14 +955,15 @@ class FlowFormerCovNet:
             self._ctx_join = None
 
     @torch.inference_mode()
-    def inference(self, image1: Tensor, image2: Tensor) -> tuple[Tensor, Tensor]:
-        """(B,3,H,W) x2 in [0,1] -> flow (B,2,H,W), cov = exp(2 log sigma) (B,2,H,W)."""
+    def inference(self, image1: Tensor, image2: Tensor, shared: tuple[int, int] | None = None) -> tuple[Tensor, Tensor]:
+        """(B,3,H,W) x2 in [0,1] -> flow (B,2,H,W), cov = exp(2 log sigma) (B,2,H,W); shared = (i, j) promises that image2[j] is
+        image1[i] (it is then encoded once, see `memory_encoder`)."""
         H, W = image1.shape[-2:]
         ph, pw = (-H) % 8, (-W) % 8
         pad = [pw // 2, pw - pw // 2, ph // 2, ph - ph // 2]       # InputPadder 'sintel' (core/utils.py:4-24)
         if ph or pw:
             image1, image2 = F.pad(image1, pad, mode="replicate"), F.pad(image2, pad, mode="replicate")
-        flow, logsig = self.forward(image1, image2)
+        flow, logsig = self.forward(image1, image2, shared)
         if ph or pw:
             flow = flow[..., pad[2]:flow.shape[-2] - pad[3], pad[0]:flow.shape[-1] - pad[1]]
             logsig = logsig[..., pad[2]:logsig.shape[-2] - pad[3], pad[0]:logsig.shape[-1] - pad[1]]

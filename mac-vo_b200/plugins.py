@@ -98,6 +98,7 @@ class B200_FlowFormerCovFrontend(IFrontend):
         self._graph = None
         self._static: dict = {}
         self._score: ops.ScoreBuffers | None = None
+        self.dedup_shared_image = os.environ.get("MACVO_B200_DEDUP", "1") != "0"
 
     @property
     def provide_cov(self) -> tuple[bool, bool]:
@@ -111,7 +112,8 @@ class B200_FlowFormerCovFrontend(IFrontend):
         return ops.dense_postproc(est_flow, est_cov, bl_fx, self.config.enforce_positive_disparity, score=self._score)
 
     def _run(self, input_A, input_B, bl_fx: float):
-        est_flow, est_cov = self.net.inference(input_A, input_B)
+        # input_A = [t2.L, t1.L], input_B = [t2.R, t2.L]: B[1] is A[0], which the feature encoder then sees once
+        est_flow, est_cov = self.net.inference(input_A, input_B, shared=(0, 1) if self.dedup_shared_image else None)
         return self._postprocess(est_flow.float(), est_cov.float(), bl_fx)
 
     def _outputs(self, d: dict, clone: bool):

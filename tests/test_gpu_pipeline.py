@@ -261,6 +261,24 @@ def test_fused_tail_equals_plugin_api_path(plugins):
     np.testing.assert_allclose(pb.numpy(), pa.numpy(), rtol=1e-5, atol=1e-6)
 
 
+def test_shared_image_is_encoded_once(plugins):
+    """The frontend batches [t2.L, t1.L] against [t2.R, t2.L] (Frontend.py:284-285): t2.L appears on both sides, so the feature
+    encoder sees 3 images instead of 4 (`shared=(0, 1)`). Same result as encoding it twice (batch-size dependent library kernel
+    selection only: 1e-5 of the flow scale, 1e-4 relative on the covariance, strict fp32)."""
+    from macvo_b200 import synthetic
+    fe = _frontend(plugins, False, 4)
+    _strict_fp32()
+    fr = synthetic.make_sequence(3, 192, 256)
+    A = torch.cat([fr[2].imageL, fr[1].imageL]).to(DEV)
+    B = torch.cat([fr[2].imageR, fr[2].imageL]).to(DEV)
+    f0, c0 = fe.net.inference(A, B)
+    f1, c1 = fe.net.inference(A, B, shared=(0, 1))
+    assert (f1 - f0).abs().max().item() <= 1e-5 * max(1.0, f0.abs().max().item())
+    assert ((c1 - c0).abs() / c0.abs().clamp_min(1e-6)).max().item() <= 1e-4
+    with pytest.raises(ValueError):
+        fe.net.inference(A, B, shared=(0, 5))
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_software_pipelined_frames_equal_sequential(plugins, graph):
     """`run_pair(frame, next_frame=...)` (next frontend launched ahead, this frame's tail on a second stream) returns exactly what
