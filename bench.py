@@ -220,7 +220,9 @@ def run_gpu(cfg: dict, steps: int, warmup: int, n_gpus: int) -> dict:
         # fused driver: the next frame is announced so its frontend is launched ahead of this frame's tail (software pipelining
         # across frames: pipeline.FusedTwoFrameOdometry.run_pair); every frame of the timed region is still uploaded, run through
         # the whole path and finished inside it (odo.finish() drains the last tail)
-        step = (lambda i: odo.run_pair(seq[i], next_frame=seq[i + 1] if i + 1 < len(seq) else None)) if fused \
+        # (the last warm-up step announces nothing: the first timed frame's frontend must be launched INSIDE the timed region, so
+        # that the region holds exactly `steps` frontends and `steps` tails)
+        step = (lambda i: odo.run_pair(seq[i], next_frame=seq[i + 1] if i + 1 < len(seq) and i != warmup - 1 else None)) if fused \
             else (lambda i: odo.run_pair(seq[i]))
         for i in range(warmup):
             step(i)
