@@ -88,3 +88,17 @@ def install() -> None:
         pose = opgo.lm_solve(g)
         return torch.tensor(np.asarray(pose)), torch.zeros(8, dtype=torch.float64)
     ops.pgo_solve = pgo_solve
+
+    def pgo_solve_graph(graph_type, pos_Tw, intr, init_pose, kp2_uv=None, kp2_disp=None, uv_cov=None, disp_cov=None, pc_obs=None,
+                        obs_cov=None, pts_cov=None, cluster=0, **kw):
+        n = lambda t: None if t is None else t.double().cpu().numpy()
+        K = pos_Tw.shape[0]
+        z = np.zeros
+        g = opgo.GraphData(pos_Tw=n(pos_Tw), kp2_uv=n(kp2_uv) if kp2_uv is not None else z((K, 2)),
+                           kp2_disp=n(kp2_disp).reshape(-1) if kp2_disp is not None else z(K),
+                           uv_cov=n(uv_cov) if uv_cov is not None else z((K, 3)),
+                           disp_cov=n(disp_cov).reshape(-1) if disp_cov is not None else z(K), fx=intr[0], fy=intr[1],
+                           cx=intr[2], cy=intr[3], baseline=intr[4], init_pose=n(init_pose).reshape(7), graph_type=graph_type,
+                           pc_obs=n(pc_obs), obs_cov=n(obs_cov), pts_cov=n(pts_cov))
+        return torch.tensor(np.asarray(opgo.lm_solve(g))), torch.zeros(8, dtype=torch.float64)
+    ops.pgo_solve_graph = pgo_solve_graph

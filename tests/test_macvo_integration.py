@@ -47,7 +47,7 @@ def config(b200):
         frontend=NS(type=t("FlowFormerCovFrontend"), args=fe_args),
         motion=NS(type="StaticMotionModel", args=NS()), outlier=NS(type=t("CovarianceSanityFilter"), args=NS()),
         postprocess=NS(type=t("MotionInterpolate"), args=(NS(device="cpu") if b200 else NS())), keyframe=NS(type="AllKeyframe", args=NS()),
-        optimizer=NS(type=t("TwoFrame_PGO"), args=NS(device="cpu", vectorize=True, parallel=False, graph_type="disp", autodiff=False))))
+        optimizer=NS(type=t("TwoFrame_PGO"), args=NS(device="cpu", vectorize=True, parallel=False, graph_type=sys.argv[2], autodiff=False))))
 
 def run(b200):
     cfg = config(b200)
@@ -78,7 +78,9 @@ print("MACVO-INTEGRATION-OK", got[1], got[2])
 
 
 @pytest.mark.skipif(not refharness.available(), reason="MAC-VO reference tree not present")
-def test_b200_plugins_under_the_real_macvo_run_pair(tmp_path):
-    r = subprocess.run([sys.executable, "-c", CODE, str(tmp_path / "w.pth")], capture_output=True, text=True, timeout=900,
+@pytest.mark.parametrize("graph_type", ["disp", "icp", "reproj"])
+def test_b200_plugins_under_the_real_macvo_run_pair(tmp_path, graph_type):
+    """`disp` is MACVO_Performant / Fast, `icp` Paper_Reproduce.yaml:108; each through the real GraphInput -> plugin adapter"""
+    r = subprocess.run([sys.executable, "-c", CODE, str(tmp_path / "w.pth"), graph_type], capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, TORCHDYNAMO_DISABLE="1"))
     assert "MACVO-INTEGRATION-OK" in r.stdout, r.stdout[-2500:] + r.stderr[-3500:]
