@@ -42,6 +42,27 @@ def test_host_only_queries(lib):
     assert lib.macvo_corr_workspace_bytes(2, 256, 4800, 1) == 4 * 2 * 4800 * 256 * 2
     assert lib.macvo_corr_workspace_bytes(2, 256, 4800, 2) == 2 * 2 * 4800 * 256 * 2
     assert lib.macvo_select_workspace_bytes(480, 640) >= 480 * 640
+    # padded pixel-row layouts of the decoder's tensor-core kernels (csrc/rows_layout.cuh): whole CTA pairs of 256 rows + guards
+    for b, h, w in ((1, 60, 80), (2, 60, 80), (2, 13, 17), (1, 90, 160)):
+        for vertical, padded in ((0, b * (h + 4) * (w + 4)), (1, b * w * (h + 4))):
+            rows = lib.macvo_rows_count(b, h, w, vertical)
+            assert rows == -(-padded // 256) * 256 + 32 and rows == lib.macvo_gru_tc_operand_rows(b, h, w, vertical)
+    assert lib.macvo_rows_count(0, 60, 80, 0) == 0
+
+
+def test_tensor_core_decoder_ops_refuse_bad_arguments(lib):
+    """argument validation of the decoder's tensor-core wrappers happens on the host, before any launch"""
+    import torch
+    from macvo_b200 import ops
+    with pytest.raises(ops.MacvoB200Error):
+        ops.conv_tc(torch.zeros(8, 64, dtype=torch.float16), torch.zeros(32, 64, dtype=torch.float16), None, 32, 1, False, (1, 2, 2))
+    with pytest.raises(ops.MacvoB200Error):
+        ops.softmax_rows_f16(torch.zeros(4, 8))
+    with pytest.raises(ops.MacvoB200Error):
+        ops.convex_upsample(torch.zeros(1, 2, 4, 4), torch.zeros(1, 576, 4, 4))
+    w, b, n = ops.pack_conv_filter(torch.arange(2 * 3 * 9, dtype=torch.float32).reshape(2, 3, 3, 3), torch.tensor([1.0, 2.0]))
+    assert tuple(w.shape) == (32, 9 * 64) and w.dtype == torch.float16 and n == 2 and tuple(b.shape) == (32,)
+    assert w[1, 4 * 64 + 2].item() == float(27 + 2 * 9 + 4) and not w[2:].any() and not w[:, 3:64].any()      # K index = tap * C_pad + c
 
 
 def test_sass_is_blackwell_native():
